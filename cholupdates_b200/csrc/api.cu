@@ -1,0 +1,245 @@
+// api.cu -- the C ABI declared in include/cholupdates_b200.h.
+//
+// Replaces the reference's inner kernels _seeger_impl_cython.update / .downdate
+// (src/cholupdates/rank_1/_seeger_impl_cython.pyx:22-155, :160-330) with sm_100a kernels.
+// No argument validation here (the reference kernels do none either, .pyx:30-31); the host
+// front-end (cholupdates_b200/rank_1/_seeger.py) reproduces the reference's checks.
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "dataflow.cuh"
+#include "large.cuh"
+#include "small.cuh"
+
+using namespace chub;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_path{0};
+
+int fail(cudaError_t e, const char *what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return (int)e;
+}
+#define CK(call)                                        \
+  do {                                                  \
+    cudaError_t e_ = (call);                            \
+    if (e_ != cudaSuccess) return fail(e_, #call);      \
+  } while (0)
+#define LAUNCHED()                                      \
+  do {                                                  \
+    g_launches.fetch_add(1, std::memory_order_relaxed); \
+    CK(cudaGetLastError());                             \
+  } while (0)
+
+// ---- internal per-device workspace (used when the caller passes workspace == NULL)
+struct DevCache {
+  void *ws = nullptr;
+  size_t ws_bytes = 0;
+};
+std::mutex g_mu;
+DevCache g_cache[64];
+
+int internal_ws(size_t need, void **out) {
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_mu);
+  DevCache &c = g_cache[dev & 63];
+  if (c.ws_bytes < need) {
+    if (c.ws) CK(cudaFree(c.ws));
+    c.ws = nullptr;
+    c.ws_bytes = 0;
+    CK(cudaMalloc(&c.ws, need));
+    c.ws_bytes = need;
+  }
+  *out = c.ws;
+  return 0;
+}
+
+template <typename T> constexpr int dtype_of() { return sizeof(T) == 8 ? CHUB_DTYPE_F64 : CHUB_DTYPE_F32; }
+
+// ---- single-CTA kernels (also the batched path)
+template <typename T, bool UPDATE>
+int launch_small(T *L, int64_t n, int64_t ld, int64_t stride_L, int layout, T *v, int64_t stride_v,
+                 int64_t batch, int flags, int32_t *status, cudaStream_t st) {
+  SmallArgs<T> a{L, v, status, (int)n, ld, stride_L, stride_v, flags};
+  const size_t smem = UPDATE ? small_update_smem<T>((int)n, layout) : small_downdate_smem<T>((int)n, layout);
+  auto go = [&](auto kern) -> int {
+    if (smem > 48 * 1024)
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)batch, kSmallNT, smem, st>>>(a);
+    LAUNCHED();
+    return 0;
+  };
+  if (UPDATE) {
+    if (layout == CHUB_ROW_MAJOR) return go(small_update_kernel<T, CHUB_ROW_MAJOR, kSmallNT>);
+    return go(small_update_kernel<T, CHUB_COL_MAJOR, kSmallNT>);
+  }
+  if (layout == CHUB_ROW_MAJOR) return go(small_downdate_kernel<T, CHUB_ROW_MAJOR, kSmallNT>);
+  return go(small_downdate_kernel<T, CHUB_COL_MAJOR, kSmallNT>);
+}
+
+// ---- launch-per-panel path
+template <typename T, int LAYOUT, bool UPDATE>
+int launch_panel(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs &ws, int32_t *status,
+                 cudaStream_t st) {
+  const int ni = (int)n;
+  large_prepare_kernel<T, LAYOUT><<<(ni + 255) / 256, 256, 0, st>>>(L, ni, ld, v, ws, flags, status);
+  LAUNCHED();
+  const int nb = (ni + 31) / 32;
+  large_invdiag_kernel<T, LAYOUT><<<(nb + 3) / 4, 128, 0, st>>>(L, ni, ld, ws, status);
+  LAUNCHED();
+  const int nJ = (ni + kBig - 1) / kBig;
+  for (int J = 0; J < nJ; ++J) {
+    large_chain_kernel<T, LAYOUT, UPDATE><<<1, kBig, 0, st>>>(L, ni, ld, v, ws, J, status);
+    LAUNCHED();
+    const int rbeg = J * kBig + (UPDATE ? 0 : kBig);
+    if (rbeg < ni) {
+      large_trail_kernel<T, LAYOUT, UPDATE><<<(ni - rbeg + 127) / 128, 128, 0, st>>>(L, ni, ld, ws, J, status);
+      LAUNCHED();
+    }
+  }
+  if (!UPDATE) {
+    large_dd_coef_kernel<T, LAYOUT><<<1, 1024, 0, st>>>(L, ni, ld, v, ws, status);
+    LAUNCHED();
+    large_dd_sweep_kernel<T, LAYOUT><<<(ni + 127) / 128, 128, 0, st>>>(L, ni, ld, ws, status);
+    LAUNCHED();
+  }
+  return 0;
+}
+
+constexpr int64_t kSmallCutoff = 512;  // n <= cutoff: one CTA does the whole factor
+
+template <typename T, bool UPDATE>
+int run_single(void *Lv, int64_t n, int64_t ld, int layout, void *vv, int flags, void *workspace,
+               size_t workspace_bytes, int32_t *status, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n < 0 || ld < n || (layout != CHUB_ROW_MAJOR && layout != CHUB_COL_MAJOR) || !status) {
+    snprintf(g_err, sizeof(g_err), "invalid argument (n=%lld ld=%lld layout=%d)", (long long)n,
+             (long long)ld, layout);
+    return (int)cudaErrorInvalidValue;
+  }
+  CK(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+  if (n == 0) return 0;
+  T *L = (T *)Lv;
+  T *v = (T *)vv;
+  int path = g_path.load();
+  if (path == 0) path = n <= kSmallCutoff ? 1 : 3;
+  if (path == 1 && n > kSmallMaxN) path = 2;
+  if (path == 3 && !dataflow_supported<T>(n, ld, layout, L)) path = 2;
+  if (path == 1) return launch_small<T, UPDATE>(L, n, ld, 0, layout, v, 0, 1, flags, status, st);
+
+  const size_t need = chub_workspace_bytes(dtype_of<T>(), n);
+  if (!workspace) {
+    int rc = internal_ws(need, &workspace);
+    if (rc) return rc;
+  } else if (workspace_bytes < need) {
+    snprintf(g_err, sizeof(g_err), "workspace too small: %zu < %zu", workspace_bytes, need);
+    return (int)cudaErrorInvalidValue;
+  }
+  LargeWs ws = large_ws_carve(workspace, n);
+  if (path == 3) {
+    int64_t nl = 0;
+    int rc = layout == CHUB_ROW_MAJOR
+                 ? launch_dataflow<T, CHUB_ROW_MAJOR, UPDATE>(L, n, ld, v, flags, ws, status, st, &nl)
+                 : launch_dataflow<T, CHUB_COL_MAJOR, UPDATE>(L, n, ld, v, flags, ws, status, st, &nl);
+    g_launches.fetch_add(nl, std::memory_order_relaxed);
+    if (rc) return fail((cudaError_t)rc, "dataflow launch");
+    return 0;
+  }
+  return layout == CHUB_ROW_MAJOR
+             ? launch_panel<T, CHUB_ROW_MAJOR, UPDATE>(L, n, ld, v, flags, ws, status, st)
+             : launch_panel<T, CHUB_COL_MAJOR, UPDATE>(L, n, ld, v, flags, ws, status, st);
+}
+
+template <typename T, bool UPDATE>
+int run_batched(void *Lv, int64_t n, int64_t ld, int64_t stride_L, int layout, void *vv,
+                int64_t stride_v, int64_t batch, int flags, int32_t *status, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n < 0 || ld < n || batch < 0 || !status ||
+      (layout != CHUB_ROW_MAJOR && layout != CHUB_COL_MAJOR)) {
+    snprintf(g_err, sizeof(g_err), "invalid argument");
+    return (int)cudaErrorInvalidValue;
+  }
+  if (batch == 0) return 0;
+  CK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)batch, st));
+  if (n == 0) return 0;
+  if (n <= kSmallMaxN)
+    return launch_small<T, UPDATE>((T *)Lv, n, ld, stride_L, layout, (T *)vv, stride_v, batch, flags,
+                                   status, st);
+  // very large factors in a batch: one after the other through the single-factor path
+  for (int64_t b = 0; b < batch; ++b) {
+    int rc = run_single<T, UPDATE>((T *)Lv + b * stride_L, n, ld, layout, (T *)vv + b * stride_v,
+                                   flags, nullptr, 0, status + b, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int chub_version(void) { return 100; }
+const char *chub_last_error(void) { return g_err; }
+
+int chub_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int chub_device_info(int *sm_count, int64_t *l2_bytes, int *cc_major, int *cc_minor) {
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (l2_bytes) *l2_bytes = p.l2CacheSize;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return 0;
+}
+
+size_t chub_workspace_bytes(int dtype, int64_t n) {
+  (void)dtype;
+  if (n < 0) n = 0;
+  return large_ws_doubles(n) * sizeof(double) + dataflow_flag_bytes(n);
+}
+
+int chub_set_path(int path) { return g_path.exchange(path); }
+int64_t chub_launch_count(int reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+#define DEFINE_SINGLE(NAME, T, UPD)                                                              \
+  int NAME(void *L, int64_t n, int64_t ld, int layout, void *v, int flags, void *workspace,      \
+           size_t workspace_bytes, int32_t *status, void *stream) {                              \
+    return run_single<T, UPD>(L, n, ld, layout, v, flags, workspace, workspace_bytes, status,    \
+                              stream);                                                           \
+  }
+DEFINE_SINGLE(chub_update_f64, double, true)
+DEFINE_SINGLE(chub_update_f32, float, true)
+DEFINE_SINGLE(chub_downdate_f64, double, false)
+DEFINE_SINGLE(chub_downdate_f32, float, false)
+
+#define DEFINE_BATCHED(NAME, T, UPD)                                                             \
+  int NAME(void *L, int64_t n, int64_t ld, int64_t stride_L, int layout, void *v,                \
+           int64_t stride_v, int64_t batch, int flags, int32_t *status, void *stream) {          \
+    return run_batched<T, UPD>(L, n, ld, stride_L, layout, v, stride_v, batch, flags, status,    \
+                               stream);                                                          \
+  }
+DEFINE_BATCHED(chub_update_batched_f64, double, true)
+DEFINE_BATCHED(chub_update_batched_f32, float, true)
+DEFINE_BATCHED(chub_downdate_batched_f64, double, false)
+DEFINE_BATCHED(chub_downdate_batched_f32, float, false)
+
+}  // extern "C"

@@ -1,0 +1,388 @@
+// large.cuh -- multi-CTA kernels for one large factor ("panel path").
+//
+// Algorithm (Gill-Golub-Murray-Saunders closed form of the
+// Seeger / LINPACK dchud rotations).  With p = L^{-1} v, t_0 = 1, t_{k+1} = t_k + p_k^2
+// and the running forward-substitution residual  w_i^{(k)} = v_i - sum_{m<k} L_im p_m :
+//
+//     c_k      = sgn_k sqrt(t_k / t_{k+1})            (sgn_k = sign of the input L_kk)
+//     sigma_k  = sgn_k p_k / sqrt(t_k t_{k+1})
+//     L'_ik    = c_k L_ik + sigma_k w_i^{(k)}          (i > k)   == c_k L_ik + s_k nu_i
+//     L'_kk    = |L_kk| sqrt(t_{k+1} / t_k)                      == hypot(L_kk, nu_k)
+//     w_i^{(k+1)} = w_i^{(k)} - L_ik p_k
+//
+// which is algebraically the reference's loop (_seeger_impl_cython.pyx:92-155:
+// rotg on (L_kk, v_k), rot on (L[k+1:,k], v[k+1:])) with nu_i^{(k)} = S_k w_i^{(k)} / sqrt(t_k),
+// S_k = prod_{m<k} sgn_m.  The only sequential part is the blocked forward substitution
+// for p (the "chain"): per 32-column block one 32x32 mat-vec with the pre-inverted diagonal
+// block, no sqrt / div on the chain.  Everything else is row-independent.
+//
+// The downdate (.pyx:160-330) reuses the same chain for p = L^{-1} v (read-only pass),
+// then rho^2 = 1 - p.p, q_k^2 = rho^2 + sum_{j>=k} p_j^2, c_k = q_{k+1}/q_k, s_k = p_k/q_k and
+// the row-independent reverse sweep of appendix A.3.
+//
+// This file is the launch-per-panel version: no inter-CTA waiting, works for every n and
+// both layouts.  The persistent dataflow kernel (dataflow.cuh) reuses its pieces.
+#pragma once
+
+#include "common.cuh"
+
+namespace chub {
+
+constexpr int kBig = 256;  // columns per chain-kernel launch (8 blocks of 32)
+
+struct LargeWs {
+  double *X;      // [nb][32*32] inverse of each 32x32 diagonal block (row-major, identity padded)
+  double *w;      // [n_pad]  forward-substitution residual, initialised to v
+  double *p;      // [n_pad]  p = L^{-1} v
+  double *c;      // [n_pad]  c_k (sign folded)
+  double *sg;     // [n_pad]  update: sigma_k (sign folded); downdate: s_k
+  double *dn;     // [n_pad]  update: new diagonal L'_kk;     downdate: sign of the input diagonal
+  double *scal;   // [8]      0: t (running), 1: S (running sign), 2: p.p, 3: rho^2
+  int32_t *flags; // [..]     dataflow-kernel flags (unused here)
+};
+
+inline size_t large_ws_doubles(int64_t n) {
+  int64_t n_pad = (n + 31) & ~31LL;
+  int64_t nb = n_pad / 32;
+  return (size_t)(nb * 1024 + 5 * n_pad + 8);
+}
+
+inline LargeWs large_ws_carve(void *base, int64_t n) {
+  int64_t n_pad = (n + 31) & ~31LL;
+  int64_t nb = n_pad / 32;
+  LargeWs ws;
+  double *d = reinterpret_cast<double *>(base);
+  ws.X = d; d += nb * 1024;
+  ws.w = d; d += n_pad;
+  ws.p = d; d += n_pad;
+  ws.c = d; d += n_pad;
+  ws.sg = d; d += n_pad;
+  ws.dn = d; d += n_pad;
+  ws.scal = d; d += 8;
+  ws.flags = reinterpret_cast<int32_t *>(d);
+  return ws;
+}
+
+// ---------------------------------------------------------------- prepare
+// check_diag (_arg_validation.py:18-22), w <- v, t <- 1, S <- 1.
+template <typename T, int LAYOUT>
+__global__ void large_prepare_kernel(const T *L, int n, int64_t ld, const T *v, LargeWs ws,
+                                     int flags, int32_t *status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    ws.w[i] = (double)v[i];
+    if ((flags & CHUB_FLAG_CHECK_DIAG) && L[idx<LAYOUT>(i, i, ld)] == T(0))
+      atomicMax(status, CHUB_STATUS_ZERO_DIAG);
+  }
+  if (i == 0) {
+    ws.scal[0] = 1.0; ws.scal[1] = 1.0; ws.scal[2] = 0.0; ws.scal[3] = 0.0;
+  }
+}
+
+// --------------------------------------------------------- diagonal inverses
+// One warp per 32x32 diagonal block: X = inv(L_D) (lower triangular), lane j computes column j
+// by forward substitution.  Blocks that stick out of the matrix are padded with the identity.
+template <typename T, int LAYOUT>
+__global__ void __launch_bounds__(128) large_invdiag_kernel(const T *L, int n, int64_t ld,
+                                                             LargeWs ws, const int32_t *status) {
+  __shared__ double Ls[4][kPanel][kPanel + 1];
+  if (*status != 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int blk = blockIdx.x * 4 + warp;
+  const int nb = (n + 31) / 32;
+  if (blk >= nb) return;
+  const int c0 = blk * kPanel;
+  // stage the block (lane = column for row-major reads, lane = row for column-major reads)
+  for (int r = 0; r < kPanel; ++r) {
+    int i, j;
+    if (LAYOUT == CHUB_ROW_MAJOR) { i = r; j = lane; } else { i = lane; j = r; }
+    double x = (i == j) ? 1.0 : 0.0;
+    if (c0 + i < n && c0 + j < n && j <= i) x = (double)L[idx<LAYOUT>(c0 + i, c0 + j, ld)];
+    Ls[warp][i][j] = x;
+  }
+  __syncwarp();
+  double x[kPanel];
+  const int j = lane;
+#pragma unroll
+  for (int i = 0; i < kPanel; ++i) {
+    double acc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int m = 0; m < kPanel; ++m)
+      if (m < i) acc -= (m >= j ? Ls[warp][i][m] * x[m] : 0.0);
+    x[i] = (i >= j) ? acc / Ls[warp][i][i] : 0.0;
+  }
+  double *X = ws.X + (int64_t)blk * 1024;
+#pragma unroll
+  for (int i = 0; i < kPanel; ++i) X[i * kPanel + j] = x[i];
+}
+
+// ------------------------------------------------------------------ chain
+// One CTA, 256 threads, one launch per 256 columns.  Thread a <-> row J*256 + a.
+// For each of the 8 diagonal blocks: p_blk = X_blk w_blk (mat-vec, 8 threads per row), then the
+// remaining rows of the 256-row block subtract L[:, blk] p_blk from their w (kept in a register).
+// UPDATE: afterwards the Seeger coefficients of the 256 columns are formed from a prefix sum of
+// p^2 and written to the workspace; v[k] <- rotg's z_k.
+template <typename T, int LAYOUT, bool UPDATE>
+__global__ void __launch_bounds__(kBig) large_chain_kernel(const T *L, int n, int64_t ld, T *v,
+                                                           LargeWs ws, int J,
+                                                           const int32_t *status) {
+  __shared__ double wsm[kPanel];
+  __shared__ double pall[kBig];
+  __shared__ double wtot[kBig / 32];
+  __shared__ int ntot[kBig / 32];
+  if (*status != 0) return;
+  const int a = threadIdx.x, lane = a & 31, warp = a >> 5;
+  const int base = J * kBig;
+  const int R = base + a;
+  const bool valid = R < n;
+  double wv = valid ? ws.w[R] : 0.0;
+  pall[a] = 0.0;
+  const int rr = a >> 3, part = a & 7;  // mat-vec role: row rr of the block, columns 4*part..+3
+  for (int s = 0; s < kBig / kPanel; ++s) {
+    const int c0 = base + s * kPanel;
+    if (c0 >= n) break;  // uniform
+    const double *X = ws.X + (int64_t)(c0 / kPanel) * 1024 + rr * kPanel + part * 4;
+    const double x0 = X[0], x1 = X[1], x2 = X[2], x3 = X[3];
+    // prefetch this thread's 32 entries of L[R][c0 .. c0+31] (needed only by rows below the block)
+    const bool below = valid && R >= c0 + kPanel;
+    double lrow[kPanel];
+#pragma unroll
+    for (int k = 0; k < kPanel; ++k)
+      lrow[k] = below ? (double)L[idx<LAYOUT>(R, c0 + k, ld)] : 0.0;
+    if (warp == s) wsm[lane] = wv;
+    __syncthreads();
+    double acc = x0 * wsm[part * 4] + x1 * wsm[part * 4 + 1] + x2 * wsm[part * 4 + 2] +
+                 x3 * wsm[part * 4 + 3];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (part == 0) pall[s * kPanel + rr] = acc;
+    __syncthreads();
+    if (below) {
+      const double *pp = pall + s * kPanel;
+      double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < kPanel; k += 2) {
+        d0 += lrow[k] * pp[k];
+        d1 += lrow[k + 1] * pp[k + 1];
+      }
+      wv -= d0 + d1;
+    }
+  }
+  __syncthreads();
+  const double pk = pall[a];
+  if (valid) ws.p[R] = pk;
+  if (!UPDATE) return;
+
+  // ---- coefficients of column k = R (block scan of p^2 and of the diagonal signs)
+  const double lkk = valid ? (double)L[idx<LAYOUT>(R, R, ld)] : 1.0;
+  const int neg = lkk < 0.0 ? 1 : 0;
+  double incl = pk * pk;
+  int nincl = neg;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double y = __shfl_up_sync(0xffffffffu, incl, o);
+    int m = __shfl_up_sync(0xffffffffu, nincl, o);
+    if (lane >= o) { incl += y; nincl += m; }
+  }
+  if (lane == 31) { wtot[warp] = incl; ntot[warp] = nincl; }
+  __syncthreads();
+  double off = ws.scal[0];
+  int noff = 0;
+  for (int q = 0; q < warp; ++q) { off += wtot[q]; noff += ntot[q]; }
+  const double tk1 = off + incl, tk = tk1 - pk * pk > off ? off + (incl - pk * pk) : off;
+  const double S_in = ws.scal[1];
+  const double Sk = ((noff + nincl - neg) & 1) ? -S_in : S_in;  // prod of signs of columns < k
+  const double sgn = neg ? -1.0 : 1.0;
+  const double rinv = 1.0 / sqrt(tk * tk1);
+  const double ck = sgn * tk * rinv;
+  const double sigk = sgn * pk * rinv;
+  if (valid) {
+    ws.c[R] = ck;
+    ws.sg[R] = sigk;
+    ws.dn[R] = fabs(lkk) * tk1 * rinv;
+    // rotg's z from (a, b) = (L_kk, nu_k), nu_k = S_k L_kk p_k / sqrt(t_k), s_k = S_k sgn_k p_k / sqrt(t_{k+1})
+    const double nuk = Sk * lkk * pk / sqrt(tk);
+    const double sk = Sk * sgn * pk / sqrt(tk1);
+    v[R] = (T)rotg_z<double>(lkk, nuk, ck, sk);
+  }
+  __syncthreads();
+  if (a == kBig - 1) {
+    ws.scal[0] = tk1;
+    ws.scal[1] = ((noff + nincl) & 1) ? -S_in : S_in;
+  }
+}
+
+// ------------------------------------------------------------- trailing rows
+// Rows R >= J*256, columns [J*256, min(n, J*256+256)) and below/at the diagonal:
+//   UPDATE:  L_Rk <- c_k L_Rk + sigma_k w ; w <- w - L_Rk(old) p_k ; L_RR <- dn_R
+//   !UPDATE: w <- w - L_Rk p_k            (read-only pass of the downdate's trsv)
+// Thread = row.  Row-major factors go through a swizzled shared tile (coalesced global access);
+// column-major factors are read directly (lanes = consecutive rows).
+template <typename T, int LAYOUT, bool UPDATE>
+__global__ void __launch_bounds__(128) large_trail_kernel(T *L, int n, int64_t ld, LargeWs ws,
+                                                          int J, const int32_t *status) {
+  constexpr int NT = 128;
+  __shared__ double cs[3][kPanel];
+  __shared__ __align__(16) T tile[LAYOUT == CHUB_ROW_MAJOR ? NT * kPanel : 1];
+  if (*status != 0) return;
+  const int tid = threadIdx.x;
+  const int base = J * kBig;
+  const int r0 = base + (UPDATE ? 0 : kBig) + blockIdx.x * NT;  // trsv pass: rows below the block only
+  if (r0 >= n) return;
+  const int rows = min(NT, n - r0);
+  const int R = r0 + tid;
+  const bool valid = tid < rows;
+  double w = valid ? ws.w[R] : 0.0;
+  const int cend = min(n, base + kBig);
+  for (int c0 = base; c0 < cend; c0 += kPanel) {
+    const int bw = min(kPanel, n - c0);
+    if (c0 > r0 + rows - 1) break;  // the whole tile is above the diagonal (uniform)
+    __syncthreads();
+    if (tid < kPanel) {
+      cs[0][tid] = tid < bw ? ws.p[c0 + tid] : 0.0;
+      if (UPDATE) {
+        cs[1][tid] = tid < bw ? ws.c[c0 + tid] : 1.0;
+        cs[2][tid] = tid < bw ? ws.sg[c0 + tid] : 0.0;
+      }
+    }
+    if (LAYOUT == CHUB_ROW_MAJOR) {
+      tile_load_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
+      __syncthreads();
+      if (valid) {
+#pragma unroll 8
+        for (int k = 0; k < kPanel; ++k) {
+          if (k < bw && c0 + k < R) {
+            const int o = tile_off(tid, k);
+            const double lo = (double)tile[o];
+            if (UPDATE) tile[o] = (T)(cs[1][k] * lo + cs[2][k] * w);
+            w -= lo * cs[0][k];
+          }
+        }
+        if (UPDATE && R >= c0 && R < c0 + bw) tile[tile_off(tid, R - c0)] = (T)ws.dn[R];
+      }
+      if (UPDATE) {
+        __syncthreads();
+        tile_store_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
+      }
+    } else {
+      __syncthreads();
+      if (valid) {
+        T *q = L + R + (int64_t)c0 * ld;
+#pragma unroll 8
+        for (int k = 0; k < kPanel; ++k) {
+          if (k < bw && c0 + k < R) {
+            const double lo = (double)q[(int64_t)k * ld];
+            if (UPDATE) q[(int64_t)k * ld] = (T)(cs[1][k] * lo + cs[2][k] * w);
+            w -= lo * cs[0][k];
+          }
+        }
+        if (UPDATE && R >= c0 && R < c0 + bw) q[(int64_t)(R - c0) * ld] = (T)ws.dn[R];
+      }
+    }
+  }
+  if (valid && R >= cend) ws.w[R] = w;
+}
+
+// ------------------------------------------------------- downdate coefficients
+// One CTA of 1024 threads: rho^2 = 1 - p.p (.pyx:253-259), suffix sums, (c_k, s_k), sign of the
+// input diagonal, v <- rotg's z_k (or v <- p when the result is not positive definite).
+template <typename T, int LAYOUT>
+__global__ void __launch_bounds__(1024) large_dd_coef_kernel(const T *L, int n, int64_t ld, T *v,
+                                                             LargeWs ws, int32_t *status) {
+  constexpr int NT = 1024;
+  __shared__ double red[NT];
+  if (*status != 0) return;
+  const int tid = threadIdx.x;
+  const int ch = (n + NT - 1) / NT;
+  const int b0 = min(n, tid * ch), b1 = min(n, b0 + ch);
+  double acc = 0.0;
+  for (int i = b0; i < b1; ++i) acc += ws.p[i] * ws.p[i];
+  red[tid] = acc;
+  __syncthreads();
+  double p_dot_p = 0.0, above = 0.0;
+  for (int t = 0; t < NT; ++t) {
+    p_dot_p += red[t];
+    if (t > tid) above += red[t];
+  }
+  const T rho_sq_t = T(1) - T(p_dot_p);
+  if (tid == 0) { ws.scal[2] = p_dot_p; ws.scal[3] = (double)rho_sq_t; }
+  if (rho_sq_t <= T(0)) {
+    for (int i = b0; i < b1; ++i) v[i] = (T)ws.p[i];
+    if (tid == 0) *status = CHUB_STATUS_NOT_PD;
+    return;
+  }
+  const double rho_sq = (double)rho_sq_t;
+  double run = above;  // sum_{j >= b1} p_j^2
+  for (int k = b1 - 1; k >= b0; --k) {
+    const double pk = ws.p[k];
+    const double qk1 = sqrt(rho_sq + run);
+    run += pk * pk;
+    const double qk = sqrt(rho_sq + run);
+    const double c = qk1 / qk, s = pk / qk;
+    ws.c[k] = c;
+    ws.sg[k] = s;
+    ws.dn[k] = L[idx<LAYOUT>(k, k, ld)] < T(0) ? -1.0 : 1.0;
+    v[k] = rotg_z<T>(T(qk1), T(pk), T(c), T(s));
+  }
+}
+
+// ------------------------------------------------------------- downdate sweep
+// Row-independent reverse sweep (appendix A.3; .pyx:285-330).  Thread = row; each CTA owns 128
+// rows and walks its 32-column tiles from the diagonal to column 0 with x_i in a register.
+template <typename T, int LAYOUT>
+__global__ void __launch_bounds__(128) large_dd_sweep_kernel(T *L, int n, int64_t ld, LargeWs ws,
+                                                             const int32_t *status) {
+  constexpr int NT = 128;
+  __shared__ double cs[3][kPanel];
+  __shared__ __align__(16) T tile[LAYOUT == CHUB_ROW_MAJOR ? NT * kPanel : 1];
+  if (*status != 0) return;
+  const int tid = threadIdx.x;
+  const int nblk = (n + NT - 1) / NT;
+  const int r0 = (nblk - 1 - blockIdx.x) * NT;  // longest rows first
+  const int rows = min(NT, n - r0);
+  const int R = r0 + tid;
+  const bool valid = tid < rows;
+  double x = 0.0;
+  for (int c0 = ((r0 + rows - 1) / kPanel) * kPanel; c0 >= 0; c0 -= kPanel) {
+    const int bw = min(kPanel, n - c0);
+    __syncthreads();
+    if (tid < kPanel) {
+      cs[0][tid] = tid < bw ? ws.c[c0 + tid] : 1.0;
+      cs[1][tid] = tid < bw ? ws.sg[c0 + tid] : 0.0;
+      cs[2][tid] = tid < bw ? ws.dn[c0 + tid] : 1.0;
+    }
+    if (LAYOUT == CHUB_ROW_MAJOR) {
+      tile_load_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
+      __syncthreads();
+      if (valid) {
+#pragma unroll 8
+        for (int kk = kPanel - 1; kk >= 0; --kk) {
+          if (kk < bw && c0 + kk <= R) {
+            const int o = tile_off(tid, kk);
+            const double lo = (double)tile[o], c = cs[0][kk], s = cs[1][kk];
+            tile[o] = (T)(cs[2][kk] * (c * lo - s * x));
+            x = c * x + s * lo;
+          }
+        }
+      }
+      __syncthreads();
+      tile_store_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
+    } else {
+      __syncthreads();
+      if (valid) {
+        T *q = L + R + (int64_t)c0 * ld;
+#pragma unroll 8
+        for (int kk = kPanel - 1; kk >= 0; --kk) {
+          if (kk < bw && c0 + kk <= R) {
+            const double lo = (double)q[(int64_t)kk * ld], c = cs[0][kk], s = cs[1][kk];
+            q[(int64_t)kk * ld] = (T)(cs[2][kk] * (c * lo - s * x));
+            x = c * x + s * lo;
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace chub

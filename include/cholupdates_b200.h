@@ -1,0 +1,135 @@
+/*
+ * cholupdates_b200.h -- C ABI of the B200 (sm_100a) rank-1 Seeger Cholesky
+ * update / downdate.
+ *
+ * This is the drop-in boundary for ONE hot path of marvinpfoertner/cholupdates:
+ * the inner kernels
+ *
+ *     cpdef void update  (blas_dtype[:, :] L, blas_dtype[::1] v) except *
+ *         src/cholupdates/rank_1/_seeger_impl_cython.pyx:22-155
+ *     cpdef void downdate(blas_dtype[:, :] L, blas_dtype[::1] v) except *
+ *         src/cholupdates/rank_1/_seeger_impl_cython.pyx:160-330
+ *
+ * (fused type blas_dtype in {float, double}, src/cholupdates/_blas_polymorphic.pxd:8-12)
+ * which the reference front-end selects as `_update_impl_default` /
+ * `_downdate_impl_default` (src/cholupdates/rank_1/_seeger.py:17-34) and calls at
+ * _seeger.py:279-294 / :715-730.  Like those kernels, the entry points below
+ * mutate L and v in place and do NO argument validation (shape / dtype /
+ * contiguity checks stay in the host front-end, exactly as in the reference,
+ * _seeger.py:241-269 + _arg_validation.py:6-30).
+ *
+ * Conventions
+ * -----------
+ *  - Plain C: pointers and sizes only, no CUDA or torch types.  `stream` is a
+ *    cudaStream_t passed as void* (NULL = the legacy default stream).
+ *  - All functions return 0 on success or a cudaError_t-style non-zero code
+ *    (see chub_last_error()).  Numerical outcomes are reported through
+ *    `status`, not through the return value.
+ *  - L is an n x n matrix with leading dimension `ld` (elements), element
+ *    (i, j) at L[i*ld + j] (CHUB_ROW_MAJOR, NumPy "C") or L[i + j*ld]
+ *    (CHUB_COL_MAJOR, NumPy "F").  Only i >= j is ever read or written
+ *    (reference contract, tests/cholupdates/rank_1/update/test_update.py:25-55).
+ *  - v has n contiguous elements.  On return it holds scratch: v[k] = the BLAS
+ *    rotg reconstruction parameter z_k, which is what the reference's Cython
+ *    path leaves there (.pyx:101,152 / :288).  After a CHUB_STATUS_NOT_PD
+ *    downdate it holds p = L^{-1} v (.pyx:239-259) and L is untouched.
+ *  - status codes (int32, written by the device):
+ *        CHUB_STATUS_OK         0
+ *        CHUB_STATUS_ZERO_DIAG  1   `check_diag` found L[k][k] == 0
+ *                                   (_arg_validation.py:18-22); L and v untouched
+ *        CHUB_STATUS_NOT_PD     2   downdate: rho^2 = 1 - p.p <= 0 (.pyx:255-259);
+ *                                   L untouched
+ *        CHUB_STATUS_INTERNAL   3   a device-side watchdog fired (never expected)
+ */
+#ifndef CHOLUPDATES_B200_H
+#define CHOLUPDATES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHUB_ROW_MAJOR 0
+#define CHUB_COL_MAJOR 1
+
+#define CHUB_FLAG_CHECK_DIAG 1 /* reference kwarg check_diag (_seeger.py:40) */
+
+#define CHUB_STATUS_OK 0
+#define CHUB_STATUS_ZERO_DIAG 1
+#define CHUB_STATUS_NOT_PD 2
+#define CHUB_STATUS_INTERNAL 3
+
+#define CHUB_DTYPE_F32 0
+#define CHUB_DTYPE_F64 1
+
+/* Library / device information. */
+int chub_version(void);
+const char *chub_last_error(void);
+int chub_device_count(void);
+/* SM count and L2 size of the current device (used by bench.py for grid / flush sizing). */
+int chub_device_info(int *sm_count, int64_t *l2_bytes, int *cc_major, int *cc_minor);
+
+/* Bytes of device workspace the device-pointer entry points need for a factor of
+ * order n (per call, independent of batch).  Pass a buffer of at least this size,
+ * or workspace == NULL to let the library use an internal per-device buffer. */
+size_t chub_workspace_bytes(int dtype, int64_t n);
+
+/* ---- device-pointer entry points: L, v, workspace, status are DEVICE pointers;
+ *      asynchronous on `stream`.  `status` points to one int32.
+ *      Replace _seeger_impl_cython.update / .downdate (.pyx:22-155, :160-330). */
+int chub_update_f64(void *L, int64_t n, int64_t ld, int layout, void *v, int flags,
+                    void *workspace, size_t workspace_bytes, int32_t *status, void *stream);
+int chub_update_f32(void *L, int64_t n, int64_t ld, int layout, void *v, int flags,
+                    void *workspace, size_t workspace_bytes, int32_t *status, void *stream);
+int chub_downdate_f64(void *L, int64_t n, int64_t ld, int layout, void *v, int flags,
+                      void *workspace, size_t workspace_bytes, int32_t *status, void *stream);
+int chub_downdate_f32(void *L, int64_t n, int64_t ld, int layout, void *v, int flags,
+                      void *workspace, size_t workspace_bytes, int32_t *status, void *stream);
+
+/* ---- batched entry points: `batch` independent factors, factor b at
+ *      L + b*stride_L, v + b*stride_v (elements); status[batch], one code per
+ *      factor (a failing factor is left untouched, the others proceed).
+ *      New surface (the reference has no batched call; a 3-D L must keep raising
+ *      ValueError through update(), test_update.py:88-97). */
+int chub_update_batched_f64(void *L, int64_t n, int64_t ld, int64_t stride_L, int layout, void *v,
+                            int64_t stride_v, int64_t batch, int flags, int32_t *status,
+                            void *stream);
+int chub_update_batched_f32(void *L, int64_t n, int64_t ld, int64_t stride_L, int layout, void *v,
+                            int64_t stride_v, int64_t batch, int flags, int32_t *status,
+                            void *stream);
+int chub_downdate_batched_f64(void *L, int64_t n, int64_t ld, int64_t stride_L, int layout, void *v,
+                              int64_t stride_v, int64_t batch, int flags, int32_t *status,
+                              void *stream);
+int chub_downdate_batched_f32(void *L, int64_t n, int64_t ld, int64_t stride_L, int layout, void *v,
+                              int64_t stride_v, int64_t batch, int flags, int32_t *status,
+                              void *stream);
+
+/* ---- host-buffer entry points: L and v are HOST pointers (what the reference's
+ *      NumPy callers hold, _seeger.py:37-44).  Synchronous: the lower triangle is
+ *      staged to the current device in row blocks, updated and copied back (the
+ *      strict upper triangle of the host array is never read or written);
+ *      *status is a host int32.  The downdate copies L back only if status == 0. */
+int chub_update_host_f64(void *L, int64_t n, int64_t ld, int layout, void *v, int flags,
+                         int32_t *status);
+int chub_update_host_f32(void *L, int64_t n, int64_t ld, int layout, void *v, int flags,
+                         int32_t *status);
+int chub_downdate_host_f64(void *L, int64_t n, int64_t ld, int layout, void *v, int flags,
+                           int32_t *status);
+int chub_downdate_host_f32(void *L, int64_t n, int64_t ld, int layout, void *v, int flags,
+                           int32_t *status);
+/* Release the staging buffers the host entry points cache on the current device. */
+int chub_host_release(void);
+
+/* ---- tuning / introspection (bench.py and tests) */
+/* Force a kernel path: 0 = automatic, 1 = single-CTA kernels only, 2 = panel
+ * (multi-kernel) path, 3 = persistent dataflow kernel.  Returns the previous value. */
+int chub_set_path(int path);
+/* Number of kernels launched by this library since the counter was last reset. */
+int64_t chub_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHOLUPDATES_B200_H */

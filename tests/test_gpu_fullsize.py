@@ -1,0 +1,81 @@
+"""Full-size checks at BASELINE.json's configuration 2 / 3 (n = 16384, fp64) on the GPU.
+
+The oracle (compiled C, column-major fast path) finishes n = 16384 in a fraction of a second, so
+the comparison is direct; in addition a size-independent property is checked:
+(L' L'^T) x = L (L^T x) +/- v (v^T x) for random x, which needs only mat-vecs.
+"""
+
+import numpy as np
+import pytest
+
+import seeger_oracle as oracle
+from helpers import downdate_vector, rel_fro, synth_factor, tol_for
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+import cholupdates_b200  # noqa: E402
+
+rank_1 = cholupdates_b200.rank_1
+N = 16384
+
+
+@pytest.fixture(scope="module")
+def big():
+    L = synth_factor(N, 0)
+    v = np.random.default_rng(1).standard_normal(N)
+    return L, v
+
+
+def _to_cuda(L, order):
+    if order == "C":
+        return torch.from_numpy(L).cuda()
+    return torch.from_numpy(np.ascontiguousarray(L.T)).cuda().t()
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_update_16384(big, order):
+    L, v = big
+    L_ref, v_ref = np.array(L, order="F"), v.copy()
+    oracle.update(L_ref, v_ref)
+    Lt = _to_cuda(L, order)
+    Lt = Lt + torch.triu(torch.full_like(Lt, float("nan")), 1)  # NaN above the diagonal
+    vt = torch.from_numpy(v.copy()).cuda()
+    out = rank_1.update(Lt, vt, check_diag=False, overwrite_L=True, overwrite_v=True)
+    assert out is Lt
+    got = Lt.cpu().numpy()
+    assert np.all(np.isnan(got[np.triu_indices(N, 1)]))  # never touched
+    assert rel_fro(np.nan_to_num(got), L_ref) <= tol_for(np.float64, N)
+    assert np.linalg.norm(vt.cpu().numpy() - v_ref) <= 1e-9 * np.linalg.norm(v_ref)
+    # size-independent property
+    Lo = torch.tril(torch.nan_to_num(Lt))
+    x = torch.from_numpy(np.random.default_rng(3).standard_normal(N)).cuda()
+    Lold = torch.from_numpy(np.tril(L)).cuda()
+    vv = torch.from_numpy(v).cuda()
+    lhs = Lo @ (Lo.T @ x)
+    rhs = Lold @ (Lold.T @ x) + vv * (vv @ x)
+    assert float(torch.linalg.norm(lhs - rhs) / torch.linalg.norm(rhs)) <= 1e-11
+
+
+def test_downdate_16384_near_singular_and_error_paths(big):
+    L, _ = big
+    # (i) valid but near-singular: alpha^2 = 1 - 1e-6 (mirrors test_downdate.py:189-190)
+    v = downdate_vector(L, 2, norm_p=np.sqrt(1 - 1e-6))
+    L_ref, v_ref = np.array(L, order="F"), v.copy()
+    oracle.downdate(L_ref, v_ref)
+    Lt, vt = torch.from_numpy(L.copy()).cuda(), torch.from_numpy(v.copy()).cuda()
+    rank_1.downdate(Lt, vt, check_diag=True, overwrite_L=True, overwrite_v=True)
+    assert rel_fro(Lt.cpu().numpy(), L_ref) <= tol_for(np.float64, N)
+    # (ii) invalid: alpha = 1.2 and alpha^2 = 1 + 1e-6 -> LinAlgError, L bit-unchanged
+    for norm_p in (1.2, np.sqrt(1 + 1e-6)):
+        v = downdate_vector(L, 2, norm_p=norm_p)
+        Lt, vt = torch.from_numpy(L.copy()).cuda(), torch.from_numpy(v.copy()).cuda()
+        with pytest.raises(np.linalg.LinAlgError, match="not positive definite"):
+            rank_1.downdate(Lt, vt, overwrite_L=True, overwrite_v=True)
+        assert torch.equal(Lt.cpu(), torch.from_numpy(L))
+    # (iii) planted zero on the diagonal with check_diag=True
+    Lz = L.copy()
+    Lz[12345, 12345] = 0.0
+    Lt, vt = torch.from_numpy(Lz.copy()).cuda(), torch.from_numpy(v.copy()).cuda()
+    with pytest.raises(np.linalg.LinAlgError, match="zeros on its diagonal"):
+        rank_1.downdate(Lt, vt, overwrite_L=True, overwrite_v=True)
+    assert torch.equal(Lt.cpu(), torch.from_numpy(Lz))

@@ -1,0 +1,341 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the reference-shaped front-end)
+against the oracle on identical seeded inputs, against the committed golden vectors, and through
+the reference's own property tests (tests/cholupdates/rank_1/{update,downdate}/test_*.py).
+
+Tolerances are those of helpers.tol_for: relative Frobenius error over the lower triangle
+<= 1e-12 * sqrt(n) (fp64, the north-star bar) / 1e-5 * sqrt(n) (fp32).
+"""
+
+import numpy as np
+import pytest
+
+import seeger_oracle as oracle
+from helpers import downdate_vector, rel_fro, spd_factor, synth_factor, tol_for, unpack_tril
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+import cholupdates_b200  # noqa: E402
+from cholupdates_b200 import _lib  # noqa: E402
+
+rank_1 = cholupdates_b200.rank_1
+DTYPES = [np.float64, np.float32]
+
+
+def _oracle(op, L, v):
+    Lr, vr = np.array(L, order="F"), v.copy()
+    getattr(oracle, op)(Lr, vr)
+    return Lr, vr
+
+
+def _run(op, L, v, kind, **kw):
+    """kind: 'numpy' (host staging path) or 'torch' (device pointers)."""
+    fn = getattr(rank_1, op)
+    if kind == "numpy":
+        return fn(L, v, **kw)
+    Lt, vt = torch.from_numpy(np.ascontiguousarray(L)).cuda(), torch.from_numpy(v.copy()).cuda()
+    if L.flags.f_contiguous and not L.flags.c_contiguous:
+        Lt = torch.from_numpy(np.ascontiguousarray(L.T)).cuda().t()  # column-major CUDA tensor
+    out = fn(Lt, vt, **kw)
+    return out.cpu().numpy()
+
+
+# ------------------------------------------------- reference grid (N, dtype, order, seed)
+@pytest.mark.parametrize("N", [1, 2, 3, 5, 10, 100])
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("order", ["C", "F"])
+@pytest.mark.parametrize("kind", ["numpy", "torch"])
+def test_reference_grid_update(N, dtype, order, kind):
+    for seed in range(3):
+        A, L = spd_factor(N, seed, dtype)
+        v = np.random.default_rng(seed + 100).normal(scale=10, size=N).astype(dtype)
+        L_in = np.array(L, order=order)
+        L_ud = _run("update", L_in, v, kind)
+        L_ref, _ = _oracle("update", L, v)
+        assert rel_fro(L_ud, L_ref) <= tol_for(dtype, N)
+        # test_update.py:11-22  valid square root, positive diagonal
+        rtol = 1e-7 if dtype == np.float64 else 1e-4
+        Lt = np.tril(L_ud).astype(np.float64)
+        Aud = A.astype(np.float64) + np.outer(v, v).astype(np.float64)
+        assert np.linalg.norm(Lt @ Lt.T - Aud) <= 10 * rtol * np.linalg.norm(Aud)
+        assert np.all(np.diag(L_ud) > 0)
+        # test_update_seeger.py:9-19  memory order is kept
+        if kind == "numpy" and N > 1:
+            assert L_ud.flags.c_contiguous == L_in.flags.c_contiguous
+            assert L_ud.flags.f_contiguous == L_in.flags.f_contiguous
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 5, 10, 100])
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("order", ["C", "F"])
+@pytest.mark.parametrize("kind", ["numpy", "torch"])
+def test_reference_grid_downdate(N, dtype, order, kind):
+    for seed in range(3):
+        A, L = spd_factor(N, seed, dtype)
+        v = downdate_vector(L, seed + 200)
+        L_dd = _run("downdate", np.array(L, order=order), v, kind)
+        L_ref, _ = _oracle("downdate", L, v)
+        assert rel_fro(L_dd, L_ref) <= tol_for(dtype, N) * (1 if dtype == np.float64 else 30)
+        rtol = 1e-7 if dtype == np.float64 else 3e-2
+        Lt = np.tril(L_dd).astype(np.float64)
+        Add = A.astype(np.float64) - np.outer(v, v).astype(np.float64)
+        assert np.linalg.norm(Lt @ Lt.T - Add) <= 10 * rtol * np.linalg.norm(Add)
+        assert np.all(np.diag(L_dd) > 0)
+
+
+# ------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("op", ["ud", "dd"])
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_matches_golden_vectors(golden, op, order):
+    seen = sorted({tuple(k.split("/")[:3]) for k in golden.files})
+    for tag, Ns, seeds in seen:
+        N, dtype = int(Ns[1:]), (np.float64 if tag == "f64" else np.float32)
+        pre = f"{tag}/{Ns}/{seeds}/"
+        L = unpack_tril(golden[pre + "L"], N, order)
+        v = golden[pre + f"v_{op}"].copy()
+        fn = rank_1.update if op == "ud" else rank_1.downdate
+        out = fn(L, v, overwrite_L=True, overwrite_v=True)
+        assert out is L
+        L_ref = unpack_tril(golden[pre + f"L_{op}_{order}"], N)
+        slack = 1 if dtype == np.float64 else 30
+        assert rel_fro(L, L_ref) <= tol_for(dtype, N) * slack, (tag, N, seeds)
+        assert np.all(np.triu(L, 1) == 0)
+        if dtype == np.float64:  # v on return: rotg's z_k, as the Cython path leaves it
+            v_ref = golden[pre + f"vout_{op}_{order}"]
+            err = np.linalg.norm(v - v_ref) / max(np.linalg.norm(v_ref), 1e-300)
+            assert err <= 1e-9, (tag, N, seeds, err)
+
+
+# ------------------------------------------------- sizes across kernel paths, both layouts
+SIZES = [31, 32, 33, 64, 100, 257, 511, 512, 513, 1000, 1025, 2049]
+
+
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("order", ["C", "F"])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_update_sizes(n, order, dtype):
+    L = synth_factor(n, n, dtype)
+    v = np.random.default_rng(n + 1).standard_normal(n).astype(dtype)
+    L_ref, v_ref = _oracle("update", L, v)
+    for kind in ("numpy", "torch"):
+        got = _run("update", np.array(L, order=order), v, kind)
+        assert rel_fro(got, L_ref) <= tol_for(dtype, n), (kind,)
+        np.testing.assert_array_equal(np.triu(got, 1), 0)
+    if dtype == np.float64:
+        vv = v.copy()
+        rank_1.update(np.array(L, order=order), vv, overwrite_v=True)
+        assert np.linalg.norm(vv - v_ref) <= 1e-9 * np.linalg.norm(v_ref)
+
+
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("order", ["C", "F"])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_downdate_sizes(n, order, dtype):
+    L = synth_factor(n, n, dtype)
+    v = downdate_vector(L, n + 2)
+    L_ref, v_ref = _oracle("downdate", L, v)
+    slack = 1 if dtype == np.float64 else 30
+    for kind in ("numpy", "torch"):
+        got = _run("downdate", np.array(L, order=order), v, kind)
+        assert rel_fro(got, L_ref) <= tol_for(dtype, n) * slack, (kind,)
+        np.testing.assert_array_equal(np.triu(got, 1), 0)
+    if dtype == np.float64:
+        vv = v.copy()
+        rank_1.downdate(np.array(L, order=order), vv, overwrite_v=True)
+        assert np.linalg.norm(vv - v_ref) <= 1e-9 * np.linalg.norm(v_ref)
+
+
+@pytest.mark.parametrize("path", [1, 2, 3])
+@pytest.mark.parametrize("n", [300, 777, 1536])
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_forced_kernel_paths_agree(path, n, order):
+    """1 = single-CTA kernels, 2 = launch-per-panel kernels, 3 = persistent dataflow kernel."""
+    lib = _lib.load()
+    L = synth_factor(n, 5)
+    v = np.random.default_rng(6).standard_normal(n)
+    vd = downdate_vector(L, 7)
+    prev = lib.chub_set_path(path)
+    try:
+        got_u = _run("update", np.array(L, order=order), v, "torch")
+        got_d = _run("downdate", np.array(L, order=order), vd, "torch")
+    finally:
+        lib.chub_set_path(prev)
+    assert rel_fro(got_u, _oracle("update", L, v)[0]) <= tol_for(np.float64, n)
+    assert rel_fro(got_d, _oracle("downdate", L, vd)[0]) <= tol_for(np.float64, n)
+
+
+# ------------------------------------------------------------ reference property tests
+@pytest.mark.parametrize("op", ["update", "downdate"])
+@pytest.mark.parametrize("n", [10, 100, 700])
+@pytest.mark.parametrize("order", ["C", "F"])
+@pytest.mark.parametrize("kind", ["numpy", "torch"])
+def test_upper_triangular_part_not_accessed(op, n, order, kind):
+    # test_update.py:25-55 / test_downdate.py:28-58: junk (here NaN and random) above the diagonal
+    L = synth_factor(n, 3)
+    v = np.random.default_rng(4).standard_normal(n) if op == "update" else downdate_vector(L, 4)
+    junk = np.triu(np.random.default_rng(5).standard_normal((n, n)), 1)
+    junk[0, n - 1:] = np.nan if n > 1 else 0.0
+    clean = _run(op, np.array(L, order=order), v, kind)
+    dirty = _run(op, np.array(L + junk, order=order), v, kind)
+    np.testing.assert_array_equal(np.triu(dirty, 1), junk)
+    np.testing.assert_array_equal(np.tril(dirty), np.tril(clean))
+
+
+@pytest.mark.parametrize("op", ["update", "downdate"])
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_no_input_mutation(op, order):
+    # test_update.py:58-85
+    n = 100
+    L = np.array(synth_factor(n, 8), order=order)
+    v = np.random.default_rng(9).standard_normal(n) if op == "update" else downdate_vector(L, 9)
+    fn = getattr(rank_1, op)
+    for ow_L, ow_v in ((False, False), (True, False), (False, True)):
+        Lc, vc = L.copy(order="K"), v.copy()
+        out = fn(Lc, vc, overwrite_L=ow_L, overwrite_v=ow_v)
+        if not ow_L:
+            np.testing.assert_array_equal(Lc, L)
+            assert out is not Lc
+        else:
+            assert out is Lc
+        if not ow_v:
+            np.testing.assert_array_equal(vc, v)
+    Lt, vt = torch.from_numpy(L.copy()).cuda(), torch.from_numpy(v.copy()).cuda()
+    out = fn(Lt, vt)
+    assert out is not Lt
+    np.testing.assert_array_equal(Lt.cpu().numpy(), np.ascontiguousarray(L))
+    np.testing.assert_array_equal(vt.cpu().numpy(), v)
+    out = getattr(rank_1, op + "_in_place")(Lt, vt)
+    assert out is Lt
+
+
+@pytest.mark.parametrize("kind", ["numpy", "torch"])
+def test_raise_on_zero_diagonal(kind):
+    # test_update.py:129-141 / test_downdate.py:136-152; L must stay untouched
+    for n in (5, 100, 700):
+        L = synth_factor(n, 1)
+        L[n // 2, n // 2] = 0.0
+        v = np.random.default_rng(2).standard_normal(n)
+        for op in ("update", "downdate"):
+            if kind == "numpy":
+                Lc, vc = L.copy(), v.copy()
+                with pytest.raises(np.linalg.LinAlgError):
+                    getattr(rank_1, op)(Lc, vc, overwrite_L=True, overwrite_v=True)
+                np.testing.assert_array_equal(Lc, L)
+            else:
+                Lt, vt = torch.from_numpy(L.copy()).cuda(), torch.from_numpy(v.copy()).cuda()
+                with pytest.raises(np.linalg.LinAlgError):
+                    getattr(rank_1, op)(Lt, vt, overwrite_L=True, overwrite_v=True)
+                np.testing.assert_array_equal(Lt.cpu().numpy(), L)
+                np.testing.assert_array_equal(vt.cpu().numpy(), v)
+
+
+@pytest.mark.parametrize("kind", ["numpy", "torch"])
+@pytest.mark.parametrize("n", [5, 100, 700, 1500])
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_raise_on_indefinite_result(kind, n, order):
+    # test_downdate.py:155-175: ||L^-1 v|| = 1.2 -> LinAlgError, L bit-unchanged, v <- p
+    L = np.array(synth_factor(n, 11), order=order)
+    v = downdate_vector(L, 12, norm_p=1.2)
+    if kind == "numpy":
+        Lc, vc = L.copy(order="K"), v.copy()
+        with pytest.raises(np.linalg.LinAlgError, match="not positive definite"):
+            rank_1.downdate(Lc, vc, overwrite_L=True, overwrite_v=True)
+        np.testing.assert_array_equal(Lc, L)
+        p = np.linalg.solve(np.tril(L), v)
+        np.testing.assert_allclose(vc, p, rtol=1e-8, atol=1e-10)
+    else:
+        Lt, vt = torch.from_numpy(np.ascontiguousarray(L)).cuda(), torch.from_numpy(v.copy()).cuda()
+        with pytest.raises(np.linalg.LinAlgError, match="not positive definite"):
+            rank_1.downdate(Lt, vt, overwrite_L=True, overwrite_v=True)
+        np.testing.assert_array_equal(Lt.cpu().numpy(), np.ascontiguousarray(L))
+
+
+@pytest.mark.parametrize("n", [100, 1200])
+def test_ill_conditioned_matrix(n):
+    # test_update.py:144-166 / test_downdate.py:178-202
+    g = np.random.default_rng(0)
+    spectrum = np.sort(1.0 + g.gamma(10.0, 1.0, size=n))
+    Q, _ = np.linalg.qr(g.standard_normal((n, n)))
+    A = (Q * spectrum) @ Q.T
+    A = 0.5 * (A + A.T)
+    L = np.linalg.cholesky(A)
+    v = Q[:, -1] * np.sqrt(spectrum[-1] * 99999.0)
+    L_ud = rank_1.update(L, v)
+    Aud = A + np.outer(v, v)
+    assert np.linalg.norm(np.tril(L_ud) @ np.tril(L_ud).T - Aud) <= 1e-7 * np.linalg.norm(Aud)
+    assert rel_fro(L_ud, _oracle("update", L, v)[0]) <= 1e-9
+    v = Q[:, 0] * np.sqrt(spectrum[0] * (1.0 - 1e-6))
+    L_dd = rank_1.downdate(L, v)
+    Add = A - np.outer(v, v)
+    assert np.linalg.norm(np.tril(L_dd) @ np.tril(L_dd).T - Add) <= 1e-7 * np.linalg.norm(Add)
+
+
+def test_negative_input_diagonal():
+    # the sign fix (.pyx:110-113, :319-326): a factor with negative diagonal entries is still a
+    # valid square root; the result has a positive diagonal and matches the oracle
+    for n in (40, 700):
+        L = synth_factor(n, 21)
+        flip = np.random.default_rng(22).random(n) < 0.3
+        L[:, flip] *= -1.0
+        v = np.random.default_rng(23).standard_normal(n)
+        got = rank_1.update(L, v)
+        assert np.all(np.diag(got) > 0)
+        assert rel_fro(got, _oracle("update", L, v)[0]) <= tol_for(np.float64, n)
+        vd = downdate_vector(L, 24)
+        got = rank_1.downdate(L, vd)
+        assert np.all(np.diag(got) > 0)
+        assert rel_fro(got, _oracle("downdate", L, vd)[0]) <= tol_for(np.float64, n)
+
+
+# ---------------------------------------------------------------------- batched
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("layout", ["C", "F"])
+def test_batched_matches_oracle_loop(dtype, layout):
+    B, n = 24, 256
+    Ls = np.stack([synth_factor(n, [0, b], dtype) for b in range(B)])
+    vs = np.stack([np.random.default_rng([1, b]).standard_normal(n).astype(dtype) for b in range(B)])
+    Lt = torch.from_numpy(Ls).cuda()
+    if layout == "F":
+        Lt = Lt.transpose(1, 2).contiguous().transpose(1, 2)
+    out = rank_1.update_batched(Lt, torch.from_numpy(vs).cuda())
+    got = out.cpu().numpy()
+    for b in range(B):
+        assert rel_fro(got[b], _oracle("update", Ls[b], vs[b])[0]) <= tol_for(dtype, n)
+    vd = np.stack([downdate_vector(Ls[b], [2, b]) for b in range(B)])
+    vd[3] = downdate_vector(Ls[3], 5, norm_p=1.2)  # one factor loses positive definiteness
+    Ls[7, 9, 9] = 0.0  # and one has a zero on its diagonal
+    Lt = torch.from_numpy(Ls).cuda()
+    out, status = rank_1.downdate_batched(Lt, torch.from_numpy(vd).cuda(), raise_on_error=False)
+    status = status.cpu().numpy()
+    assert status[3] == 2 and status[7] == 1 and np.count_nonzero(status) == 2
+    got = out.cpu().numpy()
+    np.testing.assert_array_equal(got[3], Ls[3])
+    np.testing.assert_array_equal(got[7], Ls[7])
+    slack = 1 if dtype == np.float64 else 30
+    for b in (0, 1, 23):
+        assert rel_fro(got[b], _oracle("downdate", Ls[b], vd[b])[0]) <= tol_for(dtype, n) * slack
+    with pytest.raises(np.linalg.LinAlgError):
+        rank_1.downdate_batched(Lt, torch.from_numpy(vd).cuda())
+
+
+# ------------------------------------------------------------------- larger sizes
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_update_n4096_matches_oracle(order):
+    n = 4096
+    L = synth_factor(n, 0)
+    v = np.random.default_rng(1).standard_normal(n)
+    L_ref, v_ref = _oracle("update", L, v)
+    got = _run("update", np.array(L, order=order), v, "torch")
+    assert rel_fro(got, L_ref) <= tol_for(np.float64, n)
+    got = _run("update", np.array(L, order=order), v, "numpy")
+    assert rel_fro(got, L_ref) <= tol_for(np.float64, n)
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_downdate_n4096_matches_oracle(order):
+    n = 4096
+    L = synth_factor(n, 0)
+    v = downdate_vector(L, 2, norm_p=np.sqrt(1 - 1e-6))  # valid but near-singular (config 3 (i))
+    L_ref, _ = _oracle("downdate", L, v)
+    got = _run("downdate", np.array(L, order=order), v, "torch")
+    assert rel_fro(got, L_ref) <= tol_for(np.float64, n)
