@@ -149,8 +149,10 @@ int run_single(void *Lv, int64_t n, int64_t ld, int layout, void *vv, int flags,
                  ? launch_dataflow<T, CHUB_ROW_MAJOR, UPDATE>(L, n, ld, v, flags, ws, status, st, &nl)
                  : launch_dataflow<T, CHUB_COL_MAJOR, UPDATE>(L, n, ld, v, flags, ws, status, st, &nl);
     g_launches.fetch_add(nl, std::memory_order_relaxed);
-    if (rc) return fail((cudaError_t)rc, "dataflow launch");
-    return 0;
+    if (rc == 0) return 0;
+    if (rc != (int)cudaErrorNotSupported && rc != (int)cudaErrorCooperativeLaunchTooLarge)
+      return fail((cudaError_t)rc, "dataflow launch");
+    cudaGetLastError();  // the cooperative launch was refused: use the launch-per-panel kernels
   }
   return layout == CHUB_ROW_MAJOR
              ? launch_panel<T, CHUB_ROW_MAJOR, UPDATE>(L, n, ld, v, flags, ws, status, st)
@@ -216,6 +218,22 @@ size_t chub_workspace_bytes(int dtype, int64_t n) {
 }
 
 int chub_set_path(int path) { return g_path.exchange(path); }
+
+// Debug: copy the dataflow kernel's cycle counters (CHUB_PROFILE=1) of the internal or given
+// workspace to the host: out[cta * 16 + slot].
+int chub_debug_profile(void *workspace, int64_t n, long long *out, int ctas) {
+  if (!workspace) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    workspace = g_cache[dev & 63].ws;
+    if (!workspace) return (int)cudaErrorInvalidValue;
+  }
+  LargeWs ws = large_ws_carve(workspace, n);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, reinterpret_cast<char *>(ws.flags) + 256, (size_t)ctas * 16 * sizeof(long long),
+                cudaMemcpyDeviceToHost));
+  return 0;
+}
 int64_t chub_launch_count(int reset) {
   return reset ? g_launches.exchange(0) : g_launches.load();
 }

@@ -1,25 +1,1220 @@
 // dataflow.cuh -- persistent single-launch dataflow kernel for one large factor.
-// (placeholder: filled in after the panel path is validated on the GPU)
+//
+// Same arithmetic as large.cuh (GGMS / blocked forward-substitution form of the Seeger update,
+// SURVEY appendix A.2), organised so that the lower triangle is streamed through the SMs exactly
+// once with the sequential chain overlapped:
+//
+//   * CTA 0 is the CHAIN.  It never writes L.  For block row r (32 rows) it needs
+//         w_r = wt_r - sum_{j=r-d}^{r-1} L[r, j] p_j ,      p_r = inv(L[r, r]) w_r
+//     where wt_r ("w-tilde") is the forward-substitution residual of those rows after all block
+//     columns j < r-d, handed over by the workers through global memory, and the last d block
+//     columns (the BAND) are applied by the chain itself from tiles it prefetched with bulk async
+//     copies (TMA engine, cp.async.bulk + mbarrier).  The critical path per 32 columns is two
+//     32x32 mat-vecs out of shared memory -- no sqrt/div, no inter-CTA round trip (a spare warp
+//     polls wt_{r+1} while the mat-vecs of block column r run).  p_r is published with plain
+//     8-byte stores; consumers spin on a NaN sentinel (LL-style: the data is its own flag).
+//   * CTAs 1..G-1 are WORKERS.  Rows are dealt to them in blocks of R rows, cyclically, so the
+//     shrinking triangle stays balanced.  One thread owns one row for the whole kernel and keeps
+//     its residual w_i in a register.  At step s a row processes one 32-column tile: block column
+//     s while it is still far left of the diagonal (s < b-d, b = the row's block row), nothing
+//     while the chain is inside its band, and block column s-d for s in [b, b+d].  The delay keeps
+//     the OLD band entries in memory until the chain has consumed them (the chain publishes p_b
+//     only after reading them; step s is gated on p_s).  Each row segment (32 elements) is one
+//     bulk async copy into a padded (bank-conflict-free) shared-memory row, prefetched kStages-2
+//     steps ahead; it is updated in place
+//         L_ik <- c_k L_ik + sigma_k w_i ;  w_i <- w_i - L_ik(old) p_k ;  L_ii <- dn_i
+//     and written back with one bulk async store.  Row warps are autonomous (no CTA barriers):
+//     a thread loads, updates and stores its own row; mbarriers track the copies.  Warp 7 turns
+//     p_s into (c, sigma, dn) ahead of time (prefix sum of p^2; every worker does this
+//     redundantly, off the critical path) and hands them over through a full/empty mbarrier ring.
+//
+// Deadlock freedom: the chain at block row r waits only for workers' step r-d-1; a worker's step
+// s waits only for p_s; loads wait for nothing.  All CTAs are co-resident (cooperative launch,
+// one CTA per SM).  Every global spin has a watchdog that raises CHUB_STATUS_INTERNAL instead of
+// hanging.
 #pragma once
+
+#include <cuda.h>  // CUtensorMap (types only; cuTensorMapEncodeTiled is fetched at run time)
+
+#include <algorithm>
+#include <cstdlib>
 
 #include "large.cuh"
 
 namespace chub {
 
-inline size_t dataflow_flag_bytes(int64_t n) { (void)n; return 0; }
+constexpr int kDfThreads = 256;
+constexpr int kDfRowWarps = 7;  // warps 0..6 own rows, warp 7 derives the coefficients
+constexpr int kDfD = 4;         // band depth in block columns (look-ahead of the chain)
+constexpr int kDfStages = 6;    // worker tile ring
+constexpr int kDfSlots = 4;     // chain prefetch ring (block columns)
+constexpr int kDfCoefRing = 8;
+constexpr unsigned long long kSentinelBits = 0xFFFFFFFFFFFFFFFFull;
+constexpr long long kWatchdogCycles = 4000000000LL;  // ~2 s
+
+struct DfParams {
+  int n, T, R, r_shift, Wk, rows_max, nw;  // nw = row warps in use
+  int64_t ld;
+  LargeWs ws;
+  int32_t *status;
+  long long *prof;  // optional [gridDim.x][16] cycle counters (nullptr = off)
+};
+
+// ------------------------------------------------------------------ primitives
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(void *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(void *bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Wait with a watchdog: a copy that never lands must not hang the GPU.
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity, int32_t *status) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 255u) == 0u) {
+      if (clock64() - t0 > 4000000000LL) {
+        atomicMax(status, CHUB_STATUS_INTERNAL);
+        return;
+      }
+    }
+  }
+}
+// global -> shared bulk async copy (TMA engine), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, void *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global bulk async store, tracked by the thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+               ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+// 2-D tensor-map TMA: one instruction moves a whole box (c0 = column, c1 = row of its corner)
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, void *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+               ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, const void *smem_src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n"
+               ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const void *p) {
+  unsigned long long x;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(x) : "l"(p) : "memory");
+  return x;
+}
+__device__ __forceinline__ void st_relaxed_f64(void *p, double x) {
+  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;\n" ::"l"(p), "d"(x) : "memory");
+}
+__device__ __forceinline__ int ld_relaxed_s32(const void *p) {
+  int x;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(x) : "l"(p) : "memory");
+  return x;
+}
+
+// Spin until *p is not the sentinel.  On watchdog expiry (or if another CTA already gave up)
+// flag CHUB_STATUS_INTERNAL and return 0.0 so that the kernel drains instead of hanging.
+__device__ __forceinline__ double df_wait_value(const double *p, int32_t *status) {
+  unsigned long long bits = ld_relaxed_u64(p);
+  if (bits != kSentinelBits) return __longlong_as_double((long long)bits);
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  while (true) {
+    bits = ld_relaxed_u64(p);
+    if (bits != kSentinelBits) return __longlong_as_double((long long)bits);
+    if ((++spins & 255u) == 0u) {
+      if (ld_relaxed_s32(status) == CHUB_STATUS_INTERNAL) return 0.0;
+      if (clock64() - t0 > kWatchdogCycles) {
+        atomicMax(status, CHUB_STATUS_INTERNAL);
+        return 0.0;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ double df_sanitize(double x) {
+  // never let user data alias the sentinel
+  return (unsigned long long)__double_as_longlong(x) == kSentinelBits ? __longlong_as_double(0x7FF8000000000000LL) : x;
+}
+
+// Which block column does a row of block row b process at step s?  (-1: none)
+__device__ __forceinline__ int df_panel_at(int b, int s) {
+  if (s < b - kDfD) return s;                                  // far left of the diagonal
+  if (s >= b && s <= b + kDfD && s >= kDfD) return s - kDfD;   // band, delayed by d steps
+  return -1;
+}
+
+template <typename T> struct DfGeom {
+  static constexpr int EPC = 16 / sizeof(T);          // elements per 16 bytes
+  static constexpr int STRIDE = kPanel + EPC;         // padded row of a row-major tile (elements)
+  static constexpr int CPR = kPanel / EPC;            // 16-byte chunks per 32-element row segment
+};
+
+#define DF_PROF_T() (P.prof ? clock64() : 0LL)
+#define DF_PROF_ADD(slot, t_begin) do { if (P.prof) pacc[slot] += clock64() - (t_begin); } while (0)
+
+// ------------------------------------------------------------------ prepare
+template <typename T, int LAYOUT>
+__global__ void df_prepare_kernel(const T *L, int n, int64_t ld, const T *v, LargeWs ws, int flags,
+                                  int32_t *status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_pad = (n + 31) & ~31;
+  if (i >= n_pad) return;
+  const double sentinel = __longlong_as_double((long long)kSentinelBits);
+  ws.p[i] = sentinel;
+  if (i < n) {
+    const double vi = df_sanitize((double)v[i]);
+    const T dgi = L[idx<LAYOUT>(i, i, ld)];
+    ws.v0[i] = vi;
+    ws.dg[i] = (double)dgi;
+    ws.w[i] = (i >> 5) <= kDfD ? vi : sentinel;  // rows whose band starts at column 0
+    if ((flags & CHUB_FLAG_CHECK_DIAG) && dgi == T(0)) atomicMax(status, CHUB_STATUS_ZERO_DIAG);
+  } else {
+    ws.v0[i] = 0.0;
+    ws.dg[i] = 1.0;
+    ws.w[i] = 0.0;
+  }
+  if (i == 0) { ws.scal[0] = 1.0; ws.scal[1] = 1.0; ws.scal[2] = 0.0; ws.scal[3] = 0.0; }
+}
+
+// ------------------------------------------------------------------ chain CTA
+// Shared-memory tile of the band: row-major source -> [32 rows][STRIDE] (lane = row reads 16-byte
+// chunks conflict-free thanks to the padding); column-major source -> [32 cols][32 rows].
+template <typename T, int LAYOUT>
+__device__ void df_chain(const T *L, const DfParams &P, unsigned char *smem) {
+  constexpr int EPC = DfGeom<T>::EPC, CPR = DfGeom<T>::CPR, STRIDE = DfGeom<T>::STRIDE;
+  constexpr int TILE_ELEMS = LAYOUT == CHUB_ROW_MAJOR ? kPanel * STRIDE : kPanel * kPanel;
+  constexpr int LOADERS = kDfThreads - kDfD * 32;  // warps d..7
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = P.n, T_ = P.T;
+  const int64_t ld = P.ld;
+  long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);  // [kDfSlots]
+  double *Xs = reinterpret_cast<double *>(smem + 64);                       // [kDfSlots][kXBlock]
+  double *acc = Xs + kDfSlots * kXBlock;                                    // [kDfD+1][32]
+  double *pbuf = acc + (kDfD + 1) * kPanel;                                 // [2][32]
+  double *wvec = pbuf + 2 * kPanel;                                         // [32]
+  double *wtb = wvec + kPanel;                                              // [2][32] polled wt
+  T *tiles = reinterpret_cast<T *>(wtb + 2 * kPanel);                       // [kDfSlots][kDfD][TILE_ELEMS]
+
+  if (tid == 0) {
+    for (int i = 0; i < kDfSlots; ++i) mbar_init(&full[i], LOADERS);
+    fence_mbar_init();
+  }
+  for (int e = tid; e < (kDfD + 1) * kPanel; e += kDfThreads) acc[e] = 0.0;
+  __syncthreads();
+
+  // Loads for block column j: tiles (j+1 .. j+d, j) and X_{j+1}, into slot j % kDfSlots.
+  // Called by the LOADERS threads (t = 0 .. LOADERS-1); each arrives exactly once.
+  auto issue_slot = [&](int j, int t) {
+    if (j < 0 || j >= T_) return;
+    const int slot = j % kDfSlots;
+    void *bar = &full[slot];
+    unsigned bytes = 0;
+    const int q = t >> 5, rr = t & 31;  // tile q (block row j+1+q), row / column rr of it
+    const void *src = nullptr;
+    void *dst = nullptr;
+    if (q < kDfD) {
+      const int br = j + 1 + q;
+      T *tb = tiles + ((size_t)slot * kDfD + q) * TILE_ELEMS;
+      if (br < T_) {
+        if (LAYOUT == CHUB_ROW_MAJOR) {
+          const int64_t row = (int64_t)br * kPanel + rr;
+          if (row < n) {
+            src = L + row * ld + (int64_t)j * kPanel;
+            dst = tb + rr * STRIDE;
+            bytes = kPanel * sizeof(T);
+          }
+        } else {
+          const int64_t row0 = (int64_t)br * kPanel;
+          const int64_t col = (int64_t)j * kPanel + rr;
+          int rows_in = (int)min((int64_t)kPanel, (int64_t)n - row0);
+          rows_in = (rows_in + EPC - 1) / EPC * EPC;
+          if (rows_in > 0) {
+            src = L + row0 + col * ld;
+            dst = tb + rr * kPanel;
+            bytes = rows_in * sizeof(T);
+          }
+        }
+      }
+    }
+    const bool do_x = (t == 0) && (j + 1 < T_);
+    const unsigned xbytes = do_x ? kXBlock * sizeof(double) : 0u;
+    if (bytes + xbytes) mbar_arrive_expect_tx(bar, bytes + xbytes);
+    else mbar_arrive(bar);
+    if (bytes) bulk_g2s(dst, src, bytes, bar);
+    if (do_x) bulk_g2s(Xs + slot * kXBlock, P.ws.X + (int64_t)(j + 1) * kXBlock, xbytes, bar);
+  };
+
+  // prologue: prefetch slots 0 .. kDfSlots-2; p_0 = X_0 w_0 (w_0 = v[0:32])
+  if (warp >= kDfD)
+    for (int j = 0; j < kDfSlots - 1; ++j) issue_slot(j, tid - kDfD * 32);
+  if (warp == 0) {
+    wvec[lane] = df_wait_value(P.ws.w + lane, P.status);
+    __syncwarp();
+    const double *X0 = P.ws.X + lane * kXStride;
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < kPanel; k += 2) {
+      a0 += X0[k] * wvec[k];
+      a1 += X0[k + 1] * wvec[k + 1];
+    }
+    const double p0 = a0 + a1;
+    pbuf[lane] = p0;
+    st_relaxed_f64(P.ws.p + lane, p0);
+  }
+  __syncthreads();
+
+  const long long t_chain0 = DF_PROF_T();
+  for (int j = 0; j < T_; ++j) {
+    // ---- phase A: acc_{j+1+q} -= L[j+1+q, j] p_j  (warp q < d); warps d..7 prefetch; warp d
+    //      also polls wt_{j+1} so that phase B finds it in shared memory
+    long long tp = DF_PROF_T();
+    const double *pj = pbuf + (j & 1) * kPanel;
+    if (warp < kDfD) {
+      const int br = j + 1 + warp;
+      if (br < T_) {
+        mbar_wait(&full[j % kDfSlots], (unsigned)((j / kDfSlots) & 1), P.status);
+        if (tid == 0) DF_PROF_ADD(1, tp);
+        const T *tb = tiles + ((size_t)(j % kDfSlots) * kDfD + warp) * TILE_ELEMS;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        if ((int64_t)br * kPanel + lane < n) {
+          if (LAYOUT == CHUB_ROW_MAJOR) {
+            const T *rowp = tb + lane * STRIDE;
+#pragma unroll
+            for (int ch = 0; ch < CPR; ++ch) {
+              if (EPC == 2) {
+                const double2 x = *reinterpret_cast<const double2 *>(rowp + ch * 2);
+                if (ch & 1) { a2 += x.x * pj[ch * 2]; a3 += x.y * pj[ch * 2 + 1]; }
+                else        { a0 += x.x * pj[ch * 2]; a1 += x.y * pj[ch * 2 + 1]; }
+              } else {
+                const float4 x = *reinterpret_cast<const float4 *>(rowp + ch * 4);
+                a0 += (double)x.x * pj[ch * 4];
+                a1 += (double)x.y * pj[ch * 4 + 1];
+                a2 += (double)x.z * pj[ch * 4 + 2];
+                a3 += (double)x.w * pj[ch * 4 + 3];
+              }
+            }
+          } else {
+#pragma unroll 8
+            for (int k = 0; k < kPanel; k += 4) {
+              a0 += (double)tb[k * kPanel + lane] * pj[k];
+              a1 += (double)tb[(k + 1) * kPanel + lane] * pj[k + 1];
+              a2 += (double)tb[(k + 2) * kPanel + lane] * pj[k + 2];
+              a3 += (double)tb[(k + 3) * kPanel + lane] * pj[k + 3];
+            }
+          }
+        }
+        acc[(br % (kDfD + 1)) * kPanel + lane] -= (a0 + a1) + (a2 + a3);
+      }
+      if (tid == 0) DF_PROF_ADD(2, tp);
+    } else {
+      // refill the slot that phase A of block column j-1 released at the last barrier
+      issue_slot(j + kDfSlots - 1, tid - kDfD * 32);
+      if (warp == kDfD && j + 1 < T_) {
+        long long tq = DF_PROF_T();
+        wtb[((j + 1) & 1) * kPanel + lane] =
+            df_wait_value(P.ws.w + (int64_t)(j + 1) * kPanel + lane, P.status);
+        if (lane == 0) DF_PROF_ADD(4, tq);
+      }
+    }
+    tp = DF_PROF_T();
+    __syncthreads();
+    // ---- phase B: w_{j+1} = wt_{j+1} + acc ; p_{j+1} = X_{j+1} w_{j+1}
+    if (warp == 0 && j + 1 < T_) {
+      const int r = j + 1;
+      double *a = acc + (r % (kDfD + 1)) * kPanel;
+      wvec[lane] = wtb[(r & 1) * kPanel + lane] + a[lane];
+      a[lane] = 0.0;
+      __syncwarp();
+      if (tid == 0) DF_PROF_ADD(3, tp);
+      tp = DF_PROF_T();
+      const double *X = Xs + (j % kDfSlots) * kXBlock + lane * kXStride;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int k = 0; k < kPanel; k += 4) {
+        const double2 x = *reinterpret_cast<const double2 *>(X + k);
+        const double2 y = *reinterpret_cast<const double2 *>(X + k + 2);
+        a0 += x.x * wvec[k];
+        a1 += x.y * wvec[k + 1];
+        a2 += y.x * wvec[k + 2];
+        a3 += y.y * wvec[k + 3];
+      }
+      const double pr = (a0 + a1) + (a2 + a3);
+      pbuf[(r & 1) * kPanel + lane] = pr;
+      st_relaxed_f64(P.ws.p + (int64_t)r * kPanel + lane, pr);  // publish: data is its own flag
+      if (tid == 0) DF_PROF_ADD(5, tp);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) DF_PROF_ADD(0, t_chain0);
+  if (P.prof && (tid == 0 || tid == kDfD * 32)) {
+    for (int i = 0; i < 8; ++i)
+      if (pacc[i]) P.prof[(size_t)blockIdx.x * 16 + i] = pacc[i];
+  }
+}
+
+template <typename T>
+inline size_t df_chain_smem(int layout) {
+  const size_t tile_elems = layout == CHUB_ROW_MAJOR ? (size_t)kPanel * DfGeom<T>::STRIDE : (size_t)kPanel * kPanel;
+  return 64 + (size_t)(kDfSlots * kXBlock + (kDfD + 1) * kPanel + 5 * kPanel) * sizeof(double) +
+         (size_t)kDfSlots * kDfD * tile_elems * sizeof(T);
+}
+
+// ------------------------------------------------------------------ worker CTAs
+template <typename T, int LAYOUT, bool UPDATE>
+__device__ void df_worker(T *L, T *v, const DfParams &P, unsigned char *smem) {
+  constexpr int EPC = DfGeom<T>::EPC, CPR = DfGeom<T>::CPR, STRIDE = DfGeom<T>::STRIDE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wkr = blockIdx.x - 1;
+  const int n = P.n, T_ = P.T, R = P.R, rsh = P.r_shift, Wk = P.Wk, nw = P.nw;
+  const int64_t ld = P.ld;
+  const int nsteps = T_ + kDfD;
+  long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+  // shared memory carve-up
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);  // [kDfStages][kDfRowWarps]
+  unsigned long long *cfull = full + kDfStages * kDfRowWarps;               // [kDfCoefRing]
+  unsigned long long *cempty = cfull + kDfCoefRing;                         // [kDfCoefRing]
+  double *coef = reinterpret_cast<double *>(smem + 512);                    // [kDfCoefRing][4][32]
+  T *stages = reinterpret_cast<T *>(coef + kDfCoefRing * 4 * kPanel);
+  // row-major: stage = [nw*32 rows][STRIDE];  column-major: stage = [nw warps][32 cols][32 rows]
+  const size_t stage_elems = (size_t)nw * 32 * (LAYOUT == CHUB_ROW_MAJOR ? STRIDE : kPanel);
+
+  if (tid == 0) {
+    for (int i = 0; i < kDfStages * kDfRowWarps; ++i) mbar_init(&full[i], 32);
+    for (int i = 0; i < kDfCoefRing; ++i) { mbar_init(&cfull[i], 32); mbar_init(&cempty[i], nw); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto row_of = [&](int lr) -> int64_t {
+    return (((int64_t)wkr + (int64_t)(lr >> rsh) * Wk) << rsh) + (lr & (R - 1));
+  };
+
+  if (warp == 7) {
+    // ---------------- coefficient warp: p_s -> (p, c, sigma, dn) of block column s
+    double t_run = 1.0, S_run = 1.0;
+    for (int pan = 0; pan < T_; ++pan) {
+      const int slot = pan % kDfCoefRing;
+      if (pan >= kDfCoefRing) mbar_wait(&cempty[slot], (unsigned)((pan / kDfCoefRing - 1) & 1), P.status);
+      const int k = pan * kPanel + lane;
+      long long tq = DF_PROF_T();
+      const double pk = df_wait_value(P.ws.p + k, P.status);
+      if (lane == 0) DF_PROF_ADD(6, tq);
+      double *cf = coef + (size_t)slot * 4 * kPanel;
+      cf[lane] = pk;
+      if (UPDATE) {
+        const double dg = P.ws.dg[k];
+        double incl = pk * pk;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double y = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += y;
+        }
+        double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 0.0;
+        const double tk = t_run + excl, tk1 = t_run + incl;
+        const unsigned negmask = __ballot_sync(0xffffffffu, dg < 0.0);
+        const double Sk = (__popc(negmask & ((1u << lane) - 1u)) & 1) ? -S_run : S_run;
+        const double sgn = dg < 0.0 ? -1.0 : 1.0;
+        const double rinv = 1.0 / sqrt(tk * tk1);
+        const double ck = sgn * tk * rinv, sigk = sgn * pk * rinv;
+        cf[kPanel + lane] = ck;
+        cf[2 * kPanel + lane] = sigk;
+        cf[3 * kPanel + lane] = fabs(dg) * tk1 * rinv;
+        if (wkr == pan % Wk && k < n) {  // one worker per panel leaves rotg's z_k in v[k]
+          const double nuk = Sk * dg * pk / sqrt(tk);
+          const double sk = Sk * sgn * pk / sqrt(tk1);
+          v[k] = (T)rotg_z<double>(dg, nuk, ck, sk);
+        }
+        t_run = __shfl_sync(0xffffffffu, tk1, 31);
+        if (__popc(negmask) & 1) S_run = -S_run;
+      }
+      mbar_arrive(&cfull[slot]);  // release: the 32 lanes' shared-memory writes become visible
+      if (lane == 0) DF_PROF_ADD(7, tq);
+    }
+    if (P.prof && lane == 0) {
+      P.prof[(size_t)blockIdx.x * 16 + 6] = pacc[6];
+      P.prof[(size_t)blockIdx.x * 16 + 7] = pacc[7];
+    }
+    return;
+  }
+  if (warp >= nw) return;
+
+  // ---------------- row warps
+  const int lr = warp * 32 + lane;          // local row
+  const bool prof_me = (warp == nw - 1) && lane == 0;  // the warp that holds the bottom rows
+  const int64_t row = row_of(lr);
+  const bool has_row = lr < P.rows_max && row < n;
+  const int b = has_row ? (int)(row >> 5) : -1000000;
+  double w = has_row ? P.ws.v0[row] : 0.0;
+  // column-major: lane k moves column k of the two 16-row blocks (h = 0, 1) of this warp
+  int64_t cm_row0[2] = {0, 0};
+  int cm_b[2] = {-1000000, -1000000}, cm_rows[2] = {0, 0};
+  if (LAYOUT == CHUB_COL_MAJOR) {
+    for (int h = 0; h < 2; ++h) {
+      const int lr0 = warp * 32 + 16 * h;
+      const int64_t r0 = row_of(lr0);
+      if (lr0 < P.rows_max && r0 < n) {
+        cm_row0[h] = r0;
+        cm_b[h] = (int)(r0 >> 5);
+        cm_rows[h] = (int)min((int64_t)16, (int64_t)n - r0);
+      }
+    }
+  }
+
+  auto issue_load = [&](int s) {
+    if (s >= nsteps) return;
+    void *bar = &full[(s % kDfStages) * kDfRowWarps + warp];
+    T *st = stages + (size_t)(s % kDfStages) * stage_elems;
+    if (LAYOUT == CHUB_ROW_MAJOR) {
+      const int pan = has_row ? df_panel_at(b, s) : -1;
+      if (pan >= 0) {
+        const int64_t c0 = (int64_t)pan * kPanel;
+        int cnt = (int)min((int64_t)kPanel, min((int64_t)n - c0, row - c0 + 1));
+        cnt = (cnt + EPC - 1) / EPC * EPC;
+        const unsigned bytes = cnt * sizeof(T);
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_g2s(st + (size_t)lr * STRIDE, L + row * ld + c0, bytes, bar);
+      } else {
+        mbar_arrive(bar);
+      }
+    } else {
+      unsigned total = 0;
+      const void *src[2] = {nullptr, nullptr};
+      void *dst[2] = {nullptr, nullptr};
+      unsigned by[2] = {0, 0};
+      T *wt = st + (size_t)warp * kPanel * kPanel;
+      for (int h = 0; h < 2; ++h) {
+        const int pan = df_panel_at(cm_b[h], s);
+        if (pan < 0) continue;
+        const int64_t col = (int64_t)pan * kPanel + lane;
+        if (col >= n || col > cm_row0[h] + cm_rows[h] - 1) continue;  // outside the lower triangle
+        const int rows_r = (cm_rows[h] + EPC - 1) / EPC * EPC;
+        src[h] = L + cm_row0[h] + col * ld;
+        dst[h] = wt + lane * kPanel + 16 * h;
+        by[h] = rows_r * sizeof(T);
+        total += by[h];
+      }
+      if (total) mbar_arrive_expect_tx(bar, total);
+      else mbar_arrive(bar);
+      for (int h = 0; h < 2; ++h)
+        if (by[h]) bulk_g2s(dst[h], src[h], by[h], bar);
+    }
+  };
+
+  for (int s = 0; s < kDfStages - 2; ++s) issue_load(s);
+
+  const long long t_wk0 = DF_PROF_T();
+  for (int s = 0; s < nsteps; ++s) {
+    long long tp = DF_PROF_T();
+    if (LAYOUT == CHUB_COL_MAJOR) __syncwarp();  // lanes share the warp's tile: all done with step s-1
+    bulk_wait_read<1>();  // my store of step s-2 has left shared memory: its stage is free
+    issue_load(s + kDfStages - 2);
+    if (prof_me) DF_PROF_ADD(2, tp);
+    tp = DF_PROF_T();
+    mbar_wait(&full[(s % kDfStages) * kDfRowWarps + warp], (unsigned)((s / kDfStages) & 1), P.status);
+    if (prof_me) DF_PROF_ADD(1, tp);
+    tp = DF_PROF_T();
+    if (s < T_) mbar_wait(&cfull[s % kDfCoefRing], (unsigned)((s / kDfCoefRing) & 1), P.status);
+    if (prof_me) DF_PROF_ADD(4, tp);
+    tp = DF_PROF_T();
+
+    const int pan = has_row ? df_panel_at(b, s) : -1;
+    T *st = stages + (size_t)(s % kDfStages) * stage_elems;
+    if (pan >= 0) {
+      const double *cf = coef + (size_t)(pan % kDfCoefRing) * 4 * kPanel;
+      const int64_t c0 = (int64_t)pan * kPanel;
+      const bool full_tile = c0 + kPanel <= row;  // whole tile strictly below the diagonal
+      if (LAYOUT == CHUB_ROW_MAJOR) {
+        T *rowp = st + (size_t)lr * STRIDE;
+#pragma unroll 4
+        for (int ch = 0; ch < CPR; ++ch) {
+          int4 raw = *reinterpret_cast<const int4 *>(rowp + ch * EPC);
+          T *x = reinterpret_cast<T *>(&raw);
+#pragma unroll
+          for (int u = 0; u < EPC; ++u) {
+            const int k = ch * EPC + u;
+            const int64_t col = c0 + k;
+            if (full_tile || col < row) {
+              const double lo = (double)x[u];
+              if (UPDATE) x[u] = (T)(cf[kPanel + k] * lo + cf[2 * kPanel + k] * w);
+              w -= lo * cf[k];
+            } else if (UPDATE && col == row) {
+              x[u] = (T)cf[3 * kPanel + k];
+            }
+          }
+          if (UPDATE) *reinterpret_cast<int4 *>(rowp + ch * EPC) = raw;
+        }
+      } else {
+        T *colp = st + (size_t)warp * kPanel * kPanel + lane;
+#pragma unroll 8
+        for (int k = 0; k < kPanel; ++k) {
+          T *sm = colp + k * kPanel;
+          const int64_t col = c0 + k;
+          if (full_tile || col < row) {
+            const double lo = (double)*sm;
+            if (UPDATE) *sm = (T)(cf[kPanel + k] * lo + cf[2 * kPanel + k] * w);
+            w -= lo * cf[k];
+          } else if (UPDATE && col == row) {
+            *sm = (T)cf[3 * kPanel + k];
+          }
+        }
+      }
+      // hand the residual over to the chain after the last far-left block column
+      if (s == b - kDfD - 1) st_relaxed_f64(P.ws.w + row, df_sanitize(w));
+    }
+    if (prof_me) DF_PROF_ADD(3, tp);
+    tp = DF_PROF_T();
+
+    fence_proxy_async();  // order my generic-proxy accesses before later bulk (async proxy) copies
+    if (UPDATE) {
+      if (LAYOUT == CHUB_ROW_MAJOR) {
+        if (pan >= 0) {
+          const int64_t c0 = (int64_t)pan * kPanel;
+          const int cnt = (int)min((int64_t)kPanel, row - c0 + 1);  // never above the diagonal
+          const int cb = cnt / EPC * EPC;
+          T *rowp = st + (size_t)lr * STRIDE;
+          T *g = L + row * ld + c0;
+          if (cb) bulk_s2g(g, rowp, cb * sizeof(T));
+          for (int u = cb; u < cnt; ++u) g[u] = rowp[u];
+        }
+      } else {
+        __syncwarp();  // lane k stores column k: entries written by the other lanes of this warp
+        T *wt = st + (size_t)warp * kPanel * kPanel;
+        for (int h = 0; h < 2; ++h) {
+          const int panh = df_panel_at(cm_b[h], s);
+          if (panh < 0) continue;
+          const int64_t col = (int64_t)panh * kPanel + lane;
+          const int64_t r_hi = cm_row0[h] + cm_rows[h];
+          int64_t r_lo = max(cm_row0[h], col);
+          if (col >= n || r_lo >= r_hi) continue;
+          T *sm = wt + lane * kPanel + 16 * h - cm_row0[h];  // sm[r] = element (r, col)
+          T *g = L + col * ld;                               // g[r]  = element (r, col)
+          while (r_lo < r_hi && (r_lo & (EPC - 1))) { g[r_lo] = sm[r_lo]; ++r_lo; }
+          const int64_t r_mid = r_lo + (r_hi - r_lo) / EPC * EPC;
+          if (r_mid > r_lo) bulk_s2g(g + r_lo, sm + r_lo, (unsigned)((r_mid - r_lo) * sizeof(T)));
+          for (int64_t r = r_mid; r < r_hi; ++r) g[r] = sm[r];
+        }
+      }
+      bulk_commit();
+    }
+    // this warp is done with block column s-d for good
+    if (s >= kDfD && s - kDfD < T_) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&cempty[(s - kDfD) % kDfCoefRing]);
+    }
+    if (prof_me) DF_PROF_ADD(5, tp);
+  }
+  if (prof_me) DF_PROF_ADD(0, t_wk0);
+  bulk_wait_all<0>();
+  if (P.prof && prof_me) {
+    for (int i = 0; i < 6; ++i) P.prof[(size_t)blockIdx.x * 16 + i] = pacc[i];
+  }
+}
+
+template <typename T>
+inline size_t df_worker_smem(int layout, int nw) {
+  const size_t stage_elems = (size_t)nw * 32 * (layout == CHUB_ROW_MAJOR ? DfGeom<T>::STRIDE : kPanel);
+  return 512 + (size_t)kDfCoefRing * 4 * kPanel * sizeof(double) + (size_t)kDfStages * stage_elems * sizeof(T);
+}
+
+// ------------------------------------------------------------------ the kernel
+template <typename T, int LAYOUT, bool UPDATE>
+__global__ void __launch_bounds__(kDfThreads, 1) df_kernel_v2(T *L, T *v, DfParams P) {
+  extern __shared__ __align__(1024) unsigned char df_smem[];
+  if (*P.status != 0) return;  // check_diag failed: L and v stay untouched
+  if (blockIdx.x == 0) df_chain<T, LAYOUT>(L, P, df_smem);
+  else df_worker<T, LAYOUT, UPDATE>(L, v, P, df_smem);
+}
+
+// =====================================================================================
+// v3 (row-major): tensor-map TMA boxes + 4 threads per row
+// =====================================================================================
+// A worker's rows come in blocks of 16 (two warps of 8 rows each).  Per step a warp moves its
+// [8 rows x 32 cols] tile with one TMA instruction per 128-byte-wide box (SWIZZLE_128B, so that
+// "8 lanes = 8 rows, same 16-byte chunk" is bank-conflict free) issued by lane 0.  Lane (g, r8)
+// owns columns 8g..8g+7 of row r8: it forms the local prefix sums of L_ik p_k, the four segment
+// totals are combined by a two-step shuffle scan, and every entry is updated from
+//     L_ik <- c_k L_ik + sigma_k (w_i - sum_{m<k} L_im p_m)
+// so the serial chain per row is 8 long instead of 32 and 4x as many warps hide latency.
+constexpr int kRmMaxQ = 7;                       // row blocks (16 rows) per worker
+constexpr int kRmMaxThreads = 32 * (2 * kRmMaxQ + 2);  // 14 row warps + coefficient warp (+1 spare) = 512
+
+template <typename T> struct RmGeom {
+  static constexpr int HALVES = kPanel * sizeof(T) / 128;  // 128-byte boxes per 32-column tile (2 / 1)
+  static constexpr int BOXC = kPanel / HALVES;             // box columns (16 / 32)
+  static constexpr int EPC = 16 / sizeof(T);               // elements per 16-byte chunk (2 / 4)
+  static constexpr int CPT = 8 / EPC;                      // chunks per thread (8 columns): 4 / 2
+  static constexpr int WTILE = HALVES * 1024;              // bytes of a warp's tile (8 rows)
+  static constexpr int CTILE = HALVES * 4096;              // bytes of a chain tile (32 rows)
+};
+
+// ---- chain CTA (threads 0..255 of CTA 0)
+template <typename T>
+__device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsigned char *smem) {
+  constexpr int HALVES = RmGeom<T>::HALVES, BOXC = RmGeom<T>::BOXC, EPC = RmGeom<T>::EPC;
+  constexpr int CTILE = RmGeom<T>::CTILE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T_ = P.T;
+  long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);  // [kDfSlots]
+  double *acc = reinterpret_cast<double *>(smem + 64);                      // [kDfD+1][32]
+  double *pbuf = acc + (kDfD + 1) * kPanel;                                 // [2][32]
+  double *wvec = pbuf + 2 * kPanel;                                         // [32]
+  double *wtb = wvec + kPanel;                                              // [2][32]
+  double *Xs = reinterpret_cast<double *>(smem + 4096);                     // [kDfSlots][kXBlock]
+  unsigned char *tiles = smem + 4096 + ((kDfSlots * kXBlock * 8 + 1023) / 1024) * 1024;  // [kDfSlots][kDfD][CTILE]
+
+  if (tid == 0) {
+    for (int i = 0; i < kDfSlots; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  for (int e = tid; e < (kDfD + 1) * kPanel; e += 256) acc[e] = 0.0;
+  named_sync(1, 256);
+
+  // one thread issues everything block column j needs: tiles (j+1..j+d, j) and X_{j+1}
+  auto issue_slot = [&](int j) {
+    if (j < 0 || j >= T_) return;
+    const int slot = j % kDfSlots;
+    void *bar = &full[slot];
+    int ntiles = min(kDfD, T_ - 1 - j);
+    if (ntiles < 0) ntiles = 0;
+    const bool do_x = j + 1 < T_;
+    const unsigned bytes = (unsigned)ntiles * CTILE + (do_x ? kXBlock * 8u : 0u);
+    if (bytes == 0) { mbar_arrive(bar); return; }
+    mbar_arrive_expect_tx(bar, bytes);
+    for (int q = 0; q < ntiles; ++q)
+      for (int h = 0; h < HALVES; ++h)
+        tma_load_2d(tiles + ((size_t)slot * kDfD + q) * CTILE + h * 4096, tmap32,
+                    j * kPanel + h * BOXC, (j + 1 + q) * kPanel, bar);
+    if (do_x) bulk_g2s(Xs + slot * kXBlock, P.ws.X + (int64_t)(j + 1) * kXBlock, kXBlock * 8u, bar);
+  };
+
+  if (tid == kDfD * 32)
+    for (int j = 0; j < kDfSlots - 1; ++j) issue_slot(j);
+  if (warp == 0) {
+    wvec[lane] = df_wait_value(P.ws.w + lane, P.status);
+    __syncwarp();
+    const double *X0 = P.ws.X + lane * kXStride;
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < kPanel; k += 2) {
+      a0 += X0[k] * wvec[k];
+      a1 += X0[k + 1] * wvec[k + 1];
+    }
+    const double p0 = a0 + a1;
+    pbuf[lane] = p0;
+    st_relaxed_f64(P.ws.p + lane, p0);
+  }
+  named_sync(1, 256);
+
+  const long long t_chain0 = DF_PROF_T();
+  for (int j = 0; j < T_; ++j) {
+    long long tp = DF_PROF_T();
+    const double *pj = pbuf + (j & 1) * kPanel;
+    if (warp < kDfD) {
+      const int br = j + 1 + warp;
+      if (br < T_) {
+        mbar_wait(&full[j % kDfSlots], (unsigned)((j / kDfSlots) & 1), P.status);
+        if (tid == 0) DF_PROF_ADD(1, tp);
+        const unsigned char *tb = tiles + ((size_t)(j % kDfSlots) * kDfD + warp) * CTILE;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int h = 0; h < HALVES; ++h) {
+          const unsigned char *rowp = tb + h * 4096 + lane * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int4 raw = *reinterpret_cast<const int4 *>(rowp + ((c ^ (lane & 7)) << 4));
+            const T *x = reinterpret_cast<const T *>(&raw);
+            const int k0 = h * BOXC + c * EPC;
+            if (EPC == 2) {
+              if (c & 1) { a2 += (double)x[0] * pj[k0]; a3 += (double)x[1] * pj[k0 + 1]; }
+              else       { a0 += (double)x[0] * pj[k0]; a1 += (double)x[1] * pj[k0 + 1]; }
+            } else {
+              a0 += (double)x[0] * pj[k0];
+              a1 += (double)x[1] * pj[k0 + 1];
+              a2 += (double)x[2 % EPC] * pj[k0 + 2 % EPC];
+              a3 += (double)x[3 % EPC] * pj[k0 + 3 % EPC];
+            }
+          }
+        }
+        acc[(br % (kDfD + 1)) * kPanel + lane] -= (a0 + a1) + (a2 + a3);
+      }
+      if (tid == 0) DF_PROF_ADD(2, tp);
+    } else if (warp == kDfD) {
+      if (lane == 0) issue_slot(j + kDfSlots - 1);
+      if (j + 1 < T_) {
+        long long tq = DF_PROF_T();
+        wtb[((j + 1) & 1) * kPanel + lane] =
+            df_wait_value(P.ws.w + (int64_t)(j + 1) * kPanel + lane, P.status);
+        if (lane == 0) DF_PROF_ADD(4, tq);
+      }
+    }
+    tp = DF_PROF_T();
+    named_sync(1, 256);
+    if (warp == 0 && j + 1 < T_) {
+      const int r = j + 1;
+      double *a = acc + (r % (kDfD + 1)) * kPanel;
+      wvec[lane] = wtb[(r & 1) * kPanel + lane] + a[lane];
+      a[lane] = 0.0;
+      __syncwarp();
+      if (tid == 0) DF_PROF_ADD(3, tp);
+      tp = DF_PROF_T();
+      const double *X = Xs + (j % kDfSlots) * kXBlock + lane * kXStride;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int k = 0; k < kPanel; k += 4) {
+        const double2 x = *reinterpret_cast<const double2 *>(X + k);
+        const double2 y = *reinterpret_cast<const double2 *>(X + k + 2);
+        a0 += x.x * wvec[k];
+        a1 += x.y * wvec[k + 1];
+        a2 += y.x * wvec[k + 2];
+        a3 += y.y * wvec[k + 3];
+      }
+      const double pr = (a0 + a1) + (a2 + a3);
+      pbuf[(r & 1) * kPanel + lane] = pr;
+      st_relaxed_f64(P.ws.p + (int64_t)r * kPanel + lane, pr);
+      if (tid == 0) DF_PROF_ADD(5, tp);
+    }
+    named_sync(1, 256);
+  }
+  if (tid == 0) DF_PROF_ADD(0, t_chain0);
+  if (P.prof && (tid == 0 || tid == kDfD * 32)) {
+    for (int i = 0; i < 8; ++i)
+      if (pacc[i]) P.prof[(size_t)blockIdx.x * 16 + i] = pacc[i];
+  }
+}
+
+template <typename T>
+inline size_t df_chain_rm_smem() {
+  return 4096 + ((size_t)(kDfSlots * kXBlock * 8 + 1023) / 1024) * 1024 +
+         (size_t)kDfSlots * kDfD * RmGeom<T>::CTILE;
+}
+
+// ---- worker CTAs
+template <typename T, bool UPDATE>
+__device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *tmap8,
+                             unsigned char *smem) {
+  constexpr int HALVES = RmGeom<T>::HALVES, BOXC = RmGeom<T>::BOXC, EPC = RmGeom<T>::EPC;
+  constexpr int CPT = RmGeom<T>::CPT, WTILE = RmGeom<T>::WTILE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wkr = blockIdx.x - 1;
+  const int n = P.n, T_ = P.T, Wk = P.Wk, nrw = P.nw;  // nrw = row warps (2 per 16-row block)
+  const int64_t ld = P.ld;
+  const int nsteps = T_ + kDfD;
+  long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);  // [kDfStages][nrw]
+  unsigned long long *cfull = full + kDfStages * 2 * kRmMaxQ;               // [kDfCoefRing]
+  unsigned long long *cempty = cfull + kDfCoefRing;                         // [kDfCoefRing]
+  double *coef = reinterpret_cast<double *>(smem + 2048);                   // [kDfCoefRing][4][32]
+  unsigned char *stages = smem + 2048 + kDfCoefRing * 4 * kPanel * 8;       // 1024-aligned
+  const size_t stage_bytes = (size_t)nrw * WTILE;
+
+  if (tid == 0) {
+    for (int i = 0; i < kDfStages * nrw; ++i) mbar_init(&full[i], 1);
+    for (int i = 0; i < kDfCoefRing; ++i) { mbar_init(&cfull[i], 32); mbar_init(&cempty[i], nrw); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp > nrw) return;
+
+  if (warp == nrw) {
+    // ---------------- coefficient warp (software-pipelined: the poll of block column s+1 is in
+    // flight while the coefficients of block column s are formed)
+    double t_run = 1.0, S_run = 1.0;
+    unsigned long long nbits = ld_relaxed_u64(P.ws.p + lane);
+    double ndg = P.ws.dg[lane];
+    for (int pan = 0; pan < T_; ++pan) {
+      const int slot = pan % kDfCoefRing;
+      const int k = pan * kPanel + lane;
+      long long tq = DF_PROF_T();
+      const double pk = nbits != kSentinelBits ? __longlong_as_double((long long)nbits)
+                                               : df_wait_value(P.ws.p + k, P.status);
+      const double dg = ndg;
+      if (pan + 1 < T_) {
+        nbits = ld_relaxed_u64(P.ws.p + k + kPanel);
+        ndg = P.ws.dg[k + kPanel];
+      }
+      if (lane == 0) DF_PROF_ADD(6, tq);
+      if (pan >= kDfCoefRing) mbar_wait(&cempty[slot], (unsigned)((pan / kDfCoefRing - 1) & 1), P.status);
+      double *cf = coef + (size_t)slot * 4 * kPanel;
+      cf[lane] = pk;
+      if (UPDATE) {
+        double incl = pk * pk;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double y = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += y;
+        }
+        double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 0.0;
+        const double tk = t_run + excl, tk1 = t_run + incl;
+        const unsigned negmask = __ballot_sync(0xffffffffu, dg < 0.0);
+        const double sgn = dg < 0.0 ? -1.0 : 1.0;
+        const double rinv = rsqrt(tk * tk1);
+        const double ck = sgn * tk * rinv, sigk = sgn * pk * rinv;
+        cf[kPanel + lane] = ck;
+        cf[2 * kPanel + lane] = sigk;
+        cf[3 * kPanel + lane] = fabs(dg) * tk1 * rinv;
+        mbar_arrive(&cfull[slot]);
+        if (wkr == pan % Wk && k < n) {  // one worker per panel leaves rotg's z_k in v[k]
+          const double Sk = (__popc(negmask & ((1u << lane) - 1u)) & 1) ? -S_run : S_run;
+          const double nuk = Sk * dg * pk / sqrt(tk);
+          const double sk = Sk * sgn * pk / sqrt(tk1);
+          v[k] = (T)rotg_z<double>(dg, nuk, ck, sk);
+        }
+        t_run = __shfl_sync(0xffffffffu, tk1, 31);
+        if (__popc(negmask) & 1) S_run = -S_run;
+      } else {
+        mbar_arrive(&cfull[slot]);
+      }
+      if (lane == 0) DF_PROF_ADD(7, tq);
+    }
+    if (P.prof && lane == 0) {
+      P.prof[(size_t)blockIdx.x * 16 + 6] = pacc[6];
+      P.prof[(size_t)blockIdx.x * 16 + 7] = pacc[7];
+    }
+    return;
+  }
+
+  // ---------------- row warps: warp = 8 consecutive rows, lane = (segment g, row r8)
+  const int g = lane >> 3, r8 = lane & 7;
+  const int64_t row0 = (((int64_t)wkr + (int64_t)(warp >> 1) * Wk) << 4) + ((warp & 1) << 3);
+  const bool warp_valid = row0 < n;
+  const int b = warp_valid ? (int)(row0 >> 5) : -1000000;
+  const int64_t row = row0 + r8;
+  double w = (warp_valid && row < n) ? P.ws.v0[row] : 0.0;
+  const int64_t row0_next = (((int64_t)wkr + (int64_t)((warp + 1) >> 1) * Wk) << 4) + (((warp + 1) & 1) << 3);
+  const bool prof_me = P.prof && lane == 0 && warp_valid && (warp + 1 >= nrw || row0_next >= n);
+  // my 8 columns live in half `hh`, chunks cb .. cb+CPT-1 of the 128-byte box row
+  const int hh = (g * 8 * (int)sizeof(T)) / 128;
+  const int cb = ((g * 8 * (int)sizeof(T)) % 128) / 16;
+
+  auto issue_load = [&](int s) {  // lane 0 only
+    if (s >= nsteps) return;
+    void *bar = &full[(s % kDfStages) * nrw + warp];
+    const int pan = df_panel_at(b, s);
+    if (pan < 0) { mbar_arrive(bar); return; }
+    unsigned char *tile = stages + (size_t)(s % kDfStages) * stage_bytes + (size_t)warp * WTILE;
+    const int c0 = pan * kPanel;
+    int nh = 0;
+    for (int h = 0; h < HALVES; ++h) nh += (c0 + h * BOXC < n) ? 1 : 0;
+    mbar_arrive_expect_tx(bar, (unsigned)nh * 1024u);
+    for (int h = 0; h < nh; ++h) tma_load_2d(tile + h * 1024, tmap8, c0 + h * BOXC, (int)row0, bar);
+  };
+
+  if (lane == 0)
+    for (int s = 0; s < kDfStages - 2; ++s) issue_load(s);
+
+  const long long t_wk0 = DF_PROF_T();
+  for (int s = 0; s < nsteps; ++s) {
+    long long tp = DF_PROF_T();
+    if (lane == 0) {
+      bulk_wait_read<1>();  // the store of step s-2 has left shared memory: its stage is free
+      issue_load(s + kDfStages - 2);
+    }
+    if (prof_me) DF_PROF_ADD(2, tp);
+    tp = DF_PROF_T();
+    mbar_wait(&full[(s % kDfStages) * nrw + warp], (unsigned)((s / kDfStages) & 1), P.status);
+    if (prof_me) DF_PROF_ADD(1, tp);
+    tp = DF_PROF_T();
+    if (s < T_) mbar_wait(&cfull[s % kDfCoefRing], (unsigned)((s / kDfCoefRing) & 1), P.status);
+    if (prof_me) DF_PROF_ADD(4, tp);
+    tp = DF_PROF_T();
+
+    const int pan = df_panel_at(b, s);
+    unsigned char *tile = stages + (size_t)(s % kDfStages) * stage_bytes + (size_t)warp * WTILE;
+    bool diag_step = false;
+    if (pan >= 0) {
+      const double *cf = coef + (size_t)(pan % kDfCoefRing) * 4 * kPanel + g * 8;
+      const int64_t c0 = (int64_t)pan * kPanel + g * 8;  // my first column
+      diag_step = (pan == b);
+      unsigned char *rowp = tile + hh * 1024 + r8 * 128;
+      int4 raw[CPT];
+#pragma unroll
+      for (int i = 0; i < CPT; ++i)
+        raw[i] = *reinterpret_cast<const int4 *>(rowp + (((cb + i) ^ r8) << 4));
+      T *x = reinterpret_cast<T *>(raw);
+      double lo[8], pre[8];  // pre[j] = sum_{m<j} lo_m p_m within my segment
+      double run = 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        lo[j] = (double)x[j];
+        pre[j] = run;
+        const bool below = !diag_step || (c0 + j < row);
+        run += below ? lo[j] * cf[j] : 0.0;
+      }
+      // exclusive scan of the four segment totals (lanes g*8 + r8, same r8)
+      double incl = run;
+      double y = __shfl_up_sync(0xffffffffu, incl, 8);
+      if (g >= 1) incl += y;
+      y = __shfl_up_sync(0xffffffffu, incl, 16);
+      if (g >= 2) incl += y;
+      const double total = __shfl_sync(0xffffffffu, incl, 24 + r8);
+      const double wseg = w - (incl - run);
+      if (UPDATE) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int64_t col = c0 + j;
+          if (!diag_step || col < row) x[j] = (T)(cf[kPanel + j] * lo[j] + cf[2 * kPanel + j] * (wseg - pre[j]));
+          else if (col == row) x[j] = (T)cf[3 * kPanel + j];
+        }
+        if (!diag_step) {
+#pragma unroll
+          for (int i = 0; i < CPT; ++i)
+            *reinterpret_cast<int4 *>(rowp + (((cb + i) ^ r8) << 4)) = raw[i];
+        } else if (row < n) {  // the diagonal tile is ragged: written straight to global memory
+          T *gp = L + row * ld + c0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (c0 + j <= row) gp[j] = x[j];
+        }
+      }
+      w -= total;
+      // hand the residual over to the chain after the last far-left block column
+      if (s == b - kDfD - 1 && g == 0 && row < n) st_relaxed_f64(P.ws.w + row, df_sanitize(w));
+    }
+    if (prof_me) DF_PROF_ADD(3, tp);
+    tp = DF_PROF_T();
+
+    fence_proxy_async();  // my generic-proxy writes -> visible to the TMA (async proxy) store
+    __syncwarp();
+    if (lane == 0) {
+      if (UPDATE && pan >= 0 && !diag_step) {
+        const int c0 = pan * kPanel;
+        for (int h = 0; h < HALVES; ++h)
+          if (c0 + h * BOXC < n) tma_store_2d(tmap8, c0 + h * BOXC, (int)row0, tile + h * 1024);
+      }
+      bulk_commit();
+      if (s >= kDfD && s - kDfD < T_) mbar_arrive(&cempty[(s - kDfD) % kDfCoefRing]);
+    }
+    if (prof_me) DF_PROF_ADD(5, tp);
+  }
+  if (prof_me) DF_PROF_ADD(0, t_wk0);
+  if (lane == 0) bulk_wait_all<0>();
+  if (prof_me) {
+    for (int i = 0; i < 6; ++i) P.prof[(size_t)blockIdx.x * 16 + i] = pacc[i];
+  }
+}
+
+template <typename T>
+inline size_t df_worker_rm_smem(int nrw) {
+  return 2048 + (size_t)kDfCoefRing * 4 * kPanel * 8 + (size_t)kDfStages * nrw * RmGeom<T>::WTILE;
+}
+
+template <typename T, bool UPDATE>
+__global__ void __launch_bounds__(kRmMaxThreads, 1)
+df_kernel_rm(T *L, T *v, DfParams P, const __grid_constant__ CUtensorMap tmap8,
+             const __grid_constant__ CUtensorMap tmap32) {
+  extern __shared__ __align__(1024) unsigned char df_smem[];
+  if (*P.status != 0) return;  // check_diag failed: L and v stay untouched
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < 256) df_chain_rm<T>(P, &tmap32, df_smem);
+  } else {
+    df_worker_rm<T, UPDATE>(L, v, P, &tmap8, df_smem);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+inline size_t dataflow_flag_bytes(int64_t n) { (void)n; return 256 + 256 * 16 * sizeof(long long); }
+
+struct DfPlan {
+  bool ok = false;
+  int sms = 0, R = 0, r_shift = 0, Wk = 0, rows_max = 0, nw = 0;
+  size_t smem = 0;
+};
+
+template <typename T>
+inline DfPlan df_plan(int64_t n, int64_t ld, int layout, const void *L) {
+  DfPlan pl;
+  constexpr int EPC = 16 / sizeof(T);
+  if (n < 64 || n > (1 << 30) || (ld % EPC) != 0 || (reinterpret_cast<uintptr_t>(L) & 15) != 0) return pl;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return pl;
+  int sms = 0, coop = 0, smem_optin = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (!coop || sms < 2) return pl;
+  const int Wk = sms - 1;
+  int best_R = 0, best_rows = 1 << 30;
+  // rows are dealt in blocks of R; column-major needs R = 16 (one 16-row block per half warp)
+  for (int R = 16; R >= (layout == CHUB_COL_MAJOR ? 16 : 1); R >>= 1) {
+    const int64_t nRB = (n + R - 1) / R;
+    const int rows = (int)((nRB + Wk - 1) / Wk) * R;
+    if (rows < best_rows) { best_rows = rows; best_R = R; }
+  }
+  const int nw = (best_rows + 31) / 32;
+  if (best_R == 0 || nw > kDfRowWarps) return pl;
+  const size_t smem = std::max(df_chain_smem<T>(layout), df_worker_smem<T>(layout, nw));
+  if (smem > (size_t)smem_optin) return pl;
+  pl.ok = true; pl.sms = sms; pl.R = best_R; pl.Wk = Wk; pl.rows_max = best_rows; pl.nw = nw; pl.smem = smem;
+  while ((1 << pl.r_shift) < best_R) ++pl.r_shift;
+  return pl;
+}
+
+// ---- v3 plan (row-major): rows dealt in blocks of 16, two warps per block
+struct RmPlan {
+  bool ok = false;
+  int sms = 0, Wk = 0, Q = 0, nrw = 0, threads = 0;
+  size_t smem = 0;
+};
+
+template <typename T>
+inline RmPlan rm_plan(int64_t n, int64_t ld, const void *L) {
+  RmPlan pl;
+  constexpr int EPC = 16 / sizeof(T);
+  if (n < 64 || n >= (1LL << 31) || (ld % EPC) != 0 || (reinterpret_cast<uintptr_t>(L) & 15) != 0) return pl;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return pl;
+  int sms = 0, coop = 0, smem_optin = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (!coop || sms < 2) return pl;
+  const int Wk = sms - 1;
+  const int64_t nRB = (n + 15) / 16;
+  const int Q = (int)((nRB + Wk - 1) / Wk);
+  if (Q > kRmMaxQ) return pl;
+  const int nrw = 2 * Q;
+  const size_t smem = std::max(df_chain_rm_smem<T>(), df_worker_rm_smem<T>(nrw));
+  if (smem > (size_t)smem_optin) return pl;
+  pl.ok = true; pl.sms = sms; pl.Wk = Wk; pl.Q = Q; pl.nrw = nrw;
+  pl.threads = std::max(256, 32 * (nrw + 1));
+  pl.smem = smem;
+  return pl;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// Row-major n x n matrix with leading dimension ld: boxes of [box_rows][128 bytes], SWIZZLE_128B.
+template <typename T>
+inline bool make_tmap(CUtensorMap *map, T *L, int64_t n, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)n};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(T)};
+  const cuuint32_t box[2] = {(cuuint32_t)RmGeom<T>::BOXC, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  return enc(map, dt, 2, L, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 template <typename T>
 inline bool dataflow_supported(int64_t n, int64_t ld, int layout, const T *L) {
-  (void)n; (void)ld; (void)layout; (void)L;
-  return false;
+  if (layout == CHUB_ROW_MAJOR && rm_plan<T>(n, ld, L).ok && get_encode_tiled()) return true;
+  return df_plan<T>(n, ld, layout, L).ok;
 }
 
+// Launches prepare + diagonal inverses + the persistent kernel (+ the downdate's coefficient and
+// sweep kernels).  Returns a cudaError_t-style code; *launches = kernels launched.
 template <typename T, int LAYOUT, bool UPDATE>
 int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs &ws,
                     int32_t *status, cudaStream_t st, int64_t *launches) {
-  (void)L; (void)n; (void)ld; (void)v; (void)flags; (void)ws; (void)status; (void)st;
   *launches = 0;
-  return (int)cudaErrorNotSupported;
+  const int ni = (int)n;
+  const int n_pad = (ni + 31) & ~31;
+  const int nb = n_pad / 32;
+  RmPlan rp;
+  alignas(64) CUtensorMap tmap8, tmap32;
+  if (LAYOUT == CHUB_ROW_MAJOR && !getenv("CHUB_DF_V2")) {
+    rp = rm_plan<T>(n, ld, L);
+    if (rp.ok && !(make_tmap<T>(&tmap8, L, n, ld, 8) && make_tmap<T>(&tmap32, L, n, ld, 32))) rp.ok = false;
+  }
+  DfPlan pl;
+  if (!rp.ok) {
+    pl = df_plan<T>(n, ld, LAYOUT, L);
+    if (!pl.ok) return (int)cudaErrorNotSupported;
+  }
+  df_prepare_kernel<T, LAYOUT><<<(n_pad + 255) / 256, 256, 0, st>>>(L, ni, ld, v, ws, flags, status);
+  ++*launches;
+  large_invdiag_kernel<T, LAYOUT><<<(nb + 3) / 4, 128, 0, st>>>(L, ni, ld, ws, status);
+  ++*launches;
+  DfParams P;
+  P.n = ni; P.T = nb; P.ld = ld; P.ws = ws; P.status = status;
+  P.prof = nullptr;
+  if (getenv("CHUB_PROFILE")) {
+    P.prof = reinterpret_cast<long long *>(reinterpret_cast<char *>(ws.flags) + 256);
+    cudaMemsetAsync(P.prof, 0, 256 * 16 * sizeof(long long), st);
+  }
+  cudaError_t e;
+  if (rp.ok) {
+    P.R = 16; P.r_shift = 4; P.Wk = rp.Wk; P.rows_max = rp.Q * 16; P.nw = rp.nrw;
+    auto kern = df_kernel_rm<T, UPDATE>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rp.smem);
+    if (e != cudaSuccess) return (int)e;
+    void *args[] = {(void *)&L, (void *)&v, (void *)&P, (void *)&tmap8, (void *)&tmap32};
+    e = cudaLaunchCooperativeKernel((void *)kern, dim3(rp.sms), dim3(rp.threads), args, rp.smem, st);
+  } else {
+    P.R = pl.R; P.r_shift = pl.r_shift; P.Wk = pl.Wk; P.rows_max = pl.rows_max; P.nw = pl.nw;
+    auto kern = df_kernel_v2<T, LAYOUT, UPDATE>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) return (int)e;
+    void *args[] = {(void *)&L, (void *)&v, (void *)&P};
+    e = cudaLaunchCooperativeKernel((void *)kern, dim3(pl.sms), dim3(kDfThreads), args, pl.smem, st);
+  }
+  if (e != cudaSuccess) return (int)e;
+  ++*launches;
+  if (!UPDATE) {
+    large_dd_coef_kernel<T, LAYOUT><<<1, 1024, 0, st>>>(L, ni, ld, v, ws, status);
+    ++*launches;
+    large_dd_sweep_kernel<T, LAYOUT><<<(ni + 127) / 128, 128, 0, st>>>(L, ni, ld, ws, status);
+    ++*launches;
+  }
+  e = cudaGetLastError();
+  return (int)e;
 }
 
 }  // namespace chub

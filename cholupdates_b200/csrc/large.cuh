@@ -29,22 +29,26 @@
 namespace chub {
 
 constexpr int kBig = 256;  // columns per chain-kernel launch (8 blocks of 32)
+constexpr int kXStride = kPanel + 2;         // padded row of an inverse diagonal block (doubles):
+constexpr int kXBlock = kPanel * kXStride;  // lane = row reads of 16 bytes are bank-conflict free
 
 struct LargeWs {
-  double *X;      // [nb][32*32] inverse of each 32x32 diagonal block (row-major, identity padded)
+  double *X;      // [nb][kXBlock] inverse of each 32x32 diagonal block (rows of kXStride, identity padded)
   double *w;      // [n_pad]  forward-substitution residual, initialised to v
   double *p;      // [n_pad]  p = L^{-1} v
   double *c;      // [n_pad]  c_k (sign folded)
   double *sg;     // [n_pad]  update: sigma_k (sign folded); downdate: s_k
   double *dn;     // [n_pad]  update: new diagonal L'_kk;     downdate: sign of the input diagonal
+  double *v0;     // [n_pad]  dataflow kernel: pristine copy of v
+  double *dg;     // [n_pad]  dataflow kernel: the input diagonal
   double *scal;   // [8]      0: t (running), 1: S (running sign), 2: p.p, 3: rho^2
-  int32_t *flags; // [..]     dataflow-kernel flags (unused here)
+  int32_t *flags; // [..]     spare
 };
 
 inline size_t large_ws_doubles(int64_t n) {
   int64_t n_pad = (n + 31) & ~31LL;
   int64_t nb = n_pad / 32;
-  return (size_t)(nb * 1024 + 5 * n_pad + 8);
+  return (size_t)(nb * kXBlock + 7 * n_pad + 8);
 }
 
 inline LargeWs large_ws_carve(void *base, int64_t n) {
@@ -52,12 +56,14 @@ inline LargeWs large_ws_carve(void *base, int64_t n) {
   int64_t nb = n_pad / 32;
   LargeWs ws;
   double *d = reinterpret_cast<double *>(base);
-  ws.X = d; d += nb * 1024;
+  ws.X = d; d += nb * kXBlock;
   ws.w = d; d += n_pad;
   ws.p = d; d += n_pad;
   ws.c = d; d += n_pad;
   ws.sg = d; d += n_pad;
   ws.dn = d; d += n_pad;
+  ws.v0 = d; d += n_pad;
+  ws.dg = d; d += n_pad;
   ws.scal = d; d += 8;
   ws.flags = reinterpret_cast<int32_t *>(d);
   return ws;
@@ -111,9 +117,9 @@ __global__ void __launch_bounds__(128) large_invdiag_kernel(const T *L, int n, i
       if (m < i) acc -= (m >= j ? Ls[warp][i][m] * x[m] : 0.0);
     x[i] = (i >= j) ? acc / Ls[warp][i][i] : 0.0;
   }
-  double *X = ws.X + (int64_t)blk * 1024;
+  double *X = ws.X + (int64_t)blk * kXBlock;
 #pragma unroll
-  for (int i = 0; i < kPanel; ++i) X[i * kPanel + j] = x[i];
+  for (int i = 0; i < kPanel; ++i) X[i * kXStride + j] = x[i];
 }
 
 // ------------------------------------------------------------------ chain
@@ -141,7 +147,7 @@ __global__ void __launch_bounds__(kBig) large_chain_kernel(const T *L, int n, in
   for (int s = 0; s < kBig / kPanel; ++s) {
     const int c0 = base + s * kPanel;
     if (c0 >= n) break;  // uniform
-    const double *X = ws.X + (int64_t)(c0 / kPanel) * 1024 + rr * kPanel + part * 4;
+    const double *X = ws.X + (int64_t)(c0 / kPanel) * kXBlock + rr * kXStride + part * 4;
     const double x0 = X[0], x1 = X[1], x2 = X[2], x3 = X[3];
     // prefetch this thread's 32 entries of L[R][c0 .. c0+31] (needed only by rows below the block)
     const bool below = valid && R >= c0 + kPanel;

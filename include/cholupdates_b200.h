@@ -126,6 +126,9 @@ int chub_host_release(void);
 /* Force a kernel path: 0 = automatic, 1 = single-CTA kernels only, 2 = panel
  * (multi-kernel) path, 3 = persistent dataflow kernel.  Returns the previous value. */
 int chub_set_path(int path);
+/* Debug: per-CTA cycle counters of the persistent kernel (enabled by env CHUB_PROFILE=1),
+ * out[cta * 16 + slot]; workspace == NULL reads the internal workspace. */
+int chub_debug_profile(void *workspace, int64_t n, long long *out, int ctas);
 /* Number of kernels launched by this library since the counter was last reset. */
 int64_t chub_launch_count(int reset);
 

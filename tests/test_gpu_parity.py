@@ -107,7 +107,7 @@ def test_matches_golden_vectors(golden, op, order):
 
 
 # ------------------------------------------------- sizes across kernel paths, both layouts
-SIZES = [31, 32, 33, 64, 100, 257, 511, 512, 513, 1000, 1025, 2049]
+SIZES = [31, 32, 33, 64, 100, 257, 511, 512, 513, 514, 600, 1000, 1022, 1025, 2049, 3000]
 
 
 @pytest.mark.parametrize("n", SIZES)

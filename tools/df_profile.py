@@ -1,0 +1,46 @@
+"""Phase breakdown of the persistent dataflow kernel (cycle counters, CHUB_PROFILE=1).
+
+Usage (on the GPU box):  CHUB_PROFILE=1 python tools/df_profile.py [n] [layout C|F]
+"""
+import ctypes, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("CHUB_PROFILE", "1")
+from cholupdates_b200 import _lib
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+layout = sys.argv[2] if len(sys.argv) > 2 else "C"
+lib = _lib.require_device()
+lib.chub_debug_profile.restype = ctypes.c_int
+lib.chub_debug_profile.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int]
+dev = torch.device("cuda", 0)
+L = torch.tril(torch.randn(n, n, dtype=torch.float64, device=dev) / np.sqrt(n), -1)
+L.diagonal().copy_(1 + torch.rand(n, dtype=torch.float64, device=dev))
+if layout == "F":
+    L = L.t().contiguous().t()
+v = torch.randn(n, dtype=torch.float64, device=dev)
+status = torch.zeros(1, dtype=torch.int32, device=dev)
+lay = 0 if layout == "C" else 1
+for it in range(3):
+    vv = v.clone()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = lib.chub_update_f64(L.data_ptr(), n, n, lay, vv.data_ptr(), 0, None, 0, status.data_ptr(), None)
+    e1.record()
+    torch.cuda.synchronize()
+    assert rc == 0, lib.chub_last_error()
+print(f"n={n} layout={layout} update: {e0.elapsed_time(e1):.3f} ms, status={int(status.item())}")
+ctas = 148
+out = np.zeros(ctas * 16, dtype=np.int64)
+lib.chub_debug_profile(None, n, out.ctypes.data, ctas)
+P = out.reshape(ctas, 16)
+T = (n + 31) // 32
+ch = P[0]
+print(f"CHAIN (cycles per block row, T={T}): total {ch[0]/T:.0f} | A: wait tiles {ch[1]/T:.0f} | A: total(w0) {ch[2]/T:.0f} | "
+      f"A: poll wt (w4) {ch[4]/T:.0f} | barrier+B prep {ch[3]/T:.0f} | B: matvec+publish {ch[5]/T:.0f}")
+W = P[1:]
+steps = T + 4
+names = ["total", "wait tile (mbar)", "wait_read+issue load", "compute", "wait coefs", "fence+store+release", "w7 poll p", "w7 per panel total"]
+for k, name in enumerate(names):
+    col = W[:, k] / steps
+    print(f"WORKER {name:22s}: mean {col.mean():8.0f}  min {col.min():8.0f}  max {col.max():8.0f}  cycles/step")
