@@ -230,7 +230,9 @@ int chub_debug_profile(void *workspace, int64_t n, long long *out, int ctas) {
   }
   LargeWs ws = large_ws_carve(workspace, n);
   CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(out, reinterpret_cast<char *>(ws.flags) + 256, (size_t)ctas * 16 * sizeof(long long),
+  // ctas < 0: copy -ctas raw counters (cycle counters followed by the event trace)
+  const size_t count = ctas >= 0 ? (size_t)ctas * 16 : (size_t)(-ctas);
+  CK(cudaMemcpy(out, reinterpret_cast<char *>(ws.flags) + 256, count * sizeof(long long),
                 cudaMemcpyDeviceToHost));
   return 0;
 }

@@ -121,6 +121,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n"
                ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
 }
+// exactly one lane of a converged warp (the compiler then keeps TMA operands on the uniform path)
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -177,6 +183,13 @@ template <typename T> struct DfGeom {
   static constexpr int CPR = kPanel / EPC;            // 16-byte chunks per 32-element row segment
 };
 
+__device__ __forceinline__ long long df_gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+// event trace (CHUB_PROFILE): trace[ev * T + block_row] = %globaltimer (ns)
+#define DF_TRACE(ev, r) do { if (P.prof) P.prof[256 * 16 + (size_t)(ev) * P.T + (r)] = df_gtime(); } while (0)
 #define DF_PROF_T() (P.prof ? clock64() : 0LL)
 #define DF_PROF_ADD(slot, t_begin) do { if (P.prof) pacc[slot] += clock64() - (t_begin); } while (0)
 
@@ -684,7 +697,8 @@ template <typename T>
 __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsigned char *smem) {
   constexpr int HALVES = RmGeom<T>::HALVES, BOXC = RmGeom<T>::BOXC, EPC = RmGeom<T>::EPC;
   constexpr int CTILE = RmGeom<T>::CTILE;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
   const int T_ = P.T;
   long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
@@ -721,7 +735,7 @@ __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsign
     if (do_x) bulk_g2s(Xs + slot * kXBlock, P.ws.X + (int64_t)(j + 1) * kXBlock, kXBlock * 8u, bar);
   };
 
-  if (tid == kDfD * 32)
+  if (warp == kDfD + 1 && elect_one())
     for (int j = 0; j < kDfSlots - 1; ++j) issue_slot(j);
   if (warp == 0) {
     wvec[lane] = df_wait_value(P.ws.w + lane, P.status);
@@ -737,6 +751,10 @@ __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsign
     pbuf[lane] = p0;
     st_relaxed_f64(P.ws.p + lane, p0);
   }
+  // warp d polls wt one block row ahead without blocking: the load for wt_{j+2} is in flight
+  // while block column j is processed
+  unsigned long long wt_bits = kSentinelBits;
+  if (warp == kDfD && T_ > 1) wt_bits = ld_relaxed_u64(P.ws.w + kPanel + lane);
   named_sync(1, 256);
 
   const long long t_chain0 = DF_PROF_T();
@@ -759,13 +777,16 @@ __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsign
             const T *x = reinterpret_cast<const T *>(&raw);
             const int k0 = h * BOXC + c * EPC;
             if (EPC == 2) {
-              if (c & 1) { a2 += (double)x[0] * pj[k0]; a3 += (double)x[1] * pj[k0 + 1]; }
-              else       { a0 += (double)x[0] * pj[k0]; a1 += (double)x[1] * pj[k0 + 1]; }
+              const double2 pp = *reinterpret_cast<const double2 *>(pj + k0);
+              if (c & 1) { a2 += (double)x[0] * pp.x; a3 += (double)x[1] * pp.y; }
+              else       { a0 += (double)x[0] * pp.x; a1 += (double)x[1] * pp.y; }
             } else {
-              a0 += (double)x[0] * pj[k0];
-              a1 += (double)x[1] * pj[k0 + 1];
-              a2 += (double)x[2 % EPC] * pj[k0 + 2 % EPC];
-              a3 += (double)x[3 % EPC] * pj[k0 + 3 % EPC];
+              const double2 pp = *reinterpret_cast<const double2 *>(pj + k0);
+              const double2 pq = *reinterpret_cast<const double2 *>(pj + k0 + 2);
+              a0 += (double)x[0] * pp.x;
+              a1 += (double)x[1] * pp.y;
+              a2 += (double)x[2 % EPC] * pq.x;
+              a3 += (double)x[3 % EPC] * pq.y;
             }
           }
         }
@@ -773,13 +794,18 @@ __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsign
       }
       if (tid == 0) DF_PROF_ADD(2, tp);
     } else if (warp == kDfD) {
-      if (lane == 0) issue_slot(j + kDfSlots - 1);
       if (j + 1 < T_) {
         long long tq = DF_PROF_T();
-        wtb[((j + 1) & 1) * kPanel + lane] =
-            df_wait_value(P.ws.w + (int64_t)(j + 1) * kPanel + lane, P.status);
-        if (lane == 0) DF_PROF_ADD(4, tq);
+        const double wt = wt_bits != kSentinelBits
+                              ? __longlong_as_double((long long)wt_bits)
+                              : df_wait_value(P.ws.w + (int64_t)(j + 1) * kPanel + lane, P.status);
+        wtb[((j + 1) & 1) * kPanel + lane] = wt;
+        if (j + 2 < T_) wt_bits = ld_relaxed_u64(P.ws.w + (int64_t)(j + 2) * kPanel + lane);
+        __syncwarp();
+        if (lane == 0) { DF_PROF_ADD(4, tq); DF_TRACE(1, j + 1); }
       }
+    } else if (warp == kDfD + 1) {
+      if (elect_one()) issue_slot(j + kDfSlots - 1);
     }
     tp = DF_PROF_T();
     named_sync(1, 256);
@@ -797,15 +823,17 @@ __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsign
       for (int k = 0; k < kPanel; k += 4) {
         const double2 x = *reinterpret_cast<const double2 *>(X + k);
         const double2 y = *reinterpret_cast<const double2 *>(X + k + 2);
-        a0 += x.x * wvec[k];
-        a1 += x.y * wvec[k + 1];
-        a2 += y.x * wvec[k + 2];
-        a3 += y.y * wvec[k + 3];
+        const double2 u = *reinterpret_cast<const double2 *>(wvec + k);
+        const double2 z = *reinterpret_cast<const double2 *>(wvec + k + 2);
+        a0 += x.x * u.x;
+        a1 += x.y * u.y;
+        a2 += y.x * z.x;
+        a3 += y.y * z.y;
       }
       const double pr = (a0 + a1) + (a2 + a3);
       pbuf[(r & 1) * kPanel + lane] = pr;
       st_relaxed_f64(P.ws.p + (int64_t)r * kPanel + lane, pr);
-      if (tid == 0) DF_PROF_ADD(5, tp);
+      if (tid == 0) { DF_PROF_ADD(5, tp); DF_TRACE(2, r); }
     }
     named_sync(1, 256);
   }
@@ -826,33 +854,36 @@ inline size_t df_chain_rm_smem() {
 template <typename T, bool UPDATE>
 __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *tmap8,
                              unsigned char *smem) {
-  constexpr int HALVES = RmGeom<T>::HALVES, BOXC = RmGeom<T>::BOXC, EPC = RmGeom<T>::EPC;
+  constexpr int HALVES = RmGeom<T>::HALVES, BOXC = RmGeom<T>::BOXC;
   constexpr int CPT = RmGeom<T>::CPT, WTILE = RmGeom<T>::WTILE;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
   const int wkr = blockIdx.x - 1;
   const int n = P.n, T_ = P.T, Wk = P.Wk, nrw = P.nw;  // nrw = row warps (2 per 16-row block)
   const int64_t ld = P.ld;
-  const int nsteps = T_ + kDfD;
   long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
-  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);  // [kDfStages][nrw]
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);  // [nrw][kDfStages]
   unsigned long long *cfull = full + kDfStages * 2 * kRmMaxQ;               // [kDfCoefRing]
-  unsigned long long *cempty = cfull + kDfCoefRing;                         // [kDfCoefRing]
+  volatile int *prog = reinterpret_cast<volatile int *>(cfull + kDfCoefRing);  // [32] steps finished per row warp
+  volatile int *cprog = prog + 32;  // block columns whose coefficients are in the ring
   double *coef = reinterpret_cast<double *>(smem + 2048);                   // [kDfCoefRing][4][32]
   unsigned char *stages = smem + 2048 + kDfCoefRing * 4 * kPanel * 8;       // 1024-aligned
-  const size_t stage_bytes = (size_t)nrw * WTILE;
 
   if (tid == 0) {
     for (int i = 0; i < kDfStages * nrw; ++i) mbar_init(&full[i], 1);
-    for (int i = 0; i < kDfCoefRing; ++i) { mbar_init(&cfull[i], 32); mbar_init(&cempty[i], nrw); }
+    for (int i = 0; i < kDfCoefRing; ++i) mbar_init(&cfull[i], 32);
     fence_mbar_init();
   }
+  if (tid < 32) prog[tid] = tid < nrw ? 0 : 0x7fffffff;
+  if (tid == 0) *cprog = 0;
   __syncthreads();
   if (warp > nrw) return;
 
   if (warp == nrw) {
     // ---------------- coefficient warp (software-pipelined: the poll of block column s+1 is in
-    // flight while the coefficients of block column s are formed)
+    // flight while the coefficients of block column s are formed).  A ring slot is reused once
+    // every row warp has finished the step that last read it (prog[]); finished warps have left.
     double t_run = 1.0, S_run = 1.0;
     unsigned long long nbits = ld_relaxed_u64(P.ws.p + lane);
     double ndg = P.ws.dg[lane];
@@ -868,7 +899,16 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
         ndg = P.ws.dg[k + kPanel];
       }
       if (lane == 0) DF_PROF_ADD(6, tq);
-      if (pan >= kDfCoefRing) mbar_wait(&cempty[slot], (unsigned)((pan / kDfCoefRing - 1) & 1), P.status);
+      if (lane == 0 && wkr == 0) DF_TRACE(3, pan);
+      if (pan >= kDfCoefRing) {
+        // slot last used by block column pan-8, read for the last time at step pan-8+d
+        const int need = pan - kDfCoefRing + kDfD + 1;
+        const long long t0 = clock64();
+        while (__reduce_min_sync(0xffffffffu, prog[lane]) < need) {
+          if (clock64() - t0 > kWatchdogCycles) { atomicMax(P.status, CHUB_STATUS_INTERNAL); break; }
+        }
+        __threadfence_block();
+      }
       double *cf = coef + (size_t)slot * 4 * kPanel;
       cf[lane] = pk;
       if (UPDATE) {
@@ -888,7 +928,8 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
         cf[kPanel + lane] = ck;
         cf[2 * kPanel + lane] = sigk;
         cf[3 * kPanel + lane] = fabs(dg) * tk1 * rinv;
-        mbar_arrive(&cfull[slot]);
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); *cprog = pan + 1; }
         if (wkr == pan % Wk && k < n) {  // one worker per panel leaves rotg's z_k in v[k]
           const double Sk = (__popc(negmask & ((1u << lane) - 1u)) & 1) ? -S_run : S_run;
           const double nuk = Sk * dg * pk / sqrt(tk);
@@ -898,8 +939,10 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
         t_run = __shfl_sync(0xffffffffu, tk1, 31);
         if (__popc(negmask) & 1) S_run = -S_run;
       } else {
-        mbar_arrive(&cfull[slot]);
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); *cprog = pan + 1; }
       }
+      if (lane == 0 && wkr == 0) DF_TRACE(4, pan);
       if (lane == 0) DF_PROF_ADD(7, tq);
     }
     if (P.prof && lane == 0) {
@@ -912,118 +955,189 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
   // ---------------- row warps: warp = 8 consecutive rows, lane = (segment g, row r8)
   const int g = lane >> 3, r8 = lane & 7;
   const int64_t row0 = (((int64_t)wkr + (int64_t)(warp >> 1) * Wk) << 4) + ((warp & 1) << 3);
-  const bool warp_valid = row0 < n;
-  const int b = warp_valid ? (int)(row0 >> 5) : -1000000;
+  if (row0 >= n) {  // no rows here: leave (prog = "done" so that nobody waits for this warp)
+    if (lane == 0) prog[warp] = 0x7fffffff;
+    return;
+  }
+  const int b = (int)(row0 >> 5);
+  const int last_step = min(T_ + kDfD - 1, b + kDfD);  // my rows are complete after this step
   const int64_t row = row0 + r8;
-  double w = (warp_valid && row < n) ? P.ws.v0[row] : 0.0;
+  double w = row < n ? P.ws.v0[row] : 0.0;
   const int64_t row0_next = (((int64_t)wkr + (int64_t)((warp + 1) >> 1) * Wk) << 4) + (((warp + 1) & 1) << 3);
-  const bool prof_me = P.prof && lane == 0 && warp_valid && (warp + 1 >= nrw || row0_next >= n);
+  const bool prof_me = P.prof && lane == 0 && (warp + 1 >= nrw || row0_next >= n);
   // my 8 columns live in half `hh`, chunks cb .. cb+CPT-1 of the 128-byte box row
   const int hh = (g * 8 * (int)sizeof(T)) / 128;
   const int cb = ((g * 8 * (int)sizeof(T)) % 128) / 16;
+  unsigned long long *myfull = full + warp * kDfStages;
+  unsigned char *mytile = stages + (size_t)warp * (kDfStages * WTILE);  // [kDfStages][WTILE]
+  const unsigned my_off = hh * 1024 + r8 * 128;
 
-  auto issue_load = [&](int s) {  // lane 0 only
-    if (s >= nsteps) return;
-    void *bar = &full[(s % kDfStages) * nrw + warp];
+  auto issue_load = [&](int s, int st) {  // lane 0 only; st = s % kDfStages
+    if (s > last_step) return;
+    void *bar = &myfull[st];
     const int pan = df_panel_at(b, s);
     if (pan < 0) { mbar_arrive(bar); return; }
-    unsigned char *tile = stages + (size_t)(s % kDfStages) * stage_bytes + (size_t)warp * WTILE;
+    unsigned char *tile = mytile + st * WTILE;
     const int c0 = pan * kPanel;
-    int nh = 0;
-    for (int h = 0; h < HALVES; ++h) nh += (c0 + h * BOXC < n) ? 1 : 0;
-    mbar_arrive_expect_tx(bar, (unsigned)nh * 1024u);
-    for (int h = 0; h < nh; ++h) tma_load_2d(tile + h * 1024, tmap8, c0 + h * BOXC, (int)row0, bar);
+    if (HALVES == 2 && c0 + BOXC < n) {
+      mbar_arrive_expect_tx(bar, 2048u);
+      tma_load_2d(tile, tmap8, c0, (int)row0, bar);
+      tma_load_2d(tile + 1024, tmap8, c0 + BOXC, (int)row0, bar);
+    } else {
+      mbar_arrive_expect_tx(bar, 1024u);
+      tma_load_2d(tile, tmap8, c0, (int)row0, bar);
+    }
   };
 
-  if (lane == 0)
-    for (int s = 0; s < kDfStages - 2; ++s) issue_load(s);
-
-  const long long t_wk0 = DF_PROF_T();
-  for (int s = 0; s < nsteps; ++s) {
-    long long tp = DF_PROF_T();
-    if (lane == 0) {
-      bulk_wait_read<1>();  // the store of step s-2 has left shared memory: its stage is free
-      issue_load(s + kDfStages - 2);
-    }
-    if (prof_me) DF_PROF_ADD(2, tp);
-    tp = DF_PROF_T();
-    mbar_wait(&full[(s % kDfStages) * nrw + warp], (unsigned)((s / kDfStages) & 1), P.status);
-    if (prof_me) DF_PROF_ADD(1, tp);
-    tp = DF_PROF_T();
-    if (s < T_) mbar_wait(&cfull[s % kDfCoefRing], (unsigned)((s / kDfCoefRing) & 1), P.status);
-    if (prof_me) DF_PROF_ADD(4, tp);
-    tp = DF_PROF_T();
-
+  // One block column of my 8 rows: tile in shared memory -> updated tile (or, for the ragged
+  // diagonal tile, straight to global memory).  Returns true if the tile has to be TMA-stored.
+  auto do_step = [&](int s, int st) -> bool {
     const int pan = df_panel_at(b, s);
-    unsigned char *tile = stages + (size_t)(s % kDfStages) * stage_bytes + (size_t)warp * WTILE;
-    bool diag_step = false;
-    if (pan >= 0) {
-      const double *cf = coef + (size_t)(pan % kDfCoefRing) * 4 * kPanel + g * 8;
-      const int64_t c0 = (int64_t)pan * kPanel + g * 8;  // my first column
-      diag_step = (pan == b);
-      unsigned char *rowp = tile + hh * 1024 + r8 * 128;
-      int4 raw[CPT];
+    if (pan < 0) return false;
+    unsigned char *rowp = mytile + st * WTILE + my_off;
+    const double *cf = coef + (size_t)(pan % kDfCoefRing) * 4 * kPanel + g * 8;
+    const int64_t c0 = (int64_t)pan * kPanel + g * 8;  // my first column
+    const bool diag_step = (pan == b);
+    int4 raw[CPT];
 #pragma unroll
-      for (int i = 0; i < CPT; ++i)
-        raw[i] = *reinterpret_cast<const int4 *>(rowp + (((cb + i) ^ r8) << 4));
-      T *x = reinterpret_cast<T *>(raw);
-      double lo[8], pre[8];  // pre[j] = sum_{m<j} lo_m p_m within my segment
-      double run = 0.0;
+    for (int i = 0; i < CPT; ++i)
+      raw[i] = *reinterpret_cast<const int4 *>(rowp + (((cb + i) ^ r8) << 4));
+    T *x = reinterpret_cast<T *>(raw);
+    double pc[8], cc[8], sc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const double2 a = *reinterpret_cast<const double2 *>(cf + j);
+      const double2 c = *reinterpret_cast<const double2 *>(cf + kPanel + j);
+      const double2 d = *reinterpret_cast<const double2 *>(cf + 2 * kPanel + j);
+      pc[j] = a.x; pc[j + 1] = a.y; cc[j] = c.x; cc[j + 1] = c.y; sc[j] = d.x; sc[j + 1] = d.y;
+    }
+    double lo[8], pre[8];  // pre[j] = sum_{m<j} lo_m p_m within my segment
+    double run = 0.0;
+    if (!diag_step) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         lo[j] = (double)x[j];
         pre[j] = run;
-        const bool below = !diag_step || (c0 + j < row);
-        run += below ? lo[j] * cf[j] : 0.0;
+        run = fma(lo[j], pc[j], run);
       }
-      // exclusive scan of the four segment totals (lanes g*8 + r8, same r8)
-      double incl = run;
-      double y = __shfl_up_sync(0xffffffffu, incl, 8);
-      if (g >= 1) incl += y;
-      y = __shfl_up_sync(0xffffffffu, incl, 16);
-      if (g >= 2) incl += y;
-      const double total = __shfl_sync(0xffffffffu, incl, 24 + r8);
-      const double wseg = w - (incl - run);
-      if (UPDATE) {
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        lo[j] = (double)x[j];
+        pre[j] = run;
+        if (c0 + j < row) run = fma(lo[j], pc[j], run);
+      }
+    }
+    // exclusive scan of the four segment totals (lanes g*8 + r8, same r8)
+    double incl = run;
+    double y = __shfl_up_sync(0xffffffffu, incl, 8);
+    if (g >= 1) incl += y;
+    y = __shfl_up_sync(0xffffffffu, incl, 16);
+    if (g >= 2) incl += y;
+    const double total = __shfl_sync(0xffffffffu, incl, 24 + r8);
+    const double wseg = w - (incl - run);
+    w -= total;
+    // hand the residual over to the chain after the last far-left block column -- as early as
+    // possible: this store is on the chain <-> worker latency loop
+    if (s == b - kDfD - 1 && g == 0 && row < n) {
+      st_relaxed_f64(P.ws.w + row, df_sanitize(w));
+      if (lane == 0 && (row0 & 31) == 0) DF_TRACE(0, b);
+    }
+    if (UPDATE) {
+      if (!diag_step) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (T)fma(cc[j], lo[j], sc[j] * (wseg - pre[j]));
+#pragma unroll
+        for (int i = 0; i < CPT; ++i)
+          *reinterpret_cast<int4 *>(rowp + (((cb + i) ^ r8) << 4)) = raw[i];
+        return true;
+      }
+      if (row < n) {  // the diagonal tile is ragged: written straight to global memory
+        T *gp = L + row * ld + c0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int64_t col = c0 + j;
-          if (!diag_step || col < row) x[j] = (T)(cf[kPanel + j] * lo[j] + cf[2 * kPanel + j] * (wseg - pre[j]));
-          else if (col == row) x[j] = (T)cf[3 * kPanel + j];
-        }
-        if (!diag_step) {
-#pragma unroll
-          for (int i = 0; i < CPT; ++i)
-            *reinterpret_cast<int4 *>(rowp + (((cb + i) ^ r8) << 4)) = raw[i];
-        } else if (row < n) {  // the diagonal tile is ragged: written straight to global memory
-          T *gp = L + row * ld + c0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (c0 + j <= row) gp[j] = x[j];
+          if (col < row) gp[j] = (T)fma(cc[j], lo[j], sc[j] * (wseg - pre[j]));
+          else if (col == row) gp[j] = (T)cf[3 * kPanel + j];
         }
       }
-      w -= total;
-      // hand the residual over to the chain after the last far-left block column
-      if (s == b - kDfD - 1 && g == 0 && row < n) st_relaxed_f64(P.ws.w + row, df_sanitize(w));
     }
+    return false;
+  };
+
+  auto issue_store = [&](int s, int st) {  // lane 0 only
+    const int c0 = df_panel_at(b, s) * kPanel;
+    unsigned char *tile = mytile + st * WTILE;
+    tma_store_2d(tmap8, c0, (int)row0, tile);
+    if (HALVES == 2 && c0 + BOXC < n) tma_store_2d(tmap8, c0 + BOXC, (int)row0, tile + 1024);
+  };
+
+  // Two block columns (steps 2S, 2S+1) per iteration: the fixed per-step costs (waits, TMA issue,
+  // proxy fence, commit) are paid once per 64 columns.  Stages: pair S uses (2S) % 6, (2S+1) % 6;
+  // loads run one pair ahead, the stores of pair S-2 have left shared memory when pair S+1 loads.
+  static_assert(kDfStages == 6, "the pair schedule assumes a ring of 6 stages");
+  if (elect_one()) {
+    issue_load(0, 0);
+    issue_load(1, 1);
+  }
+  const long long t_wk0 = DF_PROF_T();
+  int st = 0;        // (2S) % 6
+  unsigned ph = 0;   // ((2S) / 6) & 1
+  for (int s = 0; s <= last_step; s += 2) {
+    long long tp = DF_PROF_T();
+    const int st1 = st + 1;                      // stage of step s+1 (st is even: no wrap)
+    const int stn = st + 2 == kDfStages ? 0 : st + 2;  // stages of the next pair
+    if (elect_one()) {
+      bulk_wait_read<1>();  // stores of pair S-2 (whose stages pair S+1 reuses) have been read
+      issue_load(s + 2, stn);
+      issue_load(s + 3, stn + 1);
+    }
+    __syncwarp();
+    if (prof_me) DF_PROF_ADD(2, tp);
+    tp = DF_PROF_T();
+    const bool two = s + 1 <= last_step;
+    mbar_wait(&myfull[st], ph, P.status);
+    if (two) mbar_wait(&myfull[st1], ph, P.status);
+    if (prof_me) DF_PROF_ADD(1, tp);
+    tp = DF_PROF_T();
+    {
+      // coefficients up to block column min(s+1, T-1): implies p_{s+1} is published, i.e. the
+      // chain has consumed everything these two steps overwrite
+      const int need = min(two ? s + 1 : s, T_ - 1) + 1;
+      if (*cprog < need) {
+        const long long t0 = clock64();
+        while (*cprog < need) {
+          if (clock64() - t0 > kWatchdogCycles) { atomicMax(P.status, CHUB_STATUS_INTERNAL); break; }
+        }
+      }
+      __threadfence_block();
+    }
+    if (prof_me) DF_PROF_ADD(4, tp);
+    if (prof_me && wkr == 0 && s < T_) DF_TRACE(5, s);
+    tp = DF_PROF_T();
+    const bool store0 = do_step(s, st);
+    const bool store1 = two ? do_step(s + 1, st1) : false;
     if (prof_me) DF_PROF_ADD(3, tp);
+    if (prof_me && wkr == 0 && s < T_) DF_TRACE(6, s);
     tp = DF_PROF_T();
 
     fence_proxy_async();  // my generic-proxy writes -> visible to the TMA (async proxy) store
     __syncwarp();
-    if (lane == 0) {
-      if (UPDATE && pan >= 0 && !diag_step) {
-        const int c0 = pan * kPanel;
-        for (int h = 0; h < HALVES; ++h)
-          if (c0 + h * BOXC < n) tma_store_2d(tmap8, c0 + h * BOXC, (int)row0, tile + h * 1024);
-      }
+    const bool st0 = __any_sync(0xffffffffu, store0), st1b = __any_sync(0xffffffffu, store1);
+    if (elect_one()) {
+      if (st0) issue_store(s, st);
+      if (st1b) issue_store(s + 1, st1);
       bulk_commit();
-      if (s >= kDfD && s - kDfD < T_) mbar_arrive(&cempty[(s - kDfD) % kDfCoefRing]);
+      __threadfence_block();
+      prog[warp] = s + 1 >= last_step ? 0x7fffffff : s + 2;
     }
+    __syncwarp();
+    st = stn;
+    if (st == 0) ph ^= 1u;
     if (prof_me) DF_PROF_ADD(5, tp);
   }
   if (prof_me) DF_PROF_ADD(0, t_wk0);
-  if (lane == 0) bulk_wait_all<0>();
+  if (elect_one()) bulk_wait_all<0>();
   if (prof_me) {
     for (int i = 0; i < 6; ++i) P.prof[(size_t)blockIdx.x * 16 + i] = pacc[i];
   }
@@ -1048,7 +1162,7 @@ df_kernel_rm(T *L, T *v, DfParams P, const __grid_constant__ CUtensorMap tmap8,
 }
 
 // ------------------------------------------------------------------ host side
-inline size_t dataflow_flag_bytes(int64_t n) { (void)n; return 256 + 256 * 16 * sizeof(long long); }
+inline size_t dataflow_flag_bytes(int64_t n) { return 256 + (256 * 16 + 8 * ((size_t)n / 32 + 2)) * sizeof(long long); }
 
 struct DfPlan {
   bool ok = false;
@@ -1187,7 +1301,7 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
   P.prof = nullptr;
   if (getenv("CHUB_PROFILE")) {
     P.prof = reinterpret_cast<long long *>(reinterpret_cast<char *>(ws.flags) + 256);
-    cudaMemsetAsync(P.prof, 0, 256 * 16 * sizeof(long long), st);
+    cudaMemsetAsync(P.prof, 0, (256 * 16 + 8 * ((size_t)n / 32 + 2)) * sizeof(long long), st);
   }
   cudaError_t e;
   if (rp.ok) {

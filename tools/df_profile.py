@@ -44,3 +44,24 @@ names = ["total", "wait tile (mbar)", "wait_read+issue load", "compute", "wait c
 for k, name in enumerate(names):
     col = W[:, k] / steps
     print(f"WORKER {name:22s}: mean {col.mean():8.0f}  min {col.min():8.0f}  max {col.max():8.0f}  cycles/step")
+
+# ---- event trace (globaltimer, ns) of the hand-off pipeline
+raw = np.zeros(256 * 16 + 8 * (n // 32 + 2), dtype=np.int64)
+lib.chub_debug_profile(None, n, raw.ctypes.data, -raw.size)
+tr = raw[256 * 16:][: 8 * T].reshape(8, T).astype(np.float64)
+names = ["wt published (owner)", "chain sees wt", "chain publishes p", "coef warp has p", "coefs ready",
+         "row warp starts step", "row warp ends step"]
+t0 = tr[2][tr[2] > 0].min()
+for r in (40, 41, 42, 43, 200, 201, 202, 203, 400, 401, 402):
+    if r >= T: continue
+    print(f"r={r:4d}: " + "  ".join(f"{names[e][:12]}={(tr[e, r] - t0) / 1e3:8.2f}us" if tr[e, r] > 0 else f"{names[e][:12]}=   --   " for e in range(7)))
+d = np.diff(tr[2][50:T - 8])
+print(f"chain period (p_r -> p_r+1): mean {d.mean():.0f} ns, median {np.median(d):.0f} ns")
+for (a, b, lab) in ((0, 1, "wt published -> chain sees it"), (1, 2, "chain sees wt -> p published"), (2, 3, "p published -> coef warp has it"),
+                    (3, 4, "coef warp has p -> coefs ready"), (4, 5, "coefs ready -> row warp starts step"), (5, 6, "row warp step compute")):
+    m = (tr[a][50:T - 8] > 0) & (tr[b][50:T - 8] > 0)
+    x = (tr[b][50:T - 8] - tr[a][50:T - 8])[m]
+    print(f"{lab:40s}: mean {x.mean():8.0f} ns  median {np.median(x):8.0f}  min {x.min():8.0f}  max {x.max():8.0f}")
+x = tr[5][50:T - 8] - tr[0][50:T - 8]
+m = (tr[0][50:T - 8] > 0) & (tr[5][50:T - 8] > 0)
+print(f"wt_r published -> row warp starts step r: mean {x[m].mean():.0f} ns")
