@@ -23,19 +23,34 @@ __device__ __forceinline__ int64_t idx(int64_t i, int64_t j, int64_t ld) {
 // column" (thread-per-row compute).
 __device__ __forceinline__ int tile_off(int r, int c) { return r * kPanel + (c ^ (r & 31)); }
 
-// global (row-major) -> swizzled shared tile of [rows][32]
+// Element-sized cp.async (4 or 8 bytes): global -> shared without a register round trip, so that
+// all of a thread's loads are in flight at once.
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T *smem_dst, const T *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;\n" ::: "memory");
+}
+
+// global (row-major) -> swizzled shared tile of [rows][32]; complete after the caller's
+// __syncthreads() (the wait for this thread's copies is inside)
 template <typename T, int NT>
 __device__ __forceinline__ void tile_load_rm(T *tile, const T *L, int64_t ld, int r0, int rows,
                                              int c0, int bw) {
   for (int e = threadIdx.x; e < rows * kPanel; e += NT) {
     int rr = e >> 5, cc = e & 31;
-    if (cc < bw) tile[tile_off(rr, cc)] = L[(int64_t)(r0 + rr) * ld + c0 + cc];
+    if (cc < bw) cp_async_elem(tile + tile_off(rr, cc), L + (int64_t)(r0 + rr) * ld + c0 + cc);
   }
+  cp_async_wait_all();
 }
 // swizzled shared tile -> global (row-major); never writes above the diagonal
 template <typename T, int NT>
 __device__ __forceinline__ void tile_store_rm(const T *tile, T *L, int64_t ld, int r0, int rows,
                                               int c0, int bw) {
+#pragma unroll 8
   for (int e = threadIdx.x; e < rows * kPanel; e += NT) {
     int rr = e >> 5, cc = e & 31;
     if (cc < bw && c0 + cc <= r0 + rr) L[(int64_t)(r0 + rr) * ld + c0 + cc] = tile[tile_off(rr, cc)];

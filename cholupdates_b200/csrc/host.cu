@@ -6,10 +6,14 @@
 // the diagonal, so PCIe carries ~n^2/2 elements each way instead of n^2.  The strict upper
 // triangle of the host array is never modified.
 
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
-#include "common.cuh"
+#include <vector>
+
+#include "large.cuh"
 
 namespace {
 
@@ -18,8 +22,13 @@ struct HostCache {
   size_t L_bytes = 0;
   void *v = nullptr;
   size_t v_bytes = 0;
+  void *ws = nullptr;
+  size_t ws_bytes = 0;
   int32_t *status = nullptr;
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr;      // compute
+  cudaStream_t st_in = nullptr;   // host -> device copies
+  cudaStream_t st_out = nullptr;  // device -> host copies
+  std::vector<cudaEvent_t> ev_in, ev_done;
 };
 std::mutex h_mu;
 HostCache h_cache[64];
@@ -36,6 +45,8 @@ thread_local char h_err[256] = "";
 
 int ensure(HostCache &c, size_t Lb, size_t vb) {
   if (!c.st) HCK(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
+  if (!c.st_in) HCK(cudaStreamCreateWithFlags(&c.st_in, cudaStreamNonBlocking));
+  if (!c.st_out) HCK(cudaStreamCreateWithFlags(&c.st_out, cudaStreamNonBlocking));
   if (!c.status) HCK(cudaMalloc((void **)&c.status, sizeof(int32_t)));
   if (c.L_bytes < Lb) {
     if (c.L) HCK(cudaFree(c.L));
@@ -73,10 +84,77 @@ int copy_tri(char *dst, const char *src, int64_t n, int64_t ld_dst, int64_t ld_s
   return 0;
 }
 
+// ---- streamed update: H2D of column panel J+1, the kernels of panel J and D2H of panel J-1
+// overlap on three streams.  In the right-looking panel formulation (large.cuh) panel J only
+// touches its own 256 columns (plus the n-vector w), so a panel can be finished and shipped back as
+// soon as it has arrived; PCIe runs full duplex and the update costs about one H2D of the triangle.
+constexpr int64_t kStreamMinN = 2048;
+
+template <typename T, int LAYOUT>
+int run_host_update_streamed(HostCache &c, T *Lh, int64_t n, int64_t ld, T *vh, int32_t *status) {
+  using namespace chub;
+  const size_t es = sizeof(T);
+  const int ni = (int)n;
+  const size_t need_ws = large_ws_doubles(n) * sizeof(double) + 4096;
+  if (c.ws_bytes < need_ws) {
+    if (c.ws) HCK(cudaFree(c.ws));
+    c.ws = nullptr; c.ws_bytes = 0;
+    HCK(cudaMalloc(&c.ws, need_ws));
+    c.ws_bytes = need_ws;
+  }
+  const int nJ = (ni + kBig - 1) / kBig;
+  while ((int)c.ev_in.size() < nJ + 1) {
+    cudaEvent_t a, b;
+    HCK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    HCK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    c.ev_in.push_back(a);
+    c.ev_done.push_back(b);
+  }
+  LargeWs ws = large_ws_carve(c.ws, n);
+  T *Ld = (T *)c.L;
+  T *vd = (T *)c.v;
+  const int64_t ldd = n;  // dense device copy
+  HCK(cudaMemsetAsync(c.status, 0, sizeof(int32_t), c.st));
+  HCK(cudaMemcpyAsync(vd, vh, (size_t)n * es, cudaMemcpyHostToDevice, c.st));
+  large_prepare_kernel<T, LAYOUT><<<(ni + 255) / 256, 256, 0, c.st>>>(Ld, ni, ldd, vd, ws, 0, c.status);
+  for (int J = 0; J < nJ; ++J) {
+    const int64_t j0 = (int64_t)J * kBig;
+    const int64_t bw = std::min<int64_t>(kBig, n - j0);
+    // rectangle rows [j0, n) x columns [j0, j0 + bw)
+    size_t off_d, off_h, width, height;
+    if (LAYOUT == CHUB_ROW_MAJOR) {
+      off_d = (size_t)(j0 * ldd + j0); off_h = (size_t)(j0 * ld + j0);
+      width = (size_t)bw * es; height = (size_t)(n - j0);
+    } else {
+      off_d = (size_t)(j0 + j0 * ldd); off_h = (size_t)(j0 + j0 * ld);
+      width = (size_t)(n - j0) * es; height = (size_t)bw;
+    }
+    HCK(cudaMemcpy2DAsync(Ld + off_d, (size_t)ldd * es, Lh + off_h, (size_t)ld * es, width, height,
+                          cudaMemcpyHostToDevice, c.st_in));
+    HCK(cudaEventRecord(c.ev_in[J], c.st_in));
+    HCK(cudaStreamWaitEvent(c.st, c.ev_in[J], 0));
+    large_invdiag_kernel<T, LAYOUT><<<(kBig / 32 + 3) / 4, 128, 0, c.st>>>(Ld, ni, ldd, ws, c.status,
+                                                                           (int)(j0 / 32), kBig / 32);
+    large_chain_kernel<T, LAYOUT, true><<<1, kBig, 0, c.st>>>(Ld, ni, ldd, vd, ws, J, c.status);
+    large_trail_kernel<T, LAYOUT, true><<<(unsigned)((n - j0 + 127) / 128), 128, 0, c.st>>>(Ld, ni, ldd, ws, J,
+                                                                                           c.status);
+    HCK(cudaGetLastError());
+    HCK(cudaEventRecord(c.ev_done[J], c.st));
+    HCK(cudaStreamWaitEvent(c.st_out, c.ev_done[J], 0));
+    HCK(cudaMemcpy2DAsync(Lh + off_h, (size_t)ld * es, Ld + off_d, (size_t)ldd * es, width, height,
+                          cudaMemcpyDeviceToHost, c.st_out));
+  }
+  HCK(cudaMemcpyAsync(vh, vd, (size_t)n * es, cudaMemcpyDeviceToHost, c.st_out));
+  HCK(cudaMemcpyAsync(status, c.status, sizeof(int32_t), cudaMemcpyDeviceToHost, c.st_out));
+  HCK(cudaStreamSynchronize(c.st_out));
+  HCK(cudaStreamSynchronize(c.st));
+  return 0;
+}
+
 typedef int (*dev_fn)(void *, int64_t, int64_t, int, void *, int, void *, size_t, int32_t *, void *);
 
-int run_host(dev_fn fn, size_t es, void *L, int64_t n, int64_t ld, int layout, void *v, int flags,
-             int32_t *status) {
+int run_host(dev_fn fn, bool is_update, size_t es, void *L, int64_t n, int64_t ld, int layout, void *v,
+             int flags, int32_t *status) {
   if (!status || n < 0 || ld < n) return (int)cudaErrorInvalidValue;
   *status = 0;
   if (n == 0) return 0;
@@ -86,6 +164,24 @@ int run_host(dev_fn fn, size_t es, void *L, int64_t n, int64_t ld, int layout, v
   HostCache &c = h_cache[dev & 63];
   int rc = ensure(c, (size_t)n * n * es, (size_t)n * es);
   if (rc) return rc;
+  if (flags & CHUB_FLAG_CHECK_DIAG) {  // _arg_validation.py:18-22, on the host copy: nothing is touched
+    const char *d = (const char *)L;
+    for (int64_t i = 0; i < n; ++i) {
+      const char *e = d + (size_t)(i * ld + i) * es;
+      const bool zero = es == 8 ? *(const double *)e == 0.0 : *(const float *)e == 0.0f;
+      if (zero) { *status = CHUB_STATUS_ZERO_DIAG; return 0; }
+    }
+    flags &= ~CHUB_FLAG_CHECK_DIAG;
+  }
+  if (is_update && n >= kStreamMinN && !getenv("CHUB_HOST_NO_STREAM")) {
+    if (es == 8)
+      return layout == CHUB_ROW_MAJOR
+                 ? run_host_update_streamed<double, CHUB_ROW_MAJOR>(c, (double *)L, n, ld, (double *)v, status)
+                 : run_host_update_streamed<double, CHUB_COL_MAJOR>(c, (double *)L, n, ld, (double *)v, status);
+    return layout == CHUB_ROW_MAJOR
+               ? run_host_update_streamed<float, CHUB_ROW_MAJOR>(c, (float *)L, n, ld, (float *)v, status)
+               : run_host_update_streamed<float, CHUB_COL_MAJOR>(c, (float *)L, n, ld, (float *)v, status);
+  }
   // device copy is dense (ld = n)
   rc = copy_tri((char *)c.L, (const char *)L, n, n, ld, layout, es, cudaMemcpyHostToDevice, c.st);
   if (rc) return rc;
@@ -112,16 +208,16 @@ int run_host(dev_fn fn, size_t es, void *L, int64_t n, int64_t ld, int layout, v
 extern "C" {
 
 int chub_update_host_f64(void *L, int64_t n, int64_t ld, int layout, void *v, int flags, int32_t *status) {
-  return run_host(chub_update_f64, 8, L, n, ld, layout, v, flags, status);
+  return run_host(chub_update_f64, true, 8, L, n, ld, layout, v, flags, status);
 }
 int chub_update_host_f32(void *L, int64_t n, int64_t ld, int layout, void *v, int flags, int32_t *status) {
-  return run_host(chub_update_f32, 4, L, n, ld, layout, v, flags, status);
+  return run_host(chub_update_f32, true, 4, L, n, ld, layout, v, flags, status);
 }
 int chub_downdate_host_f64(void *L, int64_t n, int64_t ld, int layout, void *v, int flags, int32_t *status) {
-  return run_host(chub_downdate_f64, 8, L, n, ld, layout, v, flags, status);
+  return run_host(chub_downdate_f64, false, 8, L, n, ld, layout, v, flags, status);
 }
 int chub_downdate_host_f32(void *L, int64_t n, int64_t ld, int layout, void *v, int flags, int32_t *status) {
-  return run_host(chub_downdate_f32, 4, L, n, ld, layout, v, flags, status);
+  return run_host(chub_downdate_f32, false, 4, L, n, ld, layout, v, flags, status);
 }
 
 int chub_host_release(void) {
@@ -131,8 +227,9 @@ int chub_host_release(void) {
   HostCache &c = h_cache[dev & 63];
   if (c.L) cudaFree(c.L);
   if (c.v) cudaFree(c.v);
-  c.L = c.v = nullptr;
-  c.L_bytes = c.v_bytes = 0;
+  if (c.ws) cudaFree(c.ws);
+  c.L = c.v = c.ws = nullptr;
+  c.L_bytes = c.v_bytes = c.ws_bytes = 0;
   return 0;
 }
 

@@ -90,13 +90,14 @@ __global__ void large_prepare_kernel(const T *L, int n, int64_t ld, const T *v, 
 // by forward substitution.  Blocks that stick out of the matrix are padded with the identity.
 template <typename T, int LAYOUT>
 __global__ void __launch_bounds__(128) large_invdiag_kernel(const T *L, int n, int64_t ld,
-                                                             LargeWs ws, const int32_t *status) {
+                                                             LargeWs ws, const int32_t *status,
+                                                             int blk0 = 0, int nblk = 1 << 30) {
   __shared__ double Ls[4][kPanel][kPanel + 1];
   if (*status != 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int blk = blockIdx.x * 4 + warp;
+  const int blk = blk0 + blockIdx.x * 4 + warp;
   const int nb = (n + 31) / 32;
-  if (blk >= nb) return;
+  if (blk >= nb || blk >= blk0 + nblk) return;
   const int c0 = blk * kPanel;
   // stage the block (lane = column for row-major reads, lane = row for column-major reads)
   for (int r = 0; r < kPanel; ++r) {

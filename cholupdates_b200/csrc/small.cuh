@@ -49,7 +49,9 @@ __global__ void __launch_bounds__(NT) small_update_kernel(SmallArgs<T> a) {
   T *nu = reinterpret_cast<T *>(smem_raw);  // running v (A.2: nu_i), [n_pad]
   T *cc = nu + n_pad;                       // panel cosines [32]
   T *ss = cc + kPanel;                      // panel sines   [32]
-  T *tile = ss + kPanel;                    // [NT][32], row-major staging only
+  T *pp = ss + kPanel;                      // block p = L_D^{-1} nu [32]
+  T *sgm = pp + kPanel;                     // sigma_k [32]
+  T *tile = sgm + kPanel;                   // [NT][32], row-major staging only
 
   if (a.flags & CHUB_FLAG_CHECK_DIAG) {  // _arg_validation.py:18-22
     if (small_zero_diag<T, LAYOUT, NT>(L, n, ld)) {
@@ -64,37 +66,77 @@ __global__ void __launch_bounds__(NT) small_update_kernel(SmallArgs<T> a) {
     const int bw = min(kPanel, n - c0);
     if (warp == 0) {
       // Diagonal block: lane = row c0 + lane, its entries L[row][c0 .. row] in registers.
+      // The 32 rotations of the block are formed WITHOUT a sqrt / division per column on the
+      // sequential chain, through their closed form (restarted per block, t_0 = 1):
+      //   p = L_D^{-1} nu (forward substitution: one multiply, one shuffle, one FMA per column),
+      //   t_{k+1} = t_k + p_k^2 (warp scan),  c_k = sgn_k sqrt(t_k/t_{k+1}),
+      //   s_k = S_k sgn_k p_k / sqrt(t_{k+1}),  L'_kk = |L_kk| sqrt(t_{k+1}/t_k),
+      //   L'_ik = c_k L_ik + sgn_k p_k/sqrt(t_k t_{k+1}) w_i^{(k)}   (== c_k L_ik + s_k nu_i^{(k)}),
+      // which is rotg + sign fix + rot of .pyx:101-140 for these 32 columns.
       const int row = c0 + lane;
       const bool valid = lane < bw;
       T Lrow[kPanel];
+      T dii = T(1);
 #pragma unroll
-      for (int k = 0; k < kPanel; ++k)
+      for (int k = 0; k < kPanel; ++k) {
         Lrow[k] = (valid && k <= lane) ? L[idx<LAYOUT>(row, c0 + k, ld)] : T(0);
-      T w = valid ? nu[row] : T(0);
-      T za = T(0), zb = T(0), zc = T(1), zs = T(0);
+        if (k == lane && valid) dii = Lrow[k];
+      }
+      const T w0 = valid ? nu[row] : T(0);
+      const T rinv = T(1) / dii;
+      T w = w0, pk_mine = T(0);
 #pragma unroll
       for (int k = 0; k < kPanel; ++k) {
         if (k < bw) {  // uniform
-          T akk = shfl(Lrow[k], k);  // L[k][k]   (.pyx:101: rotg(L_ptr, v_ptr, &c, &s))
-          T b = shfl(w, k);          // v[k]
-          T c, s, r;
-          givens(akk, b, c, s, r);   // rotg + sign fix (.pyx:101-113)
-          if (lane == k) {
-            za = akk; zb = b; zc = c; zs = s;
-            Lrow[k] = r;
-          } else if (lane > k) {     // rot on L[k+1:, k], v[k+1:]  (.pyx:129-140)
-            T x = Lrow[k];
-            Lrow[k] = c * x + s * w;
-            w = c * w - s * x;
-          }
-          if (lane == 0) { cc[k] = c; ss[k] = s; }
+          const T pk = shfl(w * rinv, k);
+          if (lane == k) pk_mine = pk;
+          else if (lane > k) w -= Lrow[k] * pk;
+        }
+      }
+      // coefficients of all columns of the block at once (fp64 arithmetic)
+      const double pd = (double)pk_mine;
+      double incl = pd * pd;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 0.0;
+      const double tk = 1.0 + excl, tk1 = 1.0 + incl;
+      const bool neg = dii < T(0);
+      const unsigned negmask = __ballot_sync(0xffffffffu, neg);
+      const double Sk = (__popc(negmask & ((1u << lane) - 1u)) & 1) ? -1.0 : 1.0;
+      const double sgn = neg ? -1.0 : 1.0;
+      const double isq = rsqrt(tk), r1 = rsqrt(tk1);
+      const double ck = sgn * tk * isq * r1;          // sgn sqrt(t_k / t_{k+1})
+      const double sigk = sgn * pd * isq * r1;        // sgn p_k / sqrt(t_k t_{k+1})
+      const double sk = Sk * sgn * pd * r1;           // rotation sine seen by the rows below
+      const double dnew = fabs((double)dii) * tk1 * isq * r1;
+      cc[lane] = (T)ck;
+      ss[lane] = (T)sk;
+      pp[lane] = pk_mine;
+      sgm[lane] = (T)sigk;
+      __syncwarp();
+      // second pass (lane-parallel): rebuild w_i^{(k)} and rotate the block's own entries
+      T w2 = w0;
+#pragma unroll
+      for (int k = 0; k < kPanel; ++k) {
+        if (k < bw && lane > k) {
+          const T x = Lrow[k];
+          Lrow[k] = cc[k] * x + sgm[k] * w2;
+          w2 -= x * pp[k];
         }
       }
       if (valid) {
 #pragma unroll
-        for (int k = 0; k < kPanel; ++k)
-          if (k <= lane) L[idx<LAYOUT>(row, c0 + k, ld)] = Lrow[k];
-        v[row] = rotg_z(za, zb, zc, zs);  // what rotg leaves in v[k]
+        for (int k = 0; k < kPanel; ++k) {
+          if (k < lane) L[idx<LAYOUT>(row, c0 + k, ld)] = Lrow[k];
+          else if (k == lane) L[idx<LAYOUT>(row, c0 + k, ld)] = (T)dnew;
+        }
+        // what rotg leaves in v[k]: z from (a, b) = (L_kk, nu_k)
+        const double nuk = Sk * (double)dii * pd * isq;
+        v[row] = (T)rotg_z<double>((double)dii, nuk, ck, sk);
       }
     }
     __syncthreads();
@@ -141,7 +183,7 @@ __global__ void __launch_bounds__(NT) small_update_kernel(SmallArgs<T> a) {
 template <typename T>
 inline size_t small_update_smem(int n, int layout) {
   size_t n_pad = (n + 31) & ~31;
-  return (n_pad + 2 * kPanel + (layout == CHUB_ROW_MAJOR ? (size_t)kSmallNT * kPanel : 0)) * sizeof(T);
+  return (n_pad + 4 * kPanel + (layout == CHUB_ROW_MAJOR ? (size_t)kSmallNT * kPanel : 0)) * sizeof(T);
 }
 
 // ---------------------------------------------------------------- downdate
@@ -183,10 +225,15 @@ __global__ void __launch_bounds__(NT) small_downdate_kernel(SmallArgs<T> a) {
       for (int k = 0; k < kPanel; ++k)
         Lrow[k] = (valid && k <= lane) ? L[idx<LAYOUT>(row, c0 + k, ld)] : T(1);
       T w = valid ? p[row] : T(0);
+      T dii = T(1);
+#pragma unroll
+      for (int k = 0; k < kPanel; ++k)
+        if (k == lane && valid) dii = Lrow[k];
+      const T rinv = T(1) / dii;
 #pragma unroll
       for (int k = 0; k < kPanel; ++k) {
         if (k < bw) {
-          T pk = shfl(w, k) / shfl(Lrow[k], k);
+          const T pk = shfl(w * rinv, k);
           if (lane == k) w = pk;
           else if (lane > k) w -= Lrow[k] * pk;
         }

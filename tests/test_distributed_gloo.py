@@ -1,0 +1,101 @@
+"""world_size-2 gloo test (CPU) of the batched multi-GPU mode's host logic: balanced sharding by rank,
+local processing of the shard, all-gather of the per-factor status vector, identical exception on
+every rank.  The local kernel call is replaced by the oracle (no GPU here); on the B200 box the same
+code path runs with the CUDA kernels (tests/test_gpu_parity.py covers those)."""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from cholupdates_b200.distributed import shard_bounds  # noqa: E402
+
+
+def test_shard_bounds_cover_the_batch_exactly():
+    for batch in (0, 1, 7, 8, 8192, 8193):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_bounds(batch, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == batch
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 == b0
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(8, 2, 2)
+
+
+def _oracle_batched(op):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import seeger_oracle as oracle
+
+    def fn(L, v, check_diag=True, overwrite_L=False, overwrite_v=False, raise_on_error=False):
+        Ln, vn = L.numpy().copy(), v.numpy().copy()
+        status = np.zeros(Ln.shape[0], dtype=np.int32)
+        for b in range(Ln.shape[0]):
+            if check_diag and np.any(np.diag(Ln[b]) == 0):
+                status[b] = 1
+                continue
+            try:
+                Lb = np.ascontiguousarray(Ln[b])
+                getattr(oracle, op)(Lb, vn[b])
+                Ln[b] = Lb
+            except np.linalg.LinAlgError:
+                status[b] = 2
+                Ln[b] = L.numpy()[b]
+        return torch.from_numpy(Ln), torch.from_numpy(status)
+
+    return fn
+
+
+def _worker(rank, world, port, tmpdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from cholupdates_b200.distributed import shard_bounds, sharded_batched
+        from helpers import downdate_vector, synth_factor
+
+        B, n = 7, 24  # uneven split: 4 + 3
+        Ls = np.stack([synth_factor(n, [0, b]) for b in range(B)])
+        vs = np.stack([downdate_vector(Ls[b], [1, b]) for b in range(B)])
+        vs[5] = downdate_vector(Ls[5], 3, norm_p=1.3)  # lives on rank 1: not positive definite
+        Ls[1, 2, 2] = 0.0                               # lives on rank 0: zero on the diagonal
+        lo, hi = shard_bounds(B, rank, world)
+        L_loc, v_loc = torch.from_numpy(Ls[lo:hi].copy()), torch.from_numpy(vs[lo:hi].copy())
+        out, status = sharded_batched("downdate", L_loc, v_loc, raise_on_error=False,
+                                      local_fn=_oracle_batched("downdate"))
+        assert status.tolist() == [0, 1, 0, 0, 0, 2, 0], status.tolist()
+        # local results: failing factors untouched, the others changed
+        for b in range(lo, hi):
+            same = np.array_equal(out[b - lo].numpy(), Ls[b])
+            assert same == (b in (1, 5)), b
+        # every rank raises the same error
+        try:
+            sharded_batched("downdate", L_loc, v_loc, local_fn=_oracle_batched("downdate"))
+            raised = ""
+        except np.linalg.LinAlgError as exc:
+            raised = str(exc)
+        assert "factor 1 of the global batch; 2 failed" in raised, raised
+        with open(os.path.join(tmpdir, f"ok{rank}"), "w") as f:
+            f.write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_batched_world_size_2_gloo(tmp_path):
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
