@@ -12,6 +12,7 @@
 
 #include "dataflow.cuh"
 #include "large.cuh"
+#include "rowcyclic.cuh"
 #include "small.cuh"
 
 using namespace chub;
@@ -185,6 +186,56 @@ int run_batched(void *Lv, int64_t n, int64_t ld, int64_t stride_L, int layout, v
 
 }  // namespace
 
+// ---- block-row-cyclic single factor (per-panel pieces; the host driver does the broadcast)
+namespace {
+template <typename T>
+int rc_prepare(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, void *v, void *workspace,
+               int flags, int32_t *status, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  LargeWs ws = large_ws_carve(workspace, n);
+  CK(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+  rc_prepare_kernel<T><<<(unsigned)((m_loc + 255) / 256), 256, 0, st>>>((const T *)A, (int)m_loc, (int)n, ld, G, rank,
+                                                                        (const T *)v, ws, flags, status);
+  LAUNCHED();
+  return 0;
+}
+template <typename T>
+int rc_panel_owner(void *A, int64_t n, int64_t ld, int G, int rank, int J, void *v_out, void *workspace,
+                   double *payload, int32_t *status, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  LargeWs ws = large_ws_carve(workspace, n);
+  // the diagonal block of panel J is local block q = J / G; shift the base so that the panel
+  // kernels can address it with GLOBAL row indices
+  const int64_t q = J / G;
+  (void)rank;
+  T *Lsh = (T *)A + (q * kRcBlock - (int64_t)J * kRcBlock) * ld;
+  large_invdiag_kernel<T, CHUB_ROW_MAJOR><<<(kBig / 32 + 3) / 4, 128, 0, st>>>(Lsh, (int)n, ld, ws, status,
+                                                                                J * (kBig / 32), kBig / 32);
+  LAUNCHED();
+  large_chain_kernel<T, CHUB_ROW_MAJOR, true><<<1, kBig, 0, st>>>(Lsh, (int)n, ld, (T *)v_out, ws, J, status);
+  LAUNCHED();
+  rc_pack_kernel<<<1, kBig, 0, st>>>(ws, J, payload, status);
+  LAUNCHED();
+  return 0;
+}
+template <typename T>
+int rc_panel_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int J, int is_owner,
+                   void *workspace, const double *payload, int32_t *status, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  LargeWs ws = large_ws_carve(workspace, n);
+  if (!is_owner) {
+    rc_unpack_kernel<<<1, kBig, 0, st>>>(ws, J, payload, status);
+    LAUNCHED();
+  }
+  if (m_loc > 0) {
+    rc_trail_kernel<T><<<(unsigned)((m_loc + 127) / 128), 128, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, ws, J,
+                                                                       status);
+    LAUNCHED();
+  }
+  return 0;
+}
+}  // namespace
+
 extern "C" {
 
 int chub_version(void) { return 100; }
@@ -238,6 +289,33 @@ int chub_debug_profile(void *workspace, int64_t n, long long *out, int ctas) {
 }
 int64_t chub_launch_count(int reset) {
   return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int chub_rc_payload_doubles(void) { return kRcPayload; }
+int chub_rc_block_rows(void) { return kRcBlock; }
+int chub_rc_prepare_f64(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, void *v, void *workspace,
+                        int flags, int32_t *status, void *stream) {
+  return rc_prepare<double>(A, m_loc, n, ld, G, rank, v, workspace, flags, status, stream);
+}
+int chub_rc_prepare_f32(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, void *v, void *workspace,
+                        int flags, int32_t *status, void *stream) {
+  return rc_prepare<float>(A, m_loc, n, ld, G, rank, v, workspace, flags, status, stream);
+}
+int chub_rc_panel_owner_f64(void *A, int64_t n, int64_t ld, int G, int rank, int J, void *v_out, void *workspace,
+                            double *payload, int32_t *status, void *stream) {
+  return rc_panel_owner<double>(A, n, ld, G, rank, J, v_out, workspace, payload, status, stream);
+}
+int chub_rc_panel_owner_f32(void *A, int64_t n, int64_t ld, int G, int rank, int J, void *v_out, void *workspace,
+                            double *payload, int32_t *status, void *stream) {
+  return rc_panel_owner<float>(A, n, ld, G, rank, J, v_out, workspace, payload, status, stream);
+}
+int chub_rc_panel_apply_f64(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int J, int is_owner,
+                            void *workspace, const double *payload, int32_t *status, void *stream) {
+  return rc_panel_apply<double>(A, m_loc, n, ld, G, rank, J, is_owner, workspace, payload, status, stream);
+}
+int chub_rc_panel_apply_f32(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int J, int is_owner,
+                            void *workspace, const double *payload, int32_t *status, void *stream) {
+  return rc_panel_apply<float>(A, m_loc, n, ld, G, rank, J, is_owner, workspace, payload, status, stream);
 }
 
 #define DEFINE_SINGLE(NAME, T, UPD)                                                              \

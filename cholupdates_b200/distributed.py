@@ -81,3 +81,139 @@ def sharded_batched(
                     else "The downdated matrix is not positive definite.")
             raise np.linalg.LinAlgError(f"{what} (factor {b} of the global batch; {bad.numel()} failed)")
     return L_out, status_global
+
+
+# =====================================================================================
+# One huge factor, block-row-cyclic over the ranks (BASELINE.json configs[4])
+# =====================================================================================
+RC_BLOCK = 256  # rows per distribution block = columns per panel (csrc/rowcyclic.cuh: kRcBlock)
+
+
+def rc_owned_rows(n: int, rank: int, world_size: int):
+    """Global row indices owned by ``rank`` (blocks of 256 rows dealt cyclically), in local order."""
+    import numpy as np
+
+    rows = []
+    for blk in range(rank, (n + RC_BLOCK - 1) // RC_BLOCK, world_size):
+        rows.append(np.arange(blk * RC_BLOCK, min(n, (blk + 1) * RC_BLOCK)))
+    return np.concatenate(rows) if rows else np.zeros(0, dtype=np.int64)
+
+
+class _CudaRowCyclicBackend:
+    """Per-panel pieces through the C ABI (``chub_rc_*``, include/cholupdates_b200.h)."""
+
+    def __init__(self, A_local, n, rank, world):
+        import torch
+
+        from . import _lib
+
+        self.lib = _lib.require_device()
+        self.torch = torch
+        self.A, self.n, self.rank, self.world = A_local, n, rank, world
+        self.suf = "f64" if A_local.dtype == torch.float64 else "f32"
+        dev = A_local.device
+        self.ws = torch.empty(int(self.lib.chub_workspace_bytes(1, n)), dtype=torch.uint8, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.payload_doubles = int(self.lib.chub_rc_payload_doubles())
+        import ctypes
+
+        vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+        for suf in ("f64", "f32"):
+            f = getattr(self.lib, f"chub_rc_prepare_{suf}")
+            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, vp, vp, ci, vp, vp]
+            f = getattr(self.lib, f"chub_rc_panel_owner_{suf}")
+            f.restype, f.argtypes = ci, [vp, i64, i64, ci, ci, ci, vp, vp, vp, vp, vp]
+            f = getattr(self.lib, f"chub_rc_panel_apply_{suf}")
+            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, ci, ci, vp, vp, vp, vp]
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.A.device).cuda_stream
+
+    def new_payload(self):
+        return self.torch.empty(self.payload_doubles, dtype=self.torch.float64, device=self.A.device)
+
+    def prepare(self, v, v_out, check_diag):
+        from . import _lib
+
+        self.v_out = v_out
+        rc = getattr(self.lib, f"chub_rc_prepare_{self.suf}")(
+            self.A.data_ptr(), self.A.shape[0], self.n, self.A.shape[1], self.world, self.rank,
+            v.data_ptr(), self.ws.data_ptr(), _lib.FLAG_CHECK_DIAG if check_diag else 0,
+            self.status.data_ptr(), self._stream())
+        _lib.check(rc, "chub_rc_prepare")
+
+    def panel_owner(self, J, payload):
+        from . import _lib
+
+        rc = getattr(self.lib, f"chub_rc_panel_owner_{self.suf}")(
+            self.A.data_ptr(), self.n, self.A.shape[1], self.world, self.rank, J, self.v_out.data_ptr(),
+            self.ws.data_ptr(), payload.data_ptr(), self.status.data_ptr(), self._stream())
+        _lib.check(rc, "chub_rc_panel_owner")
+
+    def panel_apply(self, J, is_owner, payload):
+        from . import _lib
+
+        rc = getattr(self.lib, f"chub_rc_panel_apply_{self.suf}")(
+            self.A.data_ptr(), self.A.shape[0], self.n, self.A.shape[1], self.world, self.rank, J,
+            1 if is_owner else 0, self.ws.data_ptr(), payload.data_ptr(), self.status.data_ptr(),
+            self._stream())
+        _lib.check(rc, "chub_rc_panel_apply")
+
+    def status_tensor(self):
+        return self.status
+
+
+class RowCyclicFactor:
+    """A Cholesky factor of order ``n`` distributed block-row-cyclically: this rank holds
+    ``A_local`` = the rows ``rc_owned_rows(n, rank, world)`` (all ``n`` columns, row-major).
+
+    ``update(v)`` applies the rank-1 Seeger update ``L L^T + v v^T`` in place on every rank's rows.
+    Per 256-column panel the owner of the diagonal block (rank ``J mod world``) computes the panel's
+    coefficients and broadcasts ~8 KB; everything else is local.  ``v`` is the full
+    vector, identical on every rank.
+    """
+
+    def __init__(self, A_local, n: int, rank: int = 0, world_size: int = 1, group=None, backend=None):
+        self.A = A_local
+        self.n, self.rank, self.world, self.group = int(n), int(rank), int(world_size), group
+        expect = len(rc_owned_rows(self.n, self.rank, self.world))
+        if A_local.ndim != 2 or A_local.shape[0] != expect or A_local.shape[1] < self.n:
+            raise ValueError(
+                f"`A_local` must have shape ({expect}, >= {self.n}) on rank {rank} of {world_size} "
+                f"(given shape: {tuple(A_local.shape)}).")
+        if not A_local.is_contiguous():
+            raise ValueError("`A_local` must be row-major contiguous.")
+        self.backend = backend if backend is not None else _CudaRowCyclicBackend(A_local, self.n, rank, world_size)
+
+    def update(self, v, check_diag: bool = True):
+        """In-place update of the distributed factor.  Returns the scratch vector (rotg's z_k for the
+        panels this rank owned).  Raises ``numpy.linalg.LinAlgError`` on every rank if ``check_diag``
+        finds a zero on the diagonal anywhere (nothing is modified in that case)."""
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+
+        if v.ndim != 1 or v.shape[0] != self.n:
+            raise ValueError(
+                f"The shape of the given vector `v` is incompatible with the shape of the given "
+                f"Cholesky factor `L`. Expected shape {(self.n,)} but got {tuple(v.shape)}.")
+        be = self.backend
+        multi = self.world > 1 and dist.is_available() and dist.is_initialized()
+        v_out = torch.zeros_like(v)
+        be.prepare(v, v_out, check_diag)
+        if check_diag:
+            st = be.status_tensor()
+            if multi:
+                dist.all_reduce(st, op=dist.ReduceOp.MAX, group=self.group)
+            if int(st.item()) == 1:
+                raise np.linalg.LinAlgError("The given Cholesky factor `L` contains zeros on its diagonal")
+        payload = be.new_payload()
+        for J in range((self.n + RC_BLOCK - 1) // RC_BLOCK):
+            owner = J % self.world
+            if owner == self.rank:
+                be.panel_owner(J, payload)
+            if multi:
+                src = owner if self.group is None else dist.get_global_rank(self.group, owner)
+                dist.broadcast(payload, src=src, group=self.group)
+            be.panel_apply(J, owner == self.rank, payload)
+        return v_out

@@ -122,6 +122,30 @@ int chub_downdate_host_f32(void *L, int64_t n, int64_t ld, int layout, void *v, 
 /* Release the staging buffers the host entry points cache on the current device. */
 int chub_host_release(void);
 
+/* ---- block-row-cyclic distribution of ONE factor over G devices (update only; row-major).
+ *      New surface: the reference has no distributed mode.  Rank g stores the global
+ *      256-row blocks g, g+G, g+2G, ... back to back as A_loc[m_loc][ld] (n columns).  Per
+ *      256-column panel J the owner of the diagonal block (rank J mod G) forms the panel's
+ *      coefficients and packs them into `payload` (chub_rc_payload_doubles() doubles); the caller
+ *      broadcasts the payload (NCCL) and every rank applies the panel to its local rows.
+ *      `v` / `v_out` are full n-vectors on the device; workspace as for the single-device calls. */
+int chub_rc_payload_doubles(void);
+int chub_rc_block_rows(void);
+int chub_rc_prepare_f64(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, void *v,
+                        void *workspace, int flags, int32_t *status, void *stream);
+int chub_rc_prepare_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, void *v,
+                        void *workspace, int flags, int32_t *status, void *stream);
+int chub_rc_panel_owner_f64(void *A_loc, int64_t n, int64_t ld, int G, int rank, int J, void *v_out,
+                            void *workspace, double *payload, int32_t *status, void *stream);
+int chub_rc_panel_owner_f32(void *A_loc, int64_t n, int64_t ld, int G, int rank, int J, void *v_out,
+                            void *workspace, double *payload, int32_t *status, void *stream);
+int chub_rc_panel_apply_f64(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int J,
+                            int is_owner, void *workspace, const double *payload, int32_t *status,
+                            void *stream);
+int chub_rc_panel_apply_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int J,
+                            int is_owner, void *workspace, const double *payload, int32_t *status,
+                            void *stream);
+
 /* ---- tuning / introspection (bench.py and tests) */
 /* Force a kernel path: 0 = automatic, 1 = single-CTA kernels only, 2 = panel
  * (multi-kernel) path, 3 = persistent dataflow kernel.  Returns the previous value. */

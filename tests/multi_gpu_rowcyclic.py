@@ -1,0 +1,91 @@
+"""Multi-GPU parity + timing of the block-row-cyclic update (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \\
+        --master-port 29511 tests/multi_gpu_rowcyclic.py [n_parity] [n_time] [updates]
+
+Parity: every rank builds the same seeded factor, keeps its own rows, applies 3 successive updates
+through RowCyclicFactor (NCCL broadcast of each panel's coefficients) and compares its rows with the
+oracle (tolerance 1e-12 * sqrt(n)).  Timing: n_time with per-rank generated rows.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+    sys.path.insert(0, p)
+
+from cholupdates_b200.distributed import RowCyclicFactor, rc_owned_rows  # noqa: E402
+from helpers import synth_factor, tol_for  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
+    n_time = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
+    updates = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+
+    import seeger_oracle as oracle
+
+    L = synth_factor(n, 5)
+    rows = rc_owned_rows(n, rank, world)
+    A = torch.from_numpy(np.ascontiguousarray(L[rows])).to(dev)
+    fac = RowCyclicFactor(A, n, rank, world)
+    L_ref = np.array(L, order="F")
+    for u in range(3):
+        v = np.random.default_rng([1, u]).standard_normal(n)
+        fac.update(torch.from_numpy(v.copy()).to(dev))
+        oracle.update(L_ref, v.copy())
+    lower = np.arange(n)[None, :] <= rows[:, None]
+    got = np.where(lower, A.cpu().numpy(), 0.0)
+    want = np.tril(L_ref)[rows]
+    err = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+    ok = err <= tol_for(np.float64, n) and bool(np.all(A.cpu().numpy()[~lower] == 0.0))
+    t = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(t)
+    if rank == 0:
+        print(f"[rowcyclic parity] n={n} world={world}: rel. Frobenius error (rank 0 rows) {err:.2e} "
+              f"(bar {tol_for(np.float64, n):.1e}); all ranks ok: {int(t.item()) == 0}", flush=True)
+    assert int(t.item()) == 0
+
+    # timing at n_time, rows generated per rank
+    n = n_time
+    rows = rc_owned_rows(n, rank, world)
+    g = torch.Generator(device=dev)
+    g.manual_seed(100 + rank)
+    A = torch.randn((len(rows), n), dtype=torch.float64, device=dev, generator=g) / np.sqrt(n)
+    rt = torch.from_numpy(rows).to(dev)
+    A.masked_fill_(torch.arange(n, device=dev)[None, :] > rt[:, None], 0.0)
+    A[torch.arange(len(rows), device=dev), rt] = 1.0 + torch.rand(len(rows), dtype=torch.float64, device=dev, generator=g)
+    fac = RowCyclicFactor(A, n, rank, world)
+    gv = torch.Generator(device=dev)
+    gv.manual_seed(7)  # same vectors on every rank
+    vs = torch.randn((updates + 1, n), dtype=torch.float64, device=dev, generator=gv)
+    fac.update(vs[updates], check_diag=False)  # warm-up
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for u in range(updates):
+        fac.update(vs[u], check_diag=False)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        per = float(ms.item()) / updates
+        bytes_upd = 8 * n * (n + 1) + 16 * n
+        print(f"[rowcyclic timing] n={n} world={world}: {per:.3f} ms/update, {bytes_upd / per / 1e6:.0f} GB/s aggregate "
+              f"({bytes_upd / per / 1e6 / world:.0f} GB/s per GPU)", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

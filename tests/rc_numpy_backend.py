@@ -1,0 +1,77 @@
+"""NumPy stand-in for the per-panel pieces of the block-row-cyclic update (TEST INFRASTRUCTURE: lets the
+world_size-2 gloo test run the distributed driver on CPU).  Same formulas as csrc/large.cuh."""
+
+import numpy as np
+import torch
+
+from cholupdates_b200.distributed import RC_BLOCK, rc_owned_rows
+
+
+class NumpyRowCyclicBackend:
+    def __init__(self, A_local, n, rank, world):
+        self.A = A_local.numpy()  # shares memory with the torch tensor
+        self.n, self.rank, self.world = n, rank, world
+        self.rows = rc_owned_rows(n, rank, world)
+        self.status = torch.zeros(1, dtype=torch.int32)
+        self.w = np.zeros(n)
+        self.p, self.c, self.sg, self.dn = (np.zeros(n) for _ in range(4))
+        self.t, self.S = 1.0, 1.0
+
+    def new_payload(self):
+        return torch.zeros(4 * RC_BLOCK + 8, dtype=torch.float64)
+
+    def prepare(self, v, v_out, check_diag):
+        self.v_out = v_out.numpy()
+        vv = v.numpy()
+        self.w[self.rows] = vv[self.rows]
+        self.t, self.S = 1.0, 1.0
+        self.status[0] = 0
+        if check_diag and np.any(self.A[np.arange(len(self.rows)), self.rows] == 0):
+            self.status[0] = 1
+
+    def panel_owner(self, J, payload):
+        j0, j1 = J * RC_BLOCK, min(self.n, (J + 1) * RC_BLOCK)
+        loc = np.searchsorted(self.rows, np.arange(j0, j1))
+        LD = np.tril(self.A[loc, j0:j1])
+        p = np.linalg.solve(LD, self.w[j0:j1])  # forward substitution on the diagonal block
+        dg = np.diag(LD)
+        t_incl = self.t + np.cumsum(p * p)
+        t_excl = np.concatenate(([self.t], t_incl[:-1]))
+        sgn = np.where(dg < 0, -1.0, 1.0)
+        rinv = 1.0 / np.sqrt(t_excl * t_incl)
+        self.p[j0:j1], self.c[j0:j1] = p, sgn * t_excl * rinv
+        self.sg[j0:j1], self.dn[j0:j1] = sgn * p * rinv, np.abs(dg) * t_incl * rinv
+        self.t = t_incl[-1]
+        self.S *= np.prod(sgn)
+        buf = payload.numpy()
+        m = j1 - j0
+        buf[:] = 0
+        buf[0:m], buf[RC_BLOCK:RC_BLOCK + m] = self.p[j0:j1], self.c[j0:j1]
+        buf[2 * RC_BLOCK:2 * RC_BLOCK + m], buf[3 * RC_BLOCK:3 * RC_BLOCK + m] = self.sg[j0:j1], self.dn[j0:j1]
+        buf[4 * RC_BLOCK], buf[4 * RC_BLOCK + 1] = self.t, self.S
+
+    def panel_apply(self, J, is_owner, payload):
+        j0, j1 = J * RC_BLOCK, min(self.n, (J + 1) * RC_BLOCK)
+        m = j1 - j0
+        if not is_owner:
+            buf = payload.numpy()
+            self.p[j0:j1], self.c[j0:j1] = buf[0:m], buf[RC_BLOCK:RC_BLOCK + m]
+            self.sg[j0:j1], self.dn[j0:j1] = buf[2 * RC_BLOCK:2 * RC_BLOCK + m], buf[3 * RC_BLOCK:3 * RC_BLOCK + m]
+            self.t, self.S = buf[4 * RC_BLOCK], buf[4 * RC_BLOCK + 1]
+        sel = np.nonzero(self.rows >= j0)[0]
+        if sel.size == 0:
+            return
+        R = self.rows[sel]
+        w = self.w[R].copy()
+        for k in range(j0, j1):
+            below = R > k
+            lo = self.A[sel, k].copy()
+            self.A[sel[below], k] = self.c[k] * lo[below] + self.sg[k] * w[below]
+            w[below] -= lo[below] * self.p[k]
+            diag = R == k
+            self.A[sel[diag], k] = self.dn[k]
+        keep = R >= j1
+        self.w[R[keep]] = w[keep]
+
+    def status_tensor(self):
+        return self.status

@@ -99,3 +99,70 @@ def test_sharded_batched_world_size_2_gloo(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+# ---------------------------------------------------------------- block-row-cyclic single factor
+def _rc_worker(rank, world, port, tmpdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import seeger_oracle as oracle
+        from cholupdates_b200.distributed import RowCyclicFactor, rc_owned_rows
+        from helpers import rel_fro, synth_factor, tol_for
+        from rc_numpy_backend import NumpyRowCyclicBackend
+
+        n = 900  # 4 blocks of 256 rows (the last one partial): rank 0 owns blocks 0, 2; rank 1 owns 1, 3
+        L = synth_factor(n, 3)
+        L[:, 5] *= -1.0  # one negative diagonal entry: the sign fix must survive the distribution
+        rows = rc_owned_rows(n, rank, world)
+        A_loc = torch.from_numpy(np.ascontiguousarray(L[rows]))
+        fac = RowCyclicFactor(A_loc, n, rank, world, backend=NumpyRowCyclicBackend(A_loc, n, rank, world))
+        L_ref = np.array(L, order="F")
+        for u in range(3):  # successive updates, as in BASELINE.json configs[4]
+            v = np.random.default_rng([1, u]).standard_normal(n)
+            fac.update(torch.from_numpy(v.copy()))
+            oracle.update(L_ref, v.copy())
+        lower = np.arange(n)[None, :] <= rows[:, None]  # lower triangle in GLOBAL row indices
+        got = np.where(lower, A_loc.numpy(), 0.0)
+        want = np.tril(L_ref)[rows]
+        err = np.linalg.norm(got - want) / np.linalg.norm(want)
+        assert err <= tol_for(np.float64, n), err
+        assert np.all(A_loc.numpy()[~lower] == 0.0)  # nothing above the diagonal was written
+        # zero on the diagonal of a row owned by rank 1: both ranks raise, nothing is modified
+        before = A_loc.clone()
+        if 300 in rows:
+            A_loc[int(np.searchsorted(rows, 300)), 300] = 0.0
+            before = A_loc.clone()
+        try:
+            fac.update(torch.from_numpy(np.ones(n)))
+            raised = False
+        except np.linalg.LinAlgError:
+            raised = True
+        assert raised and torch.equal(before, A_loc)
+        with open(os.path.join(tmpdir, f"rc{rank}"), "w") as f:
+            f.write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rowcyclic_update_world_size_2_gloo(tmp_path):
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_rc_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "rc0").exists() and (tmp_path / "rc1").exists()
+
+
+def test_rc_owned_rows_partition():
+    from cholupdates_b200.distributed import rc_owned_rows
+
+    for n in (1, 255, 256, 257, 900, 4096):
+        for world in (1, 2, 3, 8):
+            allrows = np.concatenate([rc_owned_rows(n, r, world) for r in range(world)])
+            assert sorted(allrows.tolist()) == list(range(n))

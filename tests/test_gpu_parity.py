@@ -339,3 +339,41 @@ def test_downdate_n4096_matches_oracle(order):
     L_ref, _ = _oracle("downdate", L, v)
     got = _run("downdate", np.array(L, order=order), v, "torch")
     assert rel_fro(got, L_ref) <= tol_for(np.float64, n)
+
+
+# ------------------------------------------------ block-row-cyclic driver on one GPU (world = 1)
+@pytest.mark.parametrize("n", [700, 1000, 2048])
+def test_rowcyclic_single_rank_matches_oracle(n):
+    from cholupdates_b200.distributed import RowCyclicFactor
+
+    L = synth_factor(n, 31)
+    L[:, 3] *= -1.0
+    A = torch.from_numpy(L.copy()).cuda()
+    fac = RowCyclicFactor(A, n)
+    L_ref = np.array(L, order="F")
+    for u in range(2):
+        v = np.random.default_rng([7, u]).standard_normal(n)
+        fac.update(torch.from_numpy(v.copy()).cuda())
+        oracle.update(L_ref, v.copy())
+    got = A.cpu().numpy()
+    assert rel_fro(got, L_ref) <= tol_for(np.float64, n)
+    np.testing.assert_array_equal(np.triu(got, 1), 0)
+    Lz = torch.from_numpy(L.copy()).cuda()
+    Lz[n // 2, n // 2] = 0.0
+    keep = Lz.clone()
+    with pytest.raises(np.linalg.LinAlgError):
+        RowCyclicFactor(Lz, n).update(torch.ones(n, dtype=torch.float64, device="cuda"))
+    assert torch.equal(keep, Lz)
+
+
+def test_sharded_batched_single_process():
+    from cholupdates_b200.distributed import shard_bounds, sharded_batched
+
+    B, n = 6, 64
+    Ls = np.stack([synth_factor(n, [0, b]) for b in range(B)])
+    vs = np.stack([np.random.default_rng([1, b]).standard_normal(n) for b in range(B)])
+    lo, hi = shard_bounds(B, 0, 1)
+    out, status = sharded_batched("update", torch.from_numpy(Ls[lo:hi]).cuda(), torch.from_numpy(vs[lo:hi]).cuda())
+    assert status.tolist() == [0] * B
+    for b in range(B):
+        assert rel_fro(out[b].cpu().numpy(), _oracle("update", Ls[b], vs[b])[0]) <= tol_for(np.float64, n)
