@@ -33,7 +33,7 @@ def load() -> ctypes.CDLL:
         if _lib is not None:
             return _lib
         try:
-            path = _build.build()
+            path = os.environ.get("CHUB_LIB") or _build.build()  # CHUB_LIB: A/B-test another build
         except Exception as exc:  # noqa: BLE001
             raise RuntimeError(
                 "cholupdates_b200: the CUDA library libcholupdates_b200.so is not available "

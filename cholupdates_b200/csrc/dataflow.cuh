@@ -45,10 +45,22 @@ namespace chub {
 
 constexpr int kDfThreads = 256;
 constexpr int kDfRowWarps = 7;  // warps 0..6 own rows, warp 7 derives the coefficients
-constexpr int kDfD = 4;         // band depth in block columns (look-ahead of the chain)
-constexpr int kDfStages = 6;    // worker tile ring
-constexpr int kDfSlots = 4;     // chain prefetch ring (block columns)
-constexpr int kDfCoefRing = 8;
+#ifndef CHUB_DF_D
+#define CHUB_DF_D 5
+#endif
+#ifndef CHUB_DF_SLOTS
+#define CHUB_DF_SLOTS 4
+#endif
+#ifndef CHUB_DF_RING
+#define CHUB_DF_RING 16
+#endif
+constexpr int kDfD = CHUB_DF_D;         // v3 (row-major): band depth in block columns (look-ahead of the chain)
+constexpr int kDfStages = 6;            // worker tile ring
+constexpr int kDfSlots = CHUB_DF_SLOTS;  // v3: chain prefetch ring (block columns)
+constexpr int kDfCoefRing = CHUB_DF_RING;  // v3: coefficient ring
+constexpr int kV2D = 4;         // v2 (column-major) keeps its own, shallower configuration
+constexpr int kV2Slots = 4;
+constexpr int kV2CoefRing = 8;
 constexpr unsigned long long kSentinelBits = 0xFFFFFFFFFFFFFFFFull;
 constexpr long long kWatchdogCycles = 4000000000LL;  // ~2 s
 
@@ -121,6 +133,15 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n"
                ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
 }
+// CTA-scope acquire / release on shared-memory progress counters (cheaper than a MEMBAR.CTA fence)
+__device__ __forceinline__ int ld_acquire_cta_smem(const volatile int *p) {
+  int x;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];\n" : "=r"(x) : "r"(smem_u32(const_cast<const int *>(p))) : "memory");
+  return x;
+}
+__device__ __forceinline__ void st_release_cta_smem(volatile int *p, int x) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;\n" ::"r"(smem_u32(const_cast<int *>(p))), "r"(x) : "memory");
+}
 // exactly one lane of a converged warp (the compiler then keeps TMA operands on the uniform path)
 __device__ __forceinline__ bool elect_one() {
   unsigned pred;
@@ -171,9 +192,10 @@ __device__ __forceinline__ double df_sanitize(double x) {
 }
 
 // Which block column does a row of block row b process at step s?  (-1: none)
+template <int D>
 __device__ __forceinline__ int df_panel_at(int b, int s) {
-  if (s < b - kDfD) return s;                                  // far left of the diagonal
-  if (s >= b && s <= b + kDfD && s >= kDfD) return s - kDfD;   // band, delayed by d steps
+  if (s < b - D) return s;                          // far left of the diagonal
+  if (s >= b && s <= b + D && s >= D) return s - D;  // band, delayed by d steps
   return -1;
 }
 
@@ -189,14 +211,15 @@ __device__ __forceinline__ long long df_gtime() {
   return t;
 }
 // event trace (CHUB_PROFILE): trace[ev * T + block_row] = %globaltimer (ns)
-#define DF_TRACE(ev, r) do { if (P.prof) P.prof[256 * 16 + (size_t)(ev) * P.T + (r)] = df_gtime(); } while (0)
-#define DF_PROF_T() (P.prof ? clock64() : 0LL)
-#define DF_PROF_ADD(slot, t_begin) do { if (P.prof) pacc[slot] += clock64() - (t_begin); } while (0)
+// (PROF is a compile-time flag in scope: the production kernel carries none of this)
+#define DF_TRACE(ev, r) do { if (PROF && P.prof) P.prof[256 * 16 + (size_t)(ev) * P.T + (r)] = df_gtime(); } while (0)
+#define DF_PROF_T() ((PROF && P.prof) ? clock64() : 0LL)
+#define DF_PROF_ADD(slot, t_begin) do { if (PROF && P.prof) pacc[slot] += clock64() - (t_begin); } while (0)
 
 // ------------------------------------------------------------------ prepare
 template <typename T, int LAYOUT>
 __global__ void df_prepare_kernel(const T *L, int n, int64_t ld, const T *v, LargeWs ws, int flags,
-                                  int32_t *status) {
+                                  int32_t *status, int band_depth) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n_pad = (n + 31) & ~31;
   if (i >= n_pad) return;
@@ -207,7 +230,7 @@ __global__ void df_prepare_kernel(const T *L, int n, int64_t ld, const T *v, Lar
     const T dgi = L[idx<LAYOUT>(i, i, ld)];
     ws.v0[i] = vi;
     ws.dg[i] = (double)dgi;
-    ws.w[i] = (i >> 5) <= kDfD ? vi : sentinel;  // rows whose band starts at column 0
+    ws.w[i] = (i >> 5) <= band_depth ? vi : sentinel;  // rows whose band starts at column 0
     if ((flags & CHUB_FLAG_CHECK_DIAG) && dgi == T(0)) atomicMax(status, CHUB_STATUS_ZERO_DIAG);
   } else {
     ws.v0[i] = 0.0;
@@ -217,47 +240,76 @@ __global__ void df_prepare_kernel(const T *L, int n, int64_t ld, const T *v, Lar
   if (i == 0) { ws.scal[0] = 1.0; ws.scal[1] = 1.0; ws.scal[2] = 0.0; ws.scal[3] = 0.0; }
 }
 
+// Fused pre-pass: block b of 128 threads prepares entries [128 b, 128 b + 128) (= the four diagonal
+// blocks it inverts).  check_diag failures are only known after the whole grid ran, so the inverses
+// are computed unconditionally (they only read L) -- the persistent kernel checks the status word.
+template <typename T, int LAYOUT>
+__global__ void __launch_bounds__(128) df_prepass_kernel(const T *L, int n, int64_t ld, const T *v, LargeWs ws,
+                                                         int flags, int32_t *status, int band_depth) {
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  const int n_pad = (n + 31) & ~31;
+  if (i < n_pad) {
+    const double sentinel = __longlong_as_double((long long)kSentinelBits);
+    ws.p[i] = sentinel;
+    if (i < n) {
+      const double vi = df_sanitize((double)v[i]);
+      const T dgi = L[idx<LAYOUT>(i, i, ld)];
+      ws.v0[i] = vi;
+      ws.dg[i] = (double)dgi;
+      ws.w[i] = (i >> 5) <= band_depth ? vi : sentinel;
+      if ((flags & CHUB_FLAG_CHECK_DIAG) && dgi == T(0)) atomicMax(status, CHUB_STATUS_ZERO_DIAG);
+    } else {
+      ws.v0[i] = 0.0;
+      ws.dg[i] = 1.0;
+      ws.w[i] = 0.0;
+    }
+  }
+  if (i == 0) { ws.scal[0] = 1.0; ws.scal[1] = 1.0; ws.scal[2] = 0.0; ws.scal[3] = 0.0; }
+  invdiag_block<T, LAYOUT>(L, n, ld, ws, blockIdx.x * 4 + (threadIdx.x >> 5));
+}
+
 // ------------------------------------------------------------------ chain CTA
 // Shared-memory tile of the band: row-major source -> [32 rows][STRIDE] (lane = row reads 16-byte
 // chunks conflict-free thanks to the padding); column-major source -> [32 cols][32 rows].
 template <typename T, int LAYOUT>
 __device__ void df_chain(const T *L, const DfParams &P, unsigned char *smem) {
+  constexpr bool PROF = true;
   constexpr int EPC = DfGeom<T>::EPC, CPR = DfGeom<T>::CPR, STRIDE = DfGeom<T>::STRIDE;
   constexpr int TILE_ELEMS = LAYOUT == CHUB_ROW_MAJOR ? kPanel * STRIDE : kPanel * kPanel;
-  constexpr int LOADERS = kDfThreads - kDfD * 32;  // warps d..7
+  constexpr int LOADERS = kDfThreads - kV2D * 32;  // warps d..7
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = P.n, T_ = P.T;
   const int64_t ld = P.ld;
   long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
-  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);  // [kDfSlots]
-  double *Xs = reinterpret_cast<double *>(smem + 64);                       // [kDfSlots][kXBlock]
-  double *acc = Xs + kDfSlots * kXBlock;                                    // [kDfD+1][32]
-  double *pbuf = acc + (kDfD + 1) * kPanel;                                 // [2][32]
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);  // [kV2Slots]
+  double *Xs = reinterpret_cast<double *>(smem + 64);                       // [kV2Slots][kXBlock]
+  double *acc = Xs + kV2Slots * kXBlock;                                    // [kV2D+1][32]
+  double *pbuf = acc + (kV2D + 1) * kPanel;                                 // [2][32]
   double *wvec = pbuf + 2 * kPanel;                                         // [32]
   double *wtb = wvec + kPanel;                                              // [2][32] polled wt
-  T *tiles = reinterpret_cast<T *>(wtb + 2 * kPanel);                       // [kDfSlots][kDfD][TILE_ELEMS]
+  T *tiles = reinterpret_cast<T *>(wtb + 2 * kPanel);                       // [kV2Slots][kV2D][TILE_ELEMS]
 
   if (tid == 0) {
-    for (int i = 0; i < kDfSlots; ++i) mbar_init(&full[i], LOADERS);
+    for (int i = 0; i < kV2Slots; ++i) mbar_init(&full[i], LOADERS);
     fence_mbar_init();
   }
-  for (int e = tid; e < (kDfD + 1) * kPanel; e += kDfThreads) acc[e] = 0.0;
+  for (int e = tid; e < (kV2D + 1) * kPanel; e += kDfThreads) acc[e] = 0.0;
   __syncthreads();
 
-  // Loads for block column j: tiles (j+1 .. j+d, j) and X_{j+1}, into slot j % kDfSlots.
+  // Loads for block column j: tiles (j+1 .. j+d, j) and X_{j+1}, into slot j % kV2Slots.
   // Called by the LOADERS threads (t = 0 .. LOADERS-1); each arrives exactly once.
   auto issue_slot = [&](int j, int t) {
     if (j < 0 || j >= T_) return;
-    const int slot = j % kDfSlots;
+    const int slot = j % kV2Slots;
     void *bar = &full[slot];
     unsigned bytes = 0;
     const int q = t >> 5, rr = t & 31;  // tile q (block row j+1+q), row / column rr of it
     const void *src = nullptr;
     void *dst = nullptr;
-    if (q < kDfD) {
+    if (q < kV2D) {
       const int br = j + 1 + q;
-      T *tb = tiles + ((size_t)slot * kDfD + q) * TILE_ELEMS;
+      T *tb = tiles + ((size_t)slot * kV2D + q) * TILE_ELEMS;
       if (br < T_) {
         if (LAYOUT == CHUB_ROW_MAJOR) {
           const int64_t row = (int64_t)br * kPanel + rr;
@@ -287,9 +339,9 @@ __device__ void df_chain(const T *L, const DfParams &P, unsigned char *smem) {
     if (do_x) bulk_g2s(Xs + slot * kXBlock, P.ws.X + (int64_t)(j + 1) * kXBlock, xbytes, bar);
   };
 
-  // prologue: prefetch slots 0 .. kDfSlots-2; p_0 = X_0 w_0 (w_0 = v[0:32])
-  if (warp >= kDfD)
-    for (int j = 0; j < kDfSlots - 1; ++j) issue_slot(j, tid - kDfD * 32);
+  // prologue: prefetch slots 0 .. kV2Slots-2; p_0 = X_0 w_0 (w_0 = v[0:32])
+  if (warp >= kV2D)
+    for (int j = 0; j < kV2Slots - 1; ++j) issue_slot(j, tid - kV2D * 32);
   if (warp == 0) {
     wvec[lane] = df_wait_value(P.ws.w + lane, P.status);
     __syncwarp();
@@ -312,12 +364,12 @@ __device__ void df_chain(const T *L, const DfParams &P, unsigned char *smem) {
     //      also polls wt_{j+1} so that phase B finds it in shared memory
     long long tp = DF_PROF_T();
     const double *pj = pbuf + (j & 1) * kPanel;
-    if (warp < kDfD) {
+    if (warp < kV2D) {
       const int br = j + 1 + warp;
       if (br < T_) {
-        mbar_wait(&full[j % kDfSlots], (unsigned)((j / kDfSlots) & 1), P.status);
+        mbar_wait(&full[j % kV2Slots], (unsigned)((j / kV2Slots) & 1), P.status);
         if (tid == 0) DF_PROF_ADD(1, tp);
-        const T *tb = tiles + ((size_t)(j % kDfSlots) * kDfD + warp) * TILE_ELEMS;
+        const T *tb = tiles + ((size_t)(j % kV2Slots) * kV2D + warp) * TILE_ELEMS;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         if ((int64_t)br * kPanel + lane < n) {
           if (LAYOUT == CHUB_ROW_MAJOR) {
@@ -346,13 +398,13 @@ __device__ void df_chain(const T *L, const DfParams &P, unsigned char *smem) {
             }
           }
         }
-        acc[(br % (kDfD + 1)) * kPanel + lane] -= (a0 + a1) + (a2 + a3);
+        acc[(br % (kV2D + 1)) * kPanel + lane] -= (a0 + a1) + (a2 + a3);
       }
       if (tid == 0) DF_PROF_ADD(2, tp);
     } else {
       // refill the slot that phase A of block column j-1 released at the last barrier
-      issue_slot(j + kDfSlots - 1, tid - kDfD * 32);
-      if (warp == kDfD && j + 1 < T_) {
+      issue_slot(j + kV2Slots - 1, tid - kV2D * 32);
+      if (warp == kV2D && j + 1 < T_) {
         long long tq = DF_PROF_T();
         wtb[((j + 1) & 1) * kPanel + lane] =
             df_wait_value(P.ws.w + (int64_t)(j + 1) * kPanel + lane, P.status);
@@ -364,13 +416,13 @@ __device__ void df_chain(const T *L, const DfParams &P, unsigned char *smem) {
     // ---- phase B: w_{j+1} = wt_{j+1} + acc ; p_{j+1} = X_{j+1} w_{j+1}
     if (warp == 0 && j + 1 < T_) {
       const int r = j + 1;
-      double *a = acc + (r % (kDfD + 1)) * kPanel;
+      double *a = acc + (r % (kV2D + 1)) * kPanel;
       wvec[lane] = wtb[(r & 1) * kPanel + lane] + a[lane];
       a[lane] = 0.0;
       __syncwarp();
       if (tid == 0) DF_PROF_ADD(3, tp);
       tp = DF_PROF_T();
-      const double *X = Xs + (j % kDfSlots) * kXBlock + lane * kXStride;
+      const double *X = Xs + (j % kV2Slots) * kXBlock + lane * kXStride;
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
       for (int k = 0; k < kPanel; k += 4) {
@@ -389,7 +441,7 @@ __device__ void df_chain(const T *L, const DfParams &P, unsigned char *smem) {
     __syncthreads();
   }
   if (tid == 0) DF_PROF_ADD(0, t_chain0);
-  if (P.prof && (tid == 0 || tid == kDfD * 32)) {
+  if (P.prof && (tid == 0 || tid == kV2D * 32)) {
     for (int i = 0; i < 8; ++i)
       if (pacc[i]) P.prof[(size_t)blockIdx.x * 16 + i] = pacc[i];
   }
@@ -398,33 +450,34 @@ __device__ void df_chain(const T *L, const DfParams &P, unsigned char *smem) {
 template <typename T>
 inline size_t df_chain_smem(int layout) {
   const size_t tile_elems = layout == CHUB_ROW_MAJOR ? (size_t)kPanel * DfGeom<T>::STRIDE : (size_t)kPanel * kPanel;
-  return 64 + (size_t)(kDfSlots * kXBlock + (kDfD + 1) * kPanel + 5 * kPanel) * sizeof(double) +
-         (size_t)kDfSlots * kDfD * tile_elems * sizeof(T);
+  return 64 + (size_t)(kV2Slots * kXBlock + (kV2D + 1) * kPanel + 5 * kPanel) * sizeof(double) +
+         (size_t)kV2Slots * kV2D * tile_elems * sizeof(T);
 }
 
 // ------------------------------------------------------------------ worker CTAs
 template <typename T, int LAYOUT, bool UPDATE>
 __device__ void df_worker(T *L, T *v, const DfParams &P, unsigned char *smem) {
+  constexpr bool PROF = true;
   constexpr int EPC = DfGeom<T>::EPC, CPR = DfGeom<T>::CPR, STRIDE = DfGeom<T>::STRIDE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wkr = blockIdx.x - 1;
   const int n = P.n, T_ = P.T, R = P.R, rsh = P.r_shift, Wk = P.Wk, nw = P.nw;
   const int64_t ld = P.ld;
-  const int nsteps = T_ + kDfD;
+  const int nsteps = T_ + kV2D;
   long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
   // shared memory carve-up
   unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);  // [kDfStages][kDfRowWarps]
-  unsigned long long *cfull = full + kDfStages * kDfRowWarps;               // [kDfCoefRing]
-  unsigned long long *cempty = cfull + kDfCoefRing;                         // [kDfCoefRing]
-  double *coef = reinterpret_cast<double *>(smem + 512);                    // [kDfCoefRing][4][32]
-  T *stages = reinterpret_cast<T *>(coef + kDfCoefRing * 4 * kPanel);
+  unsigned long long *cfull = full + kDfStages * kDfRowWarps;               // [kV2CoefRing]
+  unsigned long long *cempty = cfull + kV2CoefRing;                         // [kV2CoefRing]
+  double *coef = reinterpret_cast<double *>(smem + 512);                    // [kV2CoefRing][4][32]
+  T *stages = reinterpret_cast<T *>(coef + kV2CoefRing * 4 * kPanel);
   // row-major: stage = [nw*32 rows][STRIDE];  column-major: stage = [nw warps][32 cols][32 rows]
   const size_t stage_elems = (size_t)nw * 32 * (LAYOUT == CHUB_ROW_MAJOR ? STRIDE : kPanel);
 
   if (tid == 0) {
     for (int i = 0; i < kDfStages * kDfRowWarps; ++i) mbar_init(&full[i], 32);
-    for (int i = 0; i < kDfCoefRing; ++i) { mbar_init(&cfull[i], 32); mbar_init(&cempty[i], nw); }
+    for (int i = 0; i < kV2CoefRing; ++i) { mbar_init(&cfull[i], 32); mbar_init(&cempty[i], nw); }
     fence_mbar_init();
   }
   __syncthreads();
@@ -437,8 +490,8 @@ __device__ void df_worker(T *L, T *v, const DfParams &P, unsigned char *smem) {
     // ---------------- coefficient warp: p_s -> (p, c, sigma, dn) of block column s
     double t_run = 1.0, S_run = 1.0;
     for (int pan = 0; pan < T_; ++pan) {
-      const int slot = pan % kDfCoefRing;
-      if (pan >= kDfCoefRing) mbar_wait(&cempty[slot], (unsigned)((pan / kDfCoefRing - 1) & 1), P.status);
+      const int slot = pan % kV2CoefRing;
+      if (pan >= kV2CoefRing) mbar_wait(&cempty[slot], (unsigned)((pan / kV2CoefRing - 1) & 1), P.status);
       const int k = pan * kPanel + lane;
       long long tq = DF_PROF_T();
       const double pk = df_wait_value(P.ws.p + k, P.status);
@@ -510,7 +563,7 @@ __device__ void df_worker(T *L, T *v, const DfParams &P, unsigned char *smem) {
     void *bar = &full[(s % kDfStages) * kDfRowWarps + warp];
     T *st = stages + (size_t)(s % kDfStages) * stage_elems;
     if (LAYOUT == CHUB_ROW_MAJOR) {
-      const int pan = has_row ? df_panel_at(b, s) : -1;
+      const int pan = has_row ? df_panel_at<kV2D>(b, s) : -1;
       if (pan >= 0) {
         const int64_t c0 = (int64_t)pan * kPanel;
         int cnt = (int)min((int64_t)kPanel, min((int64_t)n - c0, row - c0 + 1));
@@ -528,7 +581,7 @@ __device__ void df_worker(T *L, T *v, const DfParams &P, unsigned char *smem) {
       unsigned by[2] = {0, 0};
       T *wt = st + (size_t)warp * kPanel * kPanel;
       for (int h = 0; h < 2; ++h) {
-        const int pan = df_panel_at(cm_b[h], s);
+        const int pan = df_panel_at<kV2D>(cm_b[h], s);
         if (pan < 0) continue;
         const int64_t col = (int64_t)pan * kPanel + lane;
         if (col >= n || col > cm_row0[h] + cm_rows[h] - 1) continue;  // outside the lower triangle
@@ -558,14 +611,14 @@ __device__ void df_worker(T *L, T *v, const DfParams &P, unsigned char *smem) {
     mbar_wait(&full[(s % kDfStages) * kDfRowWarps + warp], (unsigned)((s / kDfStages) & 1), P.status);
     if (prof_me) DF_PROF_ADD(1, tp);
     tp = DF_PROF_T();
-    if (s < T_) mbar_wait(&cfull[s % kDfCoefRing], (unsigned)((s / kDfCoefRing) & 1), P.status);
+    if (s < T_) mbar_wait(&cfull[s % kV2CoefRing], (unsigned)((s / kV2CoefRing) & 1), P.status);
     if (prof_me) DF_PROF_ADD(4, tp);
     tp = DF_PROF_T();
 
-    const int pan = has_row ? df_panel_at(b, s) : -1;
+    const int pan = has_row ? df_panel_at<kV2D>(b, s) : -1;
     T *st = stages + (size_t)(s % kDfStages) * stage_elems;
     if (pan >= 0) {
-      const double *cf = coef + (size_t)(pan % kDfCoefRing) * 4 * kPanel;
+      const double *cf = coef + (size_t)(pan % kV2CoefRing) * 4 * kPanel;
       const int64_t c0 = (int64_t)pan * kPanel;
       const bool full_tile = c0 + kPanel <= row;  // whole tile strictly below the diagonal
       if (LAYOUT == CHUB_ROW_MAJOR) {
@@ -604,7 +657,7 @@ __device__ void df_worker(T *L, T *v, const DfParams &P, unsigned char *smem) {
         }
       }
       // hand the residual over to the chain after the last far-left block column
-      if (s == b - kDfD - 1) st_relaxed_f64(P.ws.w + row, df_sanitize(w));
+      if (s == b - kV2D - 1) st_relaxed_f64(P.ws.w + row, df_sanitize(w));
     }
     if (prof_me) DF_PROF_ADD(3, tp);
     tp = DF_PROF_T();
@@ -625,7 +678,7 @@ __device__ void df_worker(T *L, T *v, const DfParams &P, unsigned char *smem) {
         __syncwarp();  // lane k stores column k: entries written by the other lanes of this warp
         T *wt = st + (size_t)warp * kPanel * kPanel;
         for (int h = 0; h < 2; ++h) {
-          const int panh = df_panel_at(cm_b[h], s);
+          const int panh = df_panel_at<kV2D>(cm_b[h], s);
           if (panh < 0) continue;
           const int64_t col = (int64_t)panh * kPanel + lane;
           const int64_t r_hi = cm_row0[h] + cm_rows[h];
@@ -642,9 +695,9 @@ __device__ void df_worker(T *L, T *v, const DfParams &P, unsigned char *smem) {
       bulk_commit();
     }
     // this warp is done with block column s-d for good
-    if (s >= kDfD && s - kDfD < T_) {
+    if (s >= kV2D && s - kV2D < T_) {
       __syncwarp();
-      if (lane == 0) mbar_arrive(&cempty[(s - kDfD) % kDfCoefRing]);
+      if (lane == 0) mbar_arrive(&cempty[(s - kV2D) % kV2CoefRing]);
     }
     if (prof_me) DF_PROF_ADD(5, tp);
   }
@@ -658,7 +711,7 @@ __device__ void df_worker(T *L, T *v, const DfParams &P, unsigned char *smem) {
 template <typename T>
 inline size_t df_worker_smem(int layout, int nw) {
   const size_t stage_elems = (size_t)nw * 32 * (layout == CHUB_ROW_MAJOR ? DfGeom<T>::STRIDE : kPanel);
-  return 512 + (size_t)kDfCoefRing * 4 * kPanel * sizeof(double) + (size_t)kDfStages * stage_elems * sizeof(T);
+  return 512 + (size_t)kV2CoefRing * 4 * kPanel * sizeof(double) + (size_t)kDfStages * stage_elems * sizeof(T);
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -693,7 +746,7 @@ template <typename T> struct RmGeom {
 };
 
 // ---- chain CTA (threads 0..255 of CTA 0)
-template <typename T>
+template <typename T, bool PROF>
 __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsigned char *smem) {
   constexpr int HALVES = RmGeom<T>::HALVES, BOXC = RmGeom<T>::BOXC, EPC = RmGeom<T>::EPC;
   constexpr int CTILE = RmGeom<T>::CTILE;
@@ -851,7 +904,7 @@ inline size_t df_chain_rm_smem() {
 }
 
 // ---- worker CTAs
-template <typename T, bool UPDATE>
+template <typename T, bool UPDATE, bool PROF>
 __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *tmap8,
                              unsigned char *smem) {
   constexpr int HALVES = RmGeom<T>::HALVES, BOXC = RmGeom<T>::BOXC;
@@ -904,10 +957,9 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
         // slot last used by block column pan-8, read for the last time at step pan-8+d
         const int need = pan - kDfCoefRing + kDfD + 1;
         const long long t0 = clock64();
-        while (__reduce_min_sync(0xffffffffu, prog[lane]) < need) {
+        while (__reduce_min_sync(0xffffffffu, ld_acquire_cta_smem(prog + lane)) < need) {
           if (clock64() - t0 > kWatchdogCycles) { atomicMax(P.status, CHUB_STATUS_INTERNAL); break; }
         }
-        __threadfence_block();
       }
       double *cf = coef + (size_t)slot * 4 * kPanel;
       cf[lane] = pk;
@@ -929,7 +981,7 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
         cf[2 * kPanel + lane] = sigk;
         cf[3 * kPanel + lane] = fabs(dg) * tk1 * rinv;
         __syncwarp();
-        if (lane == 0) { __threadfence_block(); *cprog = pan + 1; }
+        if (lane == 0) st_release_cta_smem(cprog, pan + 1);
         if (wkr == pan % Wk && k < n) {  // one worker per panel leaves rotg's z_k in v[k]
           const double Sk = (__popc(negmask & ((1u << lane) - 1u)) & 1) ? -S_run : S_run;
           const double nuk = Sk * dg * pk / sqrt(tk);
@@ -940,7 +992,7 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
         if (__popc(negmask) & 1) S_run = -S_run;
       } else {
         __syncwarp();
-        if (lane == 0) { __threadfence_block(); *cprog = pan + 1; }
+        if (lane == 0) st_release_cta_smem(cprog, pan + 1);
       }
       if (lane == 0 && wkr == 0) DF_TRACE(4, pan);
       if (lane == 0) DF_PROF_ADD(7, tq);
@@ -964,7 +1016,7 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
   const int64_t row = row0 + r8;
   double w = row < n ? P.ws.v0[row] : 0.0;
   const int64_t row0_next = (((int64_t)wkr + (int64_t)((warp + 1) >> 1) * Wk) << 4) + (((warp + 1) & 1) << 3);
-  const bool prof_me = P.prof && lane == 0 && (warp + 1 >= nrw || row0_next >= n);
+  const bool prof_me = PROF && P.prof && lane == 0 && (warp + 1 >= nrw || row0_next >= n);
   // my 8 columns live in half `hh`, chunks cb .. cb+CPT-1 of the 128-byte box row
   const int hh = (g * 8 * (int)sizeof(T)) / 128;
   const int cb = ((g * 8 * (int)sizeof(T)) % 128) / 16;
@@ -975,7 +1027,7 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
   auto issue_load = [&](int s, int st) {  // lane 0 only; st = s % kDfStages
     if (s > last_step) return;
     void *bar = &myfull[st];
-    const int pan = df_panel_at(b, s);
+    const int pan = df_panel_at<kDfD>(b, s);
     if (pan < 0) { mbar_arrive(bar); return; }
     unsigned char *tile = mytile + st * WTILE;
     const int c0 = pan * kPanel;
@@ -992,7 +1044,7 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
   // One block column of my 8 rows: tile in shared memory -> updated tile (or, for the ragged
   // diagonal tile, straight to global memory).  Returns true if the tile has to be TMA-stored.
   auto do_step = [&](int s, int st) -> bool {
-    const int pan = df_panel_at(b, s);
+    const int pan = df_panel_at<kDfD>(b, s);
     if (pan < 0) return false;
     unsigned char *rowp = mytile + st * WTILE + my_off;
     const double *cf = coef + (size_t)(pan % kDfCoefRing) * 4 * kPanel + g * 8;
@@ -1066,7 +1118,7 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
   };
 
   auto issue_store = [&](int s, int st) {  // lane 0 only
-    const int c0 = df_panel_at(b, s) * kPanel;
+    const int c0 = df_panel_at<kDfD>(b, s) * kPanel;
     unsigned char *tile = mytile + st * WTILE;
     tma_store_2d(tmap8, c0, (int)row0, tile);
     if (HALVES == 2 && c0 + BOXC < n) tma_store_2d(tmap8, c0 + BOXC, (int)row0, tile + 1024);
@@ -1104,13 +1156,12 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
       // coefficients up to block column min(s+1, T-1): implies p_{s+1} is published, i.e. the
       // chain has consumed everything these two steps overwrite
       const int need = min(two ? s + 1 : s, T_ - 1) + 1;
-      if (*cprog < need) {
+      if (ld_acquire_cta_smem(cprog) < need) {
         const long long t0 = clock64();
-        while (*cprog < need) {
+        while (ld_acquire_cta_smem(cprog) < need) {
           if (clock64() - t0 > kWatchdogCycles) { atomicMax(P.status, CHUB_STATUS_INTERNAL); break; }
         }
       }
-      __threadfence_block();
     }
     if (prof_me) DF_PROF_ADD(4, tp);
     if (prof_me && wkr == 0 && s < T_) DF_TRACE(5, s);
@@ -1128,8 +1179,7 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
       if (st0) issue_store(s, st);
       if (st1b) issue_store(s + 1, st1);
       bulk_commit();
-      __threadfence_block();
-      prog[warp] = s + 1 >= last_step ? 0x7fffffff : s + 2;
+      st_release_cta_smem(prog + warp, s + 1 >= last_step ? 0x7fffffff : s + 2);
     }
     __syncwarp();
     st = stn;
@@ -1148,16 +1198,16 @@ inline size_t df_worker_rm_smem(int nrw) {
   return 2048 + (size_t)kDfCoefRing * 4 * kPanel * 8 + (size_t)kDfStages * nrw * RmGeom<T>::WTILE;
 }
 
-template <typename T, bool UPDATE>
+template <typename T, bool UPDATE, bool PROF>
 __global__ void __launch_bounds__(kRmMaxThreads, 1)
 df_kernel_rm(T *L, T *v, DfParams P, const __grid_constant__ CUtensorMap tmap8,
              const __grid_constant__ CUtensorMap tmap32) {
   extern __shared__ __align__(1024) unsigned char df_smem[];
   if (*P.status != 0) return;  // check_diag failed: L and v stay untouched
   if (blockIdx.x == 0) {
-    if (threadIdx.x < 256) df_chain_rm<T>(P, &tmap32, df_smem);
+    if (threadIdx.x < 256) df_chain_rm<T, PROF>(P, &tmap32, df_smem);
   } else {
-    df_worker_rm<T, UPDATE>(L, v, P, &tmap8, df_smem);
+    df_worker_rm<T, UPDATE, PROF>(L, v, P, &tmap8, df_smem);
   }
 }
 
@@ -1292,9 +1342,9 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
     pl = df_plan<T>(n, ld, LAYOUT, L);
     if (!pl.ok) return (int)cudaErrorNotSupported;
   }
-  df_prepare_kernel<T, LAYOUT><<<(n_pad + 255) / 256, 256, 0, st>>>(L, ni, ld, v, ws, flags, status);
-  ++*launches;
-  large_invdiag_kernel<T, LAYOUT><<<(nb + 3) / 4, 128, 0, st>>>(L, ni, ld, ws, status);
+  // one pre-pass: w-tilde / v0 / dg / sentinels (prepare) and the inverse diagonal blocks
+  df_prepass_kernel<T, LAYOUT><<<(nb + 3) / 4, 128, 0, st>>>(L, ni, ld, v, ws, flags, status,
+                                                              rp.ok ? kDfD : kV2D);
   ++*launches;
   DfParams P;
   P.n = ni; P.T = nb; P.ld = ld; P.ws = ws; P.status = status;
@@ -1306,7 +1356,7 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
   cudaError_t e;
   if (rp.ok) {
     P.R = 16; P.r_shift = 4; P.Wk = rp.Wk; P.rows_max = rp.Q * 16; P.nw = rp.nrw;
-    auto kern = df_kernel_rm<T, UPDATE>;
+    auto kern = P.prof ? df_kernel_rm<T, UPDATE, true> : df_kernel_rm<T, UPDATE, false>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rp.smem);
     if (e != cudaSuccess) return (int)e;
     void *args[] = {(void *)&L, (void *)&v, (void *)&P, (void *)&tmap8, (void *)&tmap32};

@@ -87,17 +87,16 @@ __global__ void large_prepare_kernel(const T *L, int n, int64_t ld, const T *v, 
 
 // --------------------------------------------------------- diagonal inverses
 // One warp per 32x32 diagonal block: X = inv(L_D) (lower triangular), lane j computes column j
-// by forward substitution.  Blocks that stick out of the matrix are padded with the identity.
+// by forward substitution (reciprocal diagonal precomputed, two accumulators per dot product so
+// that the dependent FMA chain is half as long).  Blocks that stick out of the matrix are padded
+// with the identity.  Must be called by all 4 warps of a 128-thread CTA (static shared memory).
 template <typename T, int LAYOUT>
-__global__ void __launch_bounds__(128) large_invdiag_kernel(const T *L, int n, int64_t ld,
-                                                             LargeWs ws, const int32_t *status,
-                                                             int blk0 = 0, int nblk = 1 << 30) {
+__device__ __forceinline__ void invdiag_block(const T *L, int n, int64_t ld, LargeWs ws, int blk) {
   __shared__ double Ls[4][kPanel][kPanel + 1];
-  if (*status != 0) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int blk = blk0 + blockIdx.x * 4 + warp;
+  __shared__ double Rd[4][kPanel];
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 3;
   const int nb = (n + 31) / 32;
-  if (blk >= nb || blk >= blk0 + nblk) return;
+  if (blk >= nb) return;
   const int c0 = blk * kPanel;
   // stage the block (lane = column for row-major reads, lane = row for column-major reads)
   for (int r = 0; r < kPanel; ++r) {
@@ -108,19 +107,33 @@ __global__ void __launch_bounds__(128) large_invdiag_kernel(const T *L, int n, i
     Ls[warp][i][j] = x;
   }
   __syncwarp();
+  Rd[warp][lane] = 1.0 / Ls[warp][lane][lane];
+  __syncwarp();
   double x[kPanel];
   const int j = lane;
 #pragma unroll
   for (int i = 0; i < kPanel; ++i) {
-    double acc = (i == j) ? 1.0 : 0.0;
+    double a0 = (i == j) ? 1.0 : 0.0, a1 = 0.0;
 #pragma unroll
-    for (int m = 0; m < kPanel; ++m)
-      if (m < i) acc -= (m >= j ? Ls[warp][i][m] * x[m] : 0.0);
-    x[i] = (i >= j) ? acc / Ls[warp][i][i] : 0.0;
+    for (int m = 0; m < kPanel; m += 2) {
+      if (m < i) a0 -= Ls[warp][i][m] * x[m];          // x[m] = 0 for m < j
+      if (m + 1 < i) a1 -= Ls[warp][i][m + 1] * x[m + 1];
+    }
+    x[i] = (i >= j) ? (a0 + a1) * Rd[warp][i] : 0.0;
   }
   double *X = ws.X + (int64_t)blk * kXBlock;
 #pragma unroll
   for (int i = 0; i < kPanel; ++i) X[i * kXStride + j] = x[i];
+}
+
+template <typename T, int LAYOUT>
+__global__ void __launch_bounds__(128) large_invdiag_kernel(const T *L, int n, int64_t ld,
+                                                             LargeWs ws, const int32_t *status,
+                                                             int blk0 = 0, int nblk = 1 << 30) {
+  if (*status != 0) return;
+  const int blk = blk0 + blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (blk >= blk0 + nblk) return;
+  invdiag_block<T, LAYOUT>(L, n, ld, ws, blk);
 }
 
 // ------------------------------------------------------------------ chain
