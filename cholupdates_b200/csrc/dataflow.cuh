@@ -1211,6 +1211,157 @@ df_kernel_rm(T *L, T *v, DfParams P, const __grid_constant__ CUtensorMap tmap8,
   }
 }
 
+// =====================================================================================
+// Downdate sweep (row-major): TMA-pipelined, 4 lanes per row, right-to-left affine scan
+// =====================================================================================
+// Reverse sweep of _seeger_impl_cython.pyx:285-330 in the row-independent form of SURVEY A.3:
+//   (L_ik, x_i) <- (sgn_k (c_k L_ik - s_k x_i), c_k x_i + s_k L_ik)   for k = i .. 0,  x_i = 0 at k = i.
+// Rows are independent and all (c_k, s_k, sgn_k) are known, so there is no chain: a CTA takes one
+// block row (4 warps x 8 rows) and every warp walks its tiles from the diagonal to column 0 with a
+// ring of TMA loads one step ahead.  x -> c x + s L is affine in x, so lane (g, r8) first composes
+// the map of its 8 columns, a two-step shuffle scan (right to left over the 4 lanes of a row) gives
+// every lane its incoming x, and a second local pass writes the new entries.
+constexpr int kSwStages = 4;
+
+template <typename T>
+struct SwGeom {
+  static constexpr int STAGE = RmGeom<T>::WTILE + 1024;  // tile + (c, s, sgn)[32] doubles (768 B, padded)
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) dd_sweep_rm_kernel(T *L, int n, int64_t ld, LargeWs ws,
+                                                          const int32_t *status,
+                                                          const __grid_constant__ CUtensorMap tmap8) {
+  constexpr int HALVES = RmGeom<T>::HALVES, BOXC = RmGeom<T>::BOXC, CPT = RmGeom<T>::CPT;
+  constexpr int WTILE = RmGeom<T>::WTILE, STAGE = SwGeom<T>::STAGE;
+  extern __shared__ __align__(1024) unsigned char sw_smem[];
+  if (*status != 0) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int T_ = (n + 31) / 32;
+  const int b = T_ - 1 - blockIdx.x;  // longest rows first
+  const int64_t row0 = (int64_t)b * 32 + warp * 8;
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(sw_smem) + warp * kSwStages;
+  unsigned char *mystage = sw_smem + 1024 + (size_t)warp * kSwStages * STAGE;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4 * kSwStages; ++i) mbar_init(reinterpret_cast<unsigned long long *>(sw_smem) + i, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (row0 >= n) return;
+  const int g = lane >> 3, r8 = lane & 7;
+  const int64_t row = row0 + r8;
+  const int hh = (g * 8 * (int)sizeof(T)) / 128;
+  const int cb = ((g * 8 * (int)sizeof(T)) % 128) / 16;
+  const unsigned my_off = hh * 1024 + r8 * 128;
+  const int nsteps = b + 1;  // tiles b, b-1, ..., 0
+
+  auto issue_load = [&](int s, int st) {  // elected lane
+    if (s >= nsteps) return;
+    const int pan = b - s;
+    void *bar = &full[st];
+    unsigned char *stg = mystage + (size_t)st * STAGE;
+    const int c0 = pan * kPanel;
+    const bool two = HALVES == 2 && c0 + BOXC < n;
+    mbar_arrive_expect_tx(bar, (two ? 2048u : 1024u) + 768u);
+    tma_load_2d(stg, &tmap8, c0, (int)row0, bar);
+    if (two) tma_load_2d(stg + 1024, &tmap8, c0 + BOXC, (int)row0, bar);
+    bulk_g2s(stg + WTILE, ws.c + c0, 256u, bar);
+    bulk_g2s(stg + WTILE + 256, ws.sg + c0, 256u, bar);
+    bulk_g2s(stg + WTILE + 512, ws.dn + c0, 256u, bar);
+  };
+
+  if (elect_one())
+    for (int s = 0; s < kSwStages - 2; ++s) issue_load(s, s);
+  __syncwarp();
+
+  double xc = 0.0;  // x_i carried from the tile to the right
+  int st = 0, stn = kSwStages - 2;
+  unsigned ph = 0;
+  for (int s = 0; s < nsteps; ++s) {
+    if (elect_one()) {
+      bulk_wait_read<1>();
+      issue_load(s + kSwStages - 2, stn);
+    }
+    __syncwarp();
+    mbar_wait(&full[st], ph, const_cast<int32_t *>(status));
+    const int pan = b - s;
+    unsigned char *stg = mystage + (size_t)st * STAGE;
+    unsigned char *rowp = stg + my_off;
+    const double *cf = reinterpret_cast<const double *>(stg + WTILE) + g * 8;
+    const int64_t c0 = (int64_t)pan * kPanel + g * 8;
+    const bool diag_step = (s == 0);
+    int4 raw[CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) raw[i] = *reinterpret_cast<const int4 *>(rowp + (((cb + i) ^ r8) << 4));
+    T *x = reinterpret_cast<T *>(raw);
+    double cc[8], sc[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const double2 a = *reinterpret_cast<const double2 *>(cf + j);
+      const double2 d = *reinterpret_cast<const double2 *>(cf + kPanel + j);
+      cc[j] = a.x; cc[j + 1] = a.y; sc[j] = d.x; sc[j + 1] = d.y;
+    }
+    // pass 1: the affine map x -> A x + B of my 8 columns (right to left)
+    double A = 1.0, B = 0.0;
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+      lo[j] = (double)x[j];
+      if (!diag_step || c0 + j <= row) {
+        B = fma(cc[j], B, sc[j] * lo[j]);
+        A *= cc[j];
+      } else {
+        cc[j] = 1.0; sc[j] = 0.0;  // above the diagonal: identity, and the entry is left alone
+      }
+    }
+    // inclusive suffix composition over the 4 lanes of the row: P_g = M_g o M_{g+1} o ... o M_3
+    double PA = A, PB = B;
+    double qa = __shfl_down_sync(0xffffffffu, PA, 8), qb = __shfl_down_sync(0xffffffffu, PB, 8);
+    if (g <= 2) { PB = fma(PA, qb, PB); PA *= qa; }
+    qa = __shfl_down_sync(0xffffffffu, PA, 16); qb = __shfl_down_sync(0xffffffffu, PB, 16);
+    if (g <= 1) { PB = fma(PA, qb, PB); PA *= qa; }
+    // incoming x of my segment = (M_{g+1} o ... o M_3)(xc);  outgoing x of the tile = P_0(xc)
+    const double ea = __shfl_down_sync(0xffffffffu, PA, 8), eb = __shfl_down_sync(0xffffffffu, PB, 8);
+    double xi = g == 3 ? xc : fma(ea, xc, eb);
+    const double xout = fma(__shfl_sync(0xffffffffu, PA, r8), xc, __shfl_sync(0xffffffffu, PB, r8));
+    // pass 2: new entries
+    const double *sgp = cf + 2 * kPanel;
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+      const double lnew = sgp[j] * (cc[j] * lo[j] - sc[j] * xi);
+      xi = fma(cc[j], xi, sc[j] * lo[j]);
+      if (!diag_step || c0 + j <= row) x[j] = (T)lnew;
+    }
+    xc = xout;
+    if (!diag_step) {
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) *reinterpret_cast<int4 *>(rowp + (((cb + i) ^ r8) << 4)) = raw[i];
+    } else if (row < n) {
+      T *gp = L + row * ld + c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j <= row) gp[j] = x[j];
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (elect_one()) {
+      if (!diag_step) {
+        const int cc0 = pan * kPanel;
+        tma_store_2d(&tmap8, cc0, (int)row0, stg);
+        if (HALVES == 2 && cc0 + BOXC < n) tma_store_2d(&tmap8, cc0 + BOXC, (int)row0, stg + 1024);
+      }
+      bulk_commit();
+    }
+    __syncwarp();
+    if (++st == kSwStages) { st = 0; ph ^= 1u; }
+    if (++stn == kSwStages) stn = 0;
+  }
+  if (elect_one()) bulk_wait_all<0>();
+}
+
+template <typename T>
+inline size_t dd_sweep_rm_smem() { return 1024 + (size_t)4 * kSwStages * SwGeom<T>::STAGE; }
+
 // ------------------------------------------------------------------ host side
 inline size_t dataflow_flag_bytes(int64_t n) { return 256 + (256 * 16 + 8 * ((size_t)n / 32 + 2)) * sizeof(long long); }
 
@@ -1374,7 +1525,15 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
   if (!UPDATE) {
     large_dd_coef_kernel<T, LAYOUT><<<1, 1024, 0, st>>>(L, ni, ld, v, ws, status);
     ++*launches;
-    large_dd_sweep_kernel<T, LAYOUT><<<(ni + 127) / 128, 128, 0, st>>>(L, ni, ld, ws, status);
+    if (rp.ok && !getenv("CHUB_DD_SWEEP_V1")) {
+      auto sk = dd_sweep_rm_kernel<T>;
+      const size_t ssm = dd_sweep_rm_smem<T>();
+      e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
+      if (e != cudaSuccess) return (int)e;
+      sk<<<nb, 128, ssm, st>>>(L, ni, ld, ws, status, tmap8);
+    } else {
+      large_dd_sweep_kernel<T, LAYOUT><<<(ni + 127) / 128, 128, 0, st>>>(L, ni, ld, ws, status);
+    }
     ++*launches;
   }
   e = cudaGetLastError();
