@@ -144,6 +144,50 @@ int run_single(void *Lv, int64_t n, int64_t ld, int layout, void *vv, int flags,
     return (int)cudaErrorInvalidValue;
   }
   LargeWs ws = large_ws_carve(workspace, n);
+  if (path == 3 && layout == CHUB_COL_MAJOR && !getenv("CHUB_COL_MAJOR_NATIVE")) {
+    // Column-major: the fast persistent kernel is row-major (tensor-map boxes along rows).  Until the
+    // column-major boxes exist, go through a row-major scratch copy of the lower triangle: two extra
+    // coalesced triangle passes cost less than the older column-major kernel (df_kernel_v2).
+    constexpr int64_t kEpc = 16 / sizeof(T);
+    const int64_t ldr = (n + kEpc - 1) / kEpc * kEpc;  // 16-byte aligned rows
+    T *tmp = nullptr;
+    {  // keep the scratch cached in the device's default pool between calls
+      static std::atomic<unsigned long long> pool_tuned{0};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!((pool_tuned.load() >> (dev & 63)) & 1ull)) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+          unsigned long long thr = ~0ull;
+          cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        pool_tuned.fetch_or(1ull << (dev & 63));
+      }
+    }
+    if (dataflow_supported<T>(n, ldr, CHUB_ROW_MAJOR, (const T *)nullptr) &&
+        cudaMallocAsync((void **)&tmp, (size_t)n * ldr * sizeof(T), st) == cudaSuccess) {
+      const int nt = (int)((n + 31) / 32);
+      const unsigned tiles = (unsigned)((int64_t)nt * (nt + 1) / 2);
+      tri_transpose_kernel<T, true><<<tiles, 256, 0, st>>>(tmp, ldr, L, ld, (int)n);
+      LAUNCHED();
+      int64_t nl = 0;
+      int rc = launch_dataflow<T, CHUB_ROW_MAJOR, UPDATE>(tmp, n, ldr, v, flags, ws, status, st, &nl);
+      g_launches.fetch_add(nl, std::memory_order_relaxed);
+      if (rc == 0) {
+        // (a failed check_diag / not-PD call leaves tmp == L, so copying back is harmless)
+        tri_transpose_kernel<T, false><<<tiles, 256, 0, st>>>(L, ld, tmp, ldr, (int)n);
+        LAUNCHED();
+        CK(cudaFreeAsync(tmp, st));
+        return 0;
+      }
+      cudaFreeAsync(tmp, st);
+      if (rc != (int)cudaErrorNotSupported && rc != (int)cudaErrorCooperativeLaunchTooLarge)
+        return fail((cudaError_t)rc, "dataflow launch");
+      cudaGetLastError();
+    } else {
+      cudaGetLastError();
+    }
+  }
   if (path == 3) {
     int64_t nl = 0;
     int rc = layout == CHUB_ROW_MAJOR

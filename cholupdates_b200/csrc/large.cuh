@@ -304,6 +304,46 @@ __global__ void __launch_bounds__(128) large_trail_kernel(T *L, int n, int64_t l
   if (valid && R >= cend) ws.w[R] = w;
 }
 
+// ------------------------------------------------------------ triangle transpose
+// Lower triangle of a column-major matrix <-> row-major scratch, 32x32 tiles through shared memory
+// (coalesced on both sides).  TO_ROW: dst[i*ldd + j] = src[i + j*lds] for j <= i;  otherwise the
+// inverse (dst[i + j*ldd] = src[i*lds + j]).  Entries above the diagonal are never written.
+template <typename T, bool TO_ROW>
+__global__ void __launch_bounds__(256) tri_transpose_kernel(T *dst, int64_t ldd, const T *src, int64_t lds, int n) {
+  __shared__ T tile[32][33];
+  // linear tile index -> (bi >= bj)
+  const int t = blockIdx.x;
+  int bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((int64_t)bi * (bi + 1) / 2 > t) --bi;
+  while ((int64_t)(bi + 1) * (bi + 2) / 2 <= t) ++bi;
+  const int bj = t - (int)((int64_t)bi * (bi + 1) / 2);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int i0 = bi * 32, j0 = bj * 32;
+  if (TO_ROW) {
+    // read column-major: consecutive threads = consecutive rows i
+    for (int c = ty; c < 32; c += 8) {
+      const int i = i0 + tx, j = j0 + c;
+      if (i < n && j < n) tile[c][tx] = src[i + (int64_t)j * lds];
+    }
+    __syncthreads();
+    // write row-major: consecutive threads = consecutive columns j
+    for (int r = ty; r < 32; r += 8) {
+      const int i = i0 + r, j = j0 + tx;
+      if (i < n && j <= i) dst[(int64_t)i * ldd + j] = tile[tx][r];
+    }
+  } else {
+    for (int r = ty; r < 32; r += 8) {
+      const int i = i0 + r, j = j0 + tx;
+      if (i < n && j < n) tile[r][tx] = src[(int64_t)i * lds + j];
+    }
+    __syncthreads();
+    for (int c = ty; c < 32; c += 8) {
+      const int i = i0 + tx, j = j0 + c;
+      if (i < n && j <= i) dst[i + (int64_t)j * ldd] = tile[tx][c];
+    }
+  }
+}
+
 // ------------------------------------------------------- downdate coefficients
 // One CTA of 1024 threads: rho^2 = 1 - p.p (.pyx:253-259), suffix sums, (c_k, s_k), sign of the
 // input diagonal, v <- rotg's z_k (or v <- p when the result is not positive definite).
