@@ -114,6 +114,18 @@ __device__ __forceinline__ T rotg_z(T a, T b, T c, T s) {
   return c0 != T(0) ? T(1) / c0 : T(1);
 }
 
+// CTA-scope acquire / release on shared-memory progress counters (cheaper than a MEMBAR.CTA fence)
+__device__ __forceinline__ int ld_acquire_cta_smem(const volatile int *p) {
+  int x;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];\n" : "=r"(x) : "r"((unsigned)__cvta_generic_to_shared(const_cast<const int *>(p))) : "memory");
+  return x;
+}
+__device__ __forceinline__ void st_release_cta_smem(volatile int *p, int x) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(const_cast<int *>(p))), "r"(x) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ double shfl(double x, int src) { return __shfl_sync(0xffffffffu, x, src); }
 __device__ __forceinline__ float shfl(float x, int src) { return __shfl_sync(0xffffffffu, x, src); }
 

@@ -133,15 +133,6 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n"
                ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
 }
-// CTA-scope acquire / release on shared-memory progress counters (cheaper than a MEMBAR.CTA fence)
-__device__ __forceinline__ int ld_acquire_cta_smem(const volatile int *p) {
-  int x;
-  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];\n" : "=r"(x) : "r"(smem_u32(const_cast<const int *>(p))) : "memory");
-  return x;
-}
-__device__ __forceinline__ void st_release_cta_smem(volatile int *p, int x) {
-  asm volatile("st.release.cta.shared.s32 [%0], %1;\n" ::"r"(smem_u32(const_cast<int *>(p))), "r"(x) : "memory");
-}
 // exactly one lane of a converged warp (the compiler then keeps TMA operands on the uniform path)
 __device__ __forceinline__ bool elect_one() {
   unsigned pred;
@@ -1311,7 +1302,9 @@ __global__ void __launch_bounds__(128) dd_sweep_rm_kernel(T *L, int n, int64_t l
         B = fma(cc[j], B, sc[j] * lo[j]);
         A *= cc[j];
       } else {
-        cc[j] = 1.0; sc[j] = 0.0;  // above the diagonal: identity, and the entry is left alone
+        // above the diagonal: identity map, entry left alone; its bits (never read by the reference,
+        // possibly NaN) must not reach the arithmetic
+        cc[j] = 1.0; sc[j] = 0.0; lo[j] = 0.0;
       }
     }
     // inclusive suffix composition over the 4 lanes of the row: P_g = M_g o M_{g+1} o ... o M_3
