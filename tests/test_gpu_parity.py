@@ -377,3 +377,24 @@ def test_sharded_batched_single_process():
     assert status.tolist() == [0] * B
     for b in range(B):
         assert rel_fro(out[b].cpu().numpy(), _oracle("update", Ls[b], vs[b])[0]) <= tol_for(np.float64, n)
+
+
+@pytest.mark.parametrize("op", ["update", "downdate"])
+@pytest.mark.parametrize("n", [100, 600, 1500])
+@pytest.mark.parametrize("order", ["C", "F"])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_nan_filled_upper_triangle(op, n, order, dtype):
+    """Every entry above the diagonal is NaN: the result below must be bit-identical to the clean run
+    and the NaNs must come back untouched (stronger form of test_update.py:25-55; regression test for
+    a 0 * NaN leak in the pipelined downdate sweep)."""
+    L = synth_factor(n, 17, dtype)
+    v = (np.random.default_rng(18).standard_normal(n).astype(dtype) if op == "update"
+         else downdate_vector(L, 18))
+    dirty_in = L.copy()
+    dirty_in[np.triu_indices(n, 1)] = np.nan
+    for kind in ("torch", "numpy"):
+        clean = _run(op, np.array(L, order=order), v, kind)
+        dirty = _run(op, np.array(dirty_in, order=order), v, kind)
+        assert np.all(np.isnan(dirty[np.triu_indices(n, 1)]))
+        np.testing.assert_array_equal(np.tril(dirty), np.tril(clean))
+        assert not np.any(np.isnan(np.tril(dirty)))
