@@ -88,9 +88,11 @@ __global__ void __launch_bounds__(NT) small_update_kernel(SmallArgs<T> a) {
 #pragma unroll
       for (int k = 0; k < kPanel; ++k) {
         if (k < bw) {  // uniform
+          // branch-free: Lrow[k] == 0 for lanes above the diagonal (k > lane), and lane k's own w
+          // is dead after its column, so the update runs unconditionally (no divergent branches)
           const T pk = shfl(w * rinv, k);
-          if (lane == k) pk_mine = pk;
-          else if (lane > k) w -= Lrow[k] * pk;
+          pk_mine = (lane == k) ? pk : pk_mine;
+          w -= Lrow[k] * pk;
         }
       }
       // coefficients of all columns of the block at once (fp64 arithmetic)
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(NT) small_update_kernel(SmallArgs<T> a) {
       T w2 = w0;
 #pragma unroll
       for (int k = 0; k < kPanel; ++k) {
-        if (k < bw && lane > k) {
+        if (k < bw) {  // uniform; entries with k >= lane get garbage that is never stored
           const T x = Lrow[k];
           Lrow[k] = cc[k] * x + sgm[k] * w2;
           w2 -= x * pp[k];
@@ -223,22 +225,23 @@ __global__ void __launch_bounds__(NT) small_downdate_kernel(SmallArgs<T> a) {
       T Lrow[kPanel];
 #pragma unroll
       for (int k = 0; k < kPanel; ++k)
-        Lrow[k] = (valid && k <= lane) ? L[idx<LAYOUT>(row, c0 + k, ld)] : T(1);
+        Lrow[k] = (valid && k <= lane) ? L[idx<LAYOUT>(row, c0 + k, ld)] : T(0);
       T w = valid ? p[row] : T(0);
       T dii = T(1);
 #pragma unroll
       for (int k = 0; k < kPanel; ++k)
         if (k == lane && valid) dii = Lrow[k];
       const T rinv = T(1) / dii;
+      T pmine = T(0);
 #pragma unroll
       for (int k = 0; k < kPanel; ++k) {
-        if (k < bw) {
+        if (k < bw) {  // branch-free (see the update kernel)
           const T pk = shfl(w * rinv, k);
-          if (lane == k) w = pk;
-          else if (lane > k) w -= Lrow[k] * pk;
+          pmine = (lane == k) ? pk : pmine;
+          w -= Lrow[k] * pk;
         }
       }
-      if (valid) p[row] = w;
+      if (valid) p[row] = pmine;
     }
     __syncthreads();
     const int rbeg = c0 + kPanel;
