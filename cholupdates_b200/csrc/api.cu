@@ -114,7 +114,9 @@ int launch_panel(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs &ws
   return 0;
 }
 
-constexpr int64_t kSmallCutoff = 512;  // n <= cutoff: one CTA does the whole factor
+constexpr int64_t kSmallCutoff = 95;    // n <= cutoff: one CTA does the whole factor (measured: the
+                                        // persistent kernel wins from n = 96, tools/cutoff_probe.py)
+constexpr int64_t kSmallFallback = 256;  // shapes the persistent kernel cannot take: one CTA up to here
 
 template <typename T, bool UPDATE>
 int run_single(void *Lv, int64_t n, int64_t ld, int layout, void *vv, int flags, void *workspace,
@@ -132,7 +134,7 @@ int run_single(void *Lv, int64_t n, int64_t ld, int layout, void *vv, int flags,
   int path = g_path.load();
   if (path == 0) path = n <= kSmallCutoff ? 1 : 3;
   if (path == 1 && n > kSmallMaxN) path = 2;
-  if (path == 3 && !dataflow_supported<T>(n, ld, layout, L)) path = 2;
+  if (path == 3 && !dataflow_supported<T>(n, ld, layout, L)) path = (g_path.load() == 0 && n <= kSmallFallback) ? 1 : 2;
   if (path == 1) return launch_small<T, UPDATE>(L, n, ld, 0, layout, v, 0, 1, flags, status, st);
 
   const size_t need = chub_workspace_bytes(dtype_of<T>(), n);
