@@ -398,3 +398,17 @@ def test_nan_filled_upper_triangle(op, n, order, dtype):
         assert np.all(np.isnan(dirty[np.triu_indices(n, 1)]))
         np.testing.assert_array_equal(np.tril(dirty), np.tril(clean))
         assert not np.any(np.isnan(np.tril(dirty)))
+
+
+@pytest.mark.parametrize("n", [600, 1536])
+def test_native_column_major_kernel(n, monkeypatch):
+    """Column-major factors normally go through a row-major scratch copy; the native column-major
+    dataflow kernel (df_kernel_v2) is the fallback when that scratch cannot be allocated.  Force it."""
+    monkeypatch.setenv("CHUB_COL_MAJOR_NATIVE", "1")
+    L = synth_factor(n, 41)
+    v = np.random.default_rng(42).standard_normal(n)
+    vd = downdate_vector(L, 43)
+    got_u = _run("update", np.asfortranarray(L), v, "torch")
+    got_d = _run("downdate", np.asfortranarray(L), vd, "torch")
+    assert rel_fro(got_u, _oracle("update", L, v)[0]) <= tol_for(np.float64, n)
+    assert rel_fro(got_d, _oracle("downdate", L, vd)[0]) <= tol_for(np.float64, n)
