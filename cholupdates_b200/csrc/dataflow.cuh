@@ -1117,27 +1117,24 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
 
   // Two block columns (steps 2S, 2S+1) per iteration: the fixed per-step costs (waits, TMA issue,
   // proxy fence, commit) are paid once per 64 columns.  Stages: pair S uses (2S) % 6, (2S+1) % 6;
-  // loads run one pair ahead, the stores of pair S-2 have left shared memory when pair S+1 loads.
+  // loads run two pairs ahead (issued after the compute phase, when the store of the pair whose
+  // stages they reuse has drained).
   static_assert(kDfStages == 6, "the pair schedule assumes a ring of 6 stages");
   if (elect_one()) {
     issue_load(0, 0);
     issue_load(1, 1);
+    issue_load(2, 2);
+    issue_load(3, 3);
   }
+  __syncwarp();
   const long long t_wk0 = DF_PROF_T();
   int st = 0;        // (2S) % 6
   unsigned ph = 0;   // ((2S) / 6) & 1
   for (int s = 0; s <= last_step; s += 2) {
     long long tp = DF_PROF_T();
-    const int st1 = st + 1;                      // stage of step s+1 (st is even: no wrap)
-    const int stn = st + 2 == kDfStages ? 0 : st + 2;  // stages of the next pair
-    if (elect_one()) {
-      bulk_wait_read<1>();  // stores of pair S-2 (whose stages pair S+1 reuses) have been read
-      issue_load(s + 2, stn);
-      issue_load(s + 3, stn + 1);
-    }
-    __syncwarp();
-    if (prof_me) DF_PROF_ADD(2, tp);
-    tp = DF_PROF_T();
+    const int st1 = st + 1;                             // stage of step s+1 (st is even: no wrap)
+    const int stn = st + 2 == kDfStages ? 0 : st + 2;   // stages of the next pair
+    const int stnn = st >= 2 ? st - 2 : st + 4;         // stages of pair S+2 (= those of pair S-1)
     const bool two = s + 1 <= last_step;
     mbar_wait(&myfull[st], ph, P.status);
     if (two) mbar_wait(&myfull[st1], ph, P.status);
@@ -1161,6 +1158,15 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
     const bool store1 = two ? do_step(s + 1, st1) : false;
     if (prof_me) DF_PROF_ADD(3, tp);
     if (prof_me && wkr == 0 && s < T_) DF_TRACE(6, s);
+    tp = DF_PROF_T();
+    // The ring holds the pair being processed and two pairs of loads in flight.  Pair S+2 reuses the
+    // stages of pair S-1, whose TMA store has had this whole compute phase to drain.
+    if (elect_one()) {
+      if (s >= 2) bulk_wait_read<0>();
+      issue_load(s + 4, stnn);
+      issue_load(s + 5, stnn + 1);
+    }
+    if (prof_me) DF_PROF_ADD(2, tp);
     tp = DF_PROF_T();
 
     fence_proxy_async();  // my generic-proxy writes -> visible to the TMA (async proxy) store
