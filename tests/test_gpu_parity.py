@@ -412,3 +412,30 @@ def test_native_column_major_kernel(n, monkeypatch):
     got_d = _run("downdate", np.asfortranarray(L), vd, "torch")
     assert rel_fro(got_u, _oracle("update", L, v)[0]) <= tol_for(np.float64, n)
     assert rel_fro(got_d, _oracle("downdate", L, vd)[0]) <= tol_for(np.float64, n)
+
+
+@pytest.mark.parametrize("n,ld", [(100, 128), (700, 1024), (1000, 1002)])
+@pytest.mark.parametrize("op", ["update", "downdate"])
+def test_c_abi_leading_dimension_larger_than_n(n, ld, op):
+    """The C ABI takes a leading dimension: an n x n factor living in the corner of a wider row-major
+    buffer (a superset of the reference, which only accepts contiguous arrays, _seeger.py:260-264).
+    Everything outside the n x n lower triangle must come back bit-identical."""
+    import ctypes
+
+    lib = _lib.load()
+    L = synth_factor(n, 51)
+    v = np.random.default_rng(52).standard_normal(n) if op == "update" else downdate_vector(L, 52)
+    big = np.random.default_rng(53).standard_normal((n + 3, ld))
+    big[:n, :n] = np.tril(L) + np.triu(big[:n, :n], 1)
+    bt = torch.from_numpy(big.copy()).cuda()
+    vt = torch.from_numpy(v.copy()).cuda()
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rc = getattr(lib, f"chub_{op}_f64")(bt.data_ptr(), n, ld, 0, vt.data_ptr(), 1, None, 0,
+                                        status.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert rc == 0 and int(status.item()) == 0
+    got = bt.cpu().numpy()
+    assert rel_fro(got[:n, :n], _oracle(op, L, v)[0]) <= tol_for(np.float64, n)
+    mask = np.ones_like(big, dtype=bool)
+    mask[:n, :n] = np.triu(np.ones((n, n), dtype=bool), 1)
+    np.testing.assert_array_equal(got[mask], big[mask])
