@@ -311,11 +311,11 @@ def run_gpu_arm(args):
         metric = METRIC_BATCHED
 
     # ---- warm-up, then K timed steps (device-timed with events on the launching stream)
+    sampler.start()  # clocks are sampled from the warm-up on, so that the short timed region is covered
     for i in range(args.warmup):
         step(i)
     barrier()
     lib.chub_launch_count(1)
-    sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
            for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -462,7 +462,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="update", choices=["update", "batched"])
