@@ -280,6 +280,57 @@ int rc_panel_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int ran
   }
   return 0;
 }
+// ---- wavefront over K successive updates of a block-row-cyclic factor (rowcyclic.cuh)
+template <typename T>
+int rcw_prepare(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, const void *V, int64_t K,
+                int64_t ldv, void *workspace, int flags, int32_t *status, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0 || K <= 0 || G <= 0 || K > 65535) {
+    snprintf(g_err, sizeof(g_err), "invalid argument (n=%lld K=%lld G=%d)", (long long)n, (long long)K, G);
+    return (int)cudaErrorInvalidValue;
+  }
+  RcWave wv = rcw_carve(workspace, n, K, G);
+  CK(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+  dim3 grid((unsigned)((m_loc > 0 ? m_loc + 255 : 256) / 256), (unsigned)K);
+  rcw_prepare_kernel<T><<<grid, 256, 0, st>>>((const T *)A, (int)m_loc, (int)n, ld, G, rank, (const T *)V, ldv, wv,
+                                               flags, status);
+  LAUNCHED();
+  return 0;
+}
+// tasks of anti-diagonal d: panels Jlo..Jhi (update u = d - J)
+inline void rcw_span(int64_t n, int64_t K, int64_t d, int *Jlo, int *Jhi) {
+  const int64_t nJ = rcw_panels(n);
+  *Jlo = (int)(d - K + 1 > 0 ? d - K + 1 : 0);
+  *Jhi = (int)(d < nJ - 1 ? d : nJ - 1);
+}
+template <typename T>
+int rcw_owner(void *A, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d, void *workspace,
+              double *pay_mine, int32_t *status, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  RcWave wv = rcw_carve(workspace, n, K, G);
+  int Jlo, Jhi;
+  rcw_span(n, K, d, &Jlo, &Jhi);
+  const int Jfirst = Jlo + (((rank - Jlo) % G) + G) % G;
+  if (Jfirst > Jhi) return 0;
+  const int count = (Jhi - Jfirst) / G + 1;
+  rcw_owner_kernel<T><<<count, kBig, 0, st>>>((const T *)A, (int)n, ld, G, wv, (int)d, Jfirst, pay_mine, status);
+  LAUNCHED();
+  return 0;
+}
+template <typename T>
+int rcw_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
+              void *workspace, const double *pay_all, void *V_out, int64_t ldv, int32_t *status, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  RcWave wv = rcw_carve(workspace, n, K, G);
+  int Jlo, Jhi;
+  rcw_span(n, K, d, &Jlo, &Jhi);
+  if (Jhi < Jlo) return 0;
+  dim3 grid((unsigned)((m_loc > 0 ? m_loc + 127 : 128) / 128), (unsigned)(Jhi - Jlo + 1));
+  rcw_trail_kernel<T><<<grid, 128, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, wv, (int)d, Jlo,
+                                            rcw_max_tasks(n, K, G), pay_all, (T *)V_out, ldv, status);
+  LAUNCHED();
+  return 0;
+}
 }  // namespace
 
 extern "C" {
@@ -363,6 +414,30 @@ int chub_rc_panel_apply_f32(void *A, int64_t m_loc, int64_t n, int64_t ld, int G
                             void *workspace, const double *payload, int32_t *status, void *stream) {
   return rc_panel_apply<float>(A, m_loc, n, ld, G, rank, J, is_owner, workspace, payload, status, stream);
 }
+
+int chub_rcw_payload_doubles(void) { return kRcwPayload; }
+int chub_rcw_max_tasks(int64_t n, int64_t K, int G) { return rcw_max_tasks(n, K, G > 0 ? G : 1); }
+size_t chub_rcw_workspace_bytes(int64_t n, int64_t K, int G) {
+  if (n < 0) n = 0;
+  if (K < 0) K = 0;
+  return rcw_ws_doubles(n, K, G > 0 ? G : 1) * sizeof(double);
+}
+#define DEFINE_RCW(SUF, T)                                                                                         \
+  int chub_rcw_prepare_##SUF(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, const void *V,        \
+                             int64_t K, int64_t ldv, void *workspace, int flags, int32_t *status, void *stream) {  \
+    return rcw_prepare<T>(A, m_loc, n, ld, G, rank, V, K, ldv, workspace, flags, status, stream);                  \
+  }                                                                                                                \
+  int chub_rcw_owner_##SUF(void *A, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d, void *workspace, \
+                           double *pay_mine, int32_t *status, void *stream) {                                      \
+    return rcw_owner<T>(A, n, ld, G, rank, K, d, workspace, pay_mine, status, stream);                             \
+  }                                                                                                                \
+  int chub_rcw_apply_##SUF(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,   \
+                           void *workspace, const double *pay_all, void *V_out, int64_t ldv, int32_t *status,      \
+                           void *stream) {                                                                         \
+    return rcw_apply<T>(A, m_loc, n, ld, G, rank, K, d, workspace, pay_all, V_out, ldv, status, stream);           \
+  }
+DEFINE_RCW(f64, double)
+DEFINE_RCW(f32, float)
 
 #define DEFINE_SINGLE(NAME, T, UPD)                                                              \
   int NAME(void *L, int64_t n, int64_t ld, int layout, void *v, int flags, void *workspace,      \

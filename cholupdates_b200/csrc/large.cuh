@@ -91,7 +91,7 @@ __global__ void large_prepare_kernel(const T *L, int n, int64_t ld, const T *v, 
 // that the dependent FMA chain is half as long).  Blocks that stick out of the matrix are padded
 // with the identity.  Must be called by all 4 warps of a 128-thread CTA (static shared memory).
 template <typename T, int LAYOUT>
-__device__ __forceinline__ void invdiag_block(const T *L, int n, int64_t ld, LargeWs ws, int blk) {
+__device__ __forceinline__ void invdiag_block_to(const T *L, int n, int64_t ld, double *X, int blk) {
   __shared__ double Ls[4][kPanel][kPanel + 1];
   __shared__ double Rd[4][kPanel];
   const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 3;
@@ -121,9 +121,12 @@ __device__ __forceinline__ void invdiag_block(const T *L, int n, int64_t ld, Lar
     }
     x[i] = (i >= j) ? (a0 + a1) * Rd[warp][i] : 0.0;
   }
-  double *X = ws.X + (int64_t)blk * kXBlock;
 #pragma unroll
   for (int i = 0; i < kPanel; ++i) X[i * kXStride + j] = x[i];
+}
+template <typename T, int LAYOUT>
+__device__ __forceinline__ void invdiag_block(const T *L, int n, int64_t ld, LargeWs ws, int blk) {
+  invdiag_block_to<T, LAYOUT>(L, n, ld, ws.X + (int64_t)blk * kXBlock, blk);
 }
 
 template <typename T, int LAYOUT>
@@ -142,26 +145,31 @@ __global__ void __launch_bounds__(128) large_invdiag_kernel(const T *L, int n, i
 // remaining rows of the 256-row block subtract L[:, blk] p_blk from their w (kept in a register).
 // UPDATE: afterwards the Seeger coefficients of the 256 columns are formed from a prefix sum of
 // p^2 and written to the workspace; v[k] <- rotg's z_k.
+//
+// chain_body is the kernel's body with every buffer explicit, so that the wavefront row-cyclic mode
+// (rowcyclic.cuh) can point it at a task's payload: Xp = the 8 inverse diagonal blocks of panel J,
+// w_in indexed by the global row, p/c/sg/dn/z outputs indexed by a = column - J*256 (z_out and v may
+// each be null), scal_in = {t, S} entering the panel, scal_out = {t, S} leaving it.
 template <typename T, int LAYOUT, bool UPDATE>
-__global__ void __launch_bounds__(kBig) large_chain_kernel(const T *L, int n, int64_t ld, T *v,
-                                                           LargeWs ws, int J,
-                                                           const int32_t *status) {
+__device__ __forceinline__ void chain_body(const T *L, int n, int64_t ld, int J, const double *Xp,
+                                           const double *w_in, double *p_out, double *c_out,
+                                           double *sg_out, double *dn_out, T *v, double *z_out,
+                                           const double *scal_in, double *scal_out) {
   __shared__ double wsm[kPanel];
   __shared__ double pall[kBig];
   __shared__ double wtot[kBig / 32];
   __shared__ int ntot[kBig / 32];
-  if (*status != 0) return;
   const int a = threadIdx.x, lane = a & 31, warp = a >> 5;
   const int base = J * kBig;
   const int R = base + a;
   const bool valid = R < n;
-  double wv = valid ? ws.w[R] : 0.0;
+  double wv = valid ? w_in[R] : 0.0;
   pall[a] = 0.0;
   const int rr = a >> 3, part = a & 7;  // mat-vec role: row rr of the block, columns 4*part..+3
   for (int s = 0; s < kBig / kPanel; ++s) {
     const int c0 = base + s * kPanel;
     if (c0 >= n) break;  // uniform
-    const double *X = ws.X + (int64_t)(c0 / kPanel) * kXBlock + rr * kXStride + part * 4;
+    const double *X = Xp + (int64_t)s * kXBlock + rr * kXStride + part * 4;
     const double x0 = X[0], x1 = X[1], x2 = X[2], x3 = X[3];
     // prefetch this thread's 32 entries of L[R][c0 .. c0+31] (needed only by rows below the block)
     const bool below = valid && R >= c0 + kPanel;
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(kBig) large_chain_kernel(const T *L, int n, in
   }
   __syncthreads();
   const double pk = pall[a];
-  if (valid) ws.p[R] = pk;
+  if (valid) p_out[a] = pk;
   if (!UPDATE) return;
 
   // ---- coefficients of column k = R (block scan of p^2 and of the diagonal signs)
@@ -207,31 +215,45 @@ __global__ void __launch_bounds__(kBig) large_chain_kernel(const T *L, int n, in
   }
   if (lane == 31) { wtot[warp] = incl; ntot[warp] = nincl; }
   __syncthreads();
-  double off = ws.scal[0];
+  double off = scal_in[0];
   int noff = 0;
   for (int q = 0; q < warp; ++q) { off += wtot[q]; noff += ntot[q]; }
   const double tk1 = off + incl, tk = tk1 - pk * pk > off ? off + (incl - pk * pk) : off;
-  const double S_in = ws.scal[1];
+  const double S_in = scal_in[1];
   const double Sk = ((noff + nincl - neg) & 1) ? -S_in : S_in;  // prod of signs of columns < k
   const double sgn = neg ? -1.0 : 1.0;
   const double rinv = 1.0 / sqrt(tk * tk1);
   const double ck = sgn * tk * rinv;
   const double sigk = sgn * pk * rinv;
   if (valid) {
-    ws.c[R] = ck;
-    ws.sg[R] = sigk;
-    ws.dn[R] = fabs(lkk) * tk1 * rinv;
+    c_out[a] = ck;
+    sg_out[a] = sigk;
+    dn_out[a] = fabs(lkk) * tk1 * rinv;
     // rotg's z from (a, b) = (L_kk, nu_k), nu_k = S_k L_kk p_k / sqrt(t_k), s_k = S_k sgn_k p_k / sqrt(t_{k+1})
     const double nuk = Sk * lkk * pk / sqrt(tk);
     const double sk = Sk * sgn * pk / sqrt(tk1);
-    v[R] = (T)rotg_z<double>(lkk, nuk, ck, sk);
+    const double z = rotg_z<double>(lkk, nuk, ck, sk);
+    if (v) v[R] = (T)z;
+    if (z_out) z_out[a] = z;
   }
   __syncthreads();
   if (a == kBig - 1) {
-    ws.scal[0] = tk1;
-    ws.scal[1] = ((noff + nincl) & 1) ? -S_in : S_in;
+    scal_out[0] = tk1;
+    scal_out[1] = ((noff + nincl) & 1) ? -S_in : S_in;
   }
 }
+
+template <typename T, int LAYOUT, bool UPDATE>
+__global__ void __launch_bounds__(kBig) large_chain_kernel(const T *L, int n, int64_t ld, T *v,
+                                                           LargeWs ws, int J,
+                                                           const int32_t *status) {
+  if (*status != 0) return;
+  const int base = J * kBig;
+  chain_body<T, LAYOUT, UPDATE>(L, n, ld, J, ws.X + (int64_t)(base / kPanel) * kXBlock, ws.w, ws.p + base,
+                                ws.c + base, ws.sg + base, ws.dn + base, v, (double *)nullptr, ws.scal,
+                                ws.scal);
+}
+
 
 // ------------------------------------------------------------- trailing rows
 // Rows R >= J*256, columns [J*256, min(n, J*256+256)) and below/at the diagonal:

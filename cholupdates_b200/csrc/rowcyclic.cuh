@@ -114,4 +114,156 @@ __global__ void __launch_bounds__(128) rc_trail_kernel(T *A, int m_loc, int n, i
   if (valid && R >= cend) ws.w[R] = w;
 }
 
+// =====================================================================================
+// Wavefront over K successive updates (BASELINE.json configs[4]: "64 successive updates").
+//
+// Task (u, J) = panel J of update u.  It needs task (u-1, J) (the panel after the previous update)
+// and task (u, J-1) (the residual w^{(u)} entering the panel), so all tasks on an anti-diagonal
+// d = u + J are independent: they touch different column panels and different w vectors.  One step =
+// one anti-diagonal:
+//     owner kernel  -- every rank, one CTA per task it owns (J mod G == rank): inverse diagonal
+//                      blocks + chain -> the task's payload (p, c, sigma, L'_kk, z, {t, S})
+//     all-gather    -- ONE exchange per step (host driver, NCCL): G * max_tasks payloads
+//     trail kernel  -- every rank, grid (row blocks, tasks of the step): applies each panel to the
+//                      local rows below it
+// K + nJ - 1 steps replace K * nJ per-panel broadcasts; the per-step latency is amortised over up
+// to min(K, nJ) panels of streaming work.  Same arithmetic as the per-panel kernels above.
+constexpr int kRcwPayload = 5 * kBig + 8;  // p, c, sigma, dn, z, scal[8] ({t, S} leaving the panel)
+
+struct RcWave {
+  double *W;     // [K][n_pad]  residual vector of every update (entries of the owned rows are live)
+  double *scal;  // [K][8]      {t, S} of every update entering its next panel
+  double *X;     // [max_tasks][8][kXBlock]  inverse diagonal blocks of this rank's tasks of the step
+  int64_t n_pad;
+  int K;
+};
+
+inline int rcw_panels(int64_t n) { return (int)((n + kBig - 1) / kBig); }
+inline int rcw_max_tasks(int64_t n, int64_t K, int G) {
+  const int64_t len = K < rcw_panels(n) ? K : rcw_panels(n);
+  return (int)((len + G - 1) / G) > 0 ? (int)((len + G - 1) / G) : 1;
+}
+inline size_t rcw_ws_doubles(int64_t n, int64_t K, int G) {
+  const int64_t n_pad = (n + 31) & ~31LL;
+  return (size_t)(K * n_pad + K * 8 + (int64_t)rcw_max_tasks(n, K, G) * (kBig / kPanel) * kXBlock);
+}
+inline RcWave rcw_carve(void *base, int64_t n, int64_t K, int G) {
+  RcWave wv;
+  wv.n_pad = (n + 31) & ~31LL;
+  wv.K = (int)K;
+  double *d = reinterpret_cast<double *>(base);
+  wv.W = d; d += K * wv.n_pad;
+  wv.scal = d; d += K * 8;
+  wv.X = d;
+  (void)G;
+  return wv;
+}
+
+// W[u] <- V[u] on the owned rows, check_diag on the owned diagonal entries, {t, S} <- {1, 1}.
+template <typename T>
+__global__ void rcw_prepare_kernel(const T *A, int m_loc, int n, int64_t ld, int G, int rank, const T *V,
+                                   int64_t ldv, RcWave wv, int flags, int32_t *status) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int u = blockIdx.y;
+  if (l < m_loc) {
+    const int64_t R = rc_global_row(l, G, rank);
+    if (R < n) {
+      wv.W[(int64_t)u * wv.n_pad + R] = (double)V[(int64_t)u * ldv + R];
+      if (u == 0 && (flags & CHUB_FLAG_CHECK_DIAG) && A[(int64_t)l * ld + R] == T(0))
+        atomicMax(status, CHUB_STATUS_ZERO_DIAG);
+    }
+  }
+  if (l == 0) {
+    wv.scal[u * 8 + 0] = 1.0;
+    wv.scal[u * 8 + 1] = 1.0;
+  }
+}
+
+// One CTA (256 threads) per task of this rank on anti-diagonal d: J = Jfirst + blockIdx.x * G,
+// u = d - J.  Writes the task's payload into pay_mine[blockIdx.x].
+template <typename T>
+__global__ void __launch_bounds__(kBig) rcw_owner_kernel(const T *A, int n, int64_t ld, int G, RcWave wv, int d,
+                                                         int Jfirst, double *pay_mine, const int32_t *status) {
+  if (*status != 0) return;
+  const int i = blockIdx.x;
+  const int J = Jfirst + i * G, u = d - J;
+  // the diagonal block of panel J is local block J / G; shift the base so that GLOBAL row indices work
+  const T *Lsh = A + ((int64_t)(J / G) - (int64_t)J) * kRcBlock * ld;
+  double *X = wv.X + (int64_t)i * (kBig / kPanel) * kXBlock;
+  const int warp = threadIdx.x >> 5;
+  // the 8 inverse diagonal blocks, four warps at a time (invdiag_block_to's shared staging holds 4)
+  if (warp < 4) invdiag_block_to<T, CHUB_ROW_MAJOR>(Lsh, n, ld, X + (int64_t)warp * kXBlock, J * (kBig / kPanel) + warp);
+  __syncthreads();
+  if (warp >= 4) invdiag_block_to<T, CHUB_ROW_MAJOR>(Lsh, n, ld, X + (int64_t)warp * kXBlock, J * (kBig / kPanel) + warp);
+  __syncthreads();
+  double *pay = pay_mine + (int64_t)i * kRcwPayload;
+  chain_body<T, CHUB_ROW_MAJOR, true>(Lsh, n, ld, J, X, wv.W + (int64_t)u * wv.n_pad, pay, pay + kBig, pay + 2 * kBig,
+                                      pay + 3 * kBig, (T *)nullptr, pay + 4 * kBig, wv.scal + u * 8, pay + 5 * kBig);
+}
+
+// Trailing update for every task of anti-diagonal d: blockIdx.y = t <-> J = Jlo + t, u = d - J; its
+// payload sits in slot (J mod G) * max_tasks + t / G of the gathered buffer (the owner's tasks are
+// Jfirst, Jfirst + G, ... with Jfirst - Jlo < G).  blockIdx.x = 128 consecutive local rows.
+template <typename T>
+__global__ void __launch_bounds__(128) rcw_trail_kernel(T *A, int m_loc, int n, int64_t ld, int G, int rank, RcWave wv,
+                                                        int d, int Jlo, int max_tasks, const double *pay_all,
+                                                        T *V_out, int64_t ldv, const int32_t *status) {
+  constexpr int NT = 128;
+  __shared__ double cs[3][kPanel];
+  __shared__ __align__(16) T tile[NT * kPanel];
+  if (*status != 0) return;
+  const int tid = threadIdx.x;
+  const int J = Jlo + (int)blockIdx.y, u = d - J;
+  const double *pay = pay_all + ((int64_t)(J % G) * max_tasks + blockIdx.y / G) * kRcwPayload;
+  const int base = J * kBig;
+  if (blockIdx.x == 0) {  // unpack what the next panel of update u and the caller need
+    if (tid < 2) wv.scal[u * 8 + tid] = pay[5 * kBig + tid];
+    if (V_out)
+      for (int k = tid; k < kBig; k += NT)
+        if (base + k < n) V_out[(int64_t)u * ldv + base + k] = (T)pay[4 * kBig + k];
+  }
+  const int l0 = blockIdx.x * NT;
+  if (l0 >= m_loc) return;
+  const int64_t g0 = rc_global_row(l0, G, rank);
+  int rows = min(NT, m_loc - l0);
+  if (g0 + rows > n) rows = (int)max((int64_t)0, (int64_t)n - g0);
+  if (rows <= 0 || g0 + rows <= base) return;  // entirely above the panel
+  const int r0 = (int)g0;
+  T *L = A + ((int64_t)l0 - g0) * ld;  // so that L[R * ld + c] addresses global row R
+  const int R = r0 + tid;
+  const bool valid = tid < rows && R >= base;
+  double *wu = wv.W + (int64_t)u * wv.n_pad;
+  double w = valid ? wu[R] : 0.0;
+  const int cend = min(n, base + kBig);
+  for (int c0 = base; c0 < cend; c0 += kPanel) {
+    const int bw = min(kPanel, n - c0);
+    if (c0 > r0 + rows - 1) break;
+    __syncthreads();
+    if (tid < kPanel) {
+      const int a = c0 - base + tid;
+      cs[0][tid] = tid < bw ? pay[a] : 0.0;
+      cs[1][tid] = tid < bw ? pay[kBig + a] : 1.0;
+      cs[2][tid] = tid < bw ? pay[2 * kBig + a] : 0.0;
+    }
+    tile_load_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
+    __syncthreads();
+    if (valid) {
+#pragma unroll 8
+      for (int k = 0; k < kPanel; ++k) {
+        if (k < bw && c0 + k < R) {
+          const int o = tile_off(tid, k);
+          const double lo = (double)tile[o];
+          tile[o] = (T)(cs[1][k] * lo + cs[2][k] * w);
+          w -= lo * cs[0][k];
+        }
+      }
+      if (R >= c0 && R < c0 + bw) tile[tile_off(tid, R - c0)] = (T)pay[3 * kBig + R - base];
+    }
+    __syncthreads();
+    // rows above the panel inside this CTA (R < base) are loaded but stored back unchanged
+    tile_store_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
+  }
+  if (valid && R >= cend) wu[R] = w;
+}
+
 }  // namespace chub

@@ -6,8 +6,8 @@ is the optional all-gather of the per-factor status vector, so that every rank c
 ``LinAlgError`` -- a few KB over ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests).
 
 The single large factor does not shard on one node's worth of memory pressure (n = 16384 fits one
-GPU): ``bench.py --gpus N`` runs replicas.  The block-row-cyclic mode for n = 65536 is not built yet
-(DESIGN.md section 7).
+GPU): ``bench.py --gpus N`` runs replicas.  The block-row-cyclic mode for one huge factor
+(``RowCyclicFactor``) is below.
 """
 
 from __future__ import annotations
@@ -162,6 +162,58 @@ class _CudaRowCyclicBackend:
     def status_tensor(self):
         return self.status
 
+    # ---- wavefront over K successive updates (chub_rcw_*)
+    def wave_begin(self, V, V_out, check_diag):
+        """Allocate the step buffers, W[u] <- V[u] on the owned rows; returns (pay_mine, pay_all)."""
+        import ctypes
+
+        from . import _lib
+
+        torch, lib = self.torch, self.lib
+        vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+        lib.chub_rcw_workspace_bytes.restype = ctypes.c_size_t
+        lib.chub_rcw_workspace_bytes.argtypes = [i64, i64, ci]
+        lib.chub_rcw_max_tasks.argtypes = [i64, i64, ci]
+        for suf in ("f64", "f32"):
+            f = getattr(lib, f"chub_rcw_prepare_{suf}")
+            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, vp, i64, i64, vp, ci, vp, vp]
+            f = getattr(lib, f"chub_rcw_owner_{suf}")
+            f.restype, f.argtypes = ci, [vp, i64, i64, ci, ci, i64, i64, vp, vp, vp, vp]
+            f = getattr(lib, f"chub_rcw_apply_{suf}")
+            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, i64, i64, vp, vp, vp, i64, vp, vp]
+        K, dev = int(V.shape[0]), self.A.device
+        self.K, self.V_out = K, V_out
+        need = int(lib.chub_rcw_workspace_bytes(self.n, K, self.world))
+        if getattr(self, "wave_ws", None) is None or self.wave_ws.numel() < need:
+            self.wave_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        slots = int(lib.chub_rcw_max_tasks(self.n, K, self.world)) * int(lib.chub_rcw_payload_doubles())
+        pay_all = torch.empty(self.world * slots, dtype=torch.float64, device=dev)
+        pay_mine = pay_all[self.rank * slots:(self.rank + 1) * slots] if self.world == 1 else \
+            torch.empty(slots, dtype=torch.float64, device=dev)
+        rc = getattr(lib, f"chub_rcw_prepare_{self.suf}")(
+            self.A.data_ptr(), self.A.shape[0], self.n, self.A.shape[1], self.world, self.rank,
+            V.data_ptr(), K, V.stride(0), self.wave_ws.data_ptr(),
+            _lib.FLAG_CHECK_DIAG if check_diag else 0, self.status.data_ptr(), self._stream())
+        _lib.check(rc, "chub_rcw_prepare")
+        return pay_mine, pay_all
+
+    def wave_owner(self, d, pay_mine):
+        from . import _lib
+
+        rc = getattr(self.lib, f"chub_rcw_owner_{self.suf}")(
+            self.A.data_ptr(), self.n, self.A.shape[1], self.world, self.rank, self.K, d,
+            self.wave_ws.data_ptr(), pay_mine.data_ptr(), self.status.data_ptr(), self._stream())
+        _lib.check(rc, "chub_rcw_owner")
+
+    def wave_apply(self, d, pay_all):
+        from . import _lib
+
+        rc = getattr(self.lib, f"chub_rcw_apply_{self.suf}")(
+            self.A.data_ptr(), self.A.shape[0], self.n, self.A.shape[1], self.world, self.rank, self.K, d,
+            self.wave_ws.data_ptr(), pay_all.data_ptr(), self.V_out.data_ptr(), self.V_out.stride(0),
+            self.status.data_ptr(), self._stream())
+        _lib.check(rc, "chub_rcw_apply")
+
 
 class RowCyclicFactor:
     """A Cholesky factor of order ``n`` distributed block-row-cyclically: this rank holds
@@ -217,3 +269,44 @@ class RowCyclicFactor:
                 dist.broadcast(payload, src=src, group=self.group)
             be.panel_apply(J, owner == self.rank, payload)
         return v_out
+
+    def update_many(self, V, check_diag: bool = True):
+        """Apply the K successive rank-1 updates ``V[0], V[1], ...`` (``V``: ``(K, n)``, identical on
+        every rank) in place -- the same result as K calls of ``update``, scheduled as a wavefront.
+
+        Panel J of update u needs only panel J of update u-1 and panel J-1 of update u, so all
+        (u, J) with u + J = d are independent.  Step d: every rank computes the coefficients of the
+        diagonal blocks it owns, ONE all-gather ships all of the step's coefficient sets, every rank
+        applies them to its local rows.  ``K + ceil(n/256) - 1`` exchanges replace ``K * ceil(n/256)``
+        broadcasts.  Returns the ``(K, n)`` scratch vectors (rotg's z_k, complete on
+        every rank).  Raises ``LinAlgError`` on every rank, with nothing modified, if ``check_diag``
+        finds a zero on the input diagonal."""
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+
+        if V.ndim != 2 or V.shape[1] != self.n:
+            raise ValueError(
+                f"`V` must hold one vector per row, expected shape (K, {self.n}) but got {tuple(V.shape)}.")
+        K = int(V.shape[0])
+        V_out = torch.zeros_like(V)
+        if K == 0:
+            return V_out
+        if V.stride(1) != 1:
+            raise ValueError("The rows of `V` must be contiguous.")
+        be = self.backend
+        multi = self.world > 1 and dist.is_available() and dist.is_initialized()
+        pay_mine, pay_all = be.wave_begin(V, V_out, check_diag)
+        if check_diag:
+            st = be.status_tensor()
+            if multi:
+                dist.all_reduce(st, op=dist.ReduceOp.MAX, group=self.group)
+            if int(st.item()) == 1:
+                raise np.linalg.LinAlgError("The given Cholesky factor `L` contains zeros on its diagonal")
+        for d in range(K + (self.n + RC_BLOCK - 1) // RC_BLOCK - 1):
+            be.wave_owner(d, pay_mine)
+            if multi:
+                dist.all_gather_into_tensor(pay_all, pay_mine, group=self.group)
+            be.wave_apply(d, pay_all)
+        return V_out
+

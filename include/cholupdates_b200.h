@@ -146,6 +146,33 @@ int chub_rc_panel_apply_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, i
                             int is_owner, void *workspace, const double *payload, int32_t *status,
                             void *stream);
 
+/* ---- K successive updates of one block-row-cyclic factor as a wavefront (BASELINE.json
+ *      configs[4]).  Task (u, J) = panel J of update u depends only on (u-1, J) and
+ *      (u, J-1), so the tasks of an anti-diagonal d = u + J are independent.  Per step d the caller
+ *      runs chub_rcw_owner (this rank's tasks -> pay_mine: chub_rcw_max_tasks() slots of
+ *      chub_rcw_payload_doubles() doubles), ONE all-gather of pay_mine into pay_all
+ *      (G * max_tasks slots, rank-major), then chub_rcw_apply (all tasks of the step on the local
+ *      rows): K + ceil(n/256) - 1 exchanges instead of K * ceil(n/256).  V / V_out: K vectors of n
+ *      elements, leading dimension ldv (V_out may be NULL; it receives rotg's z_k, as v does in the
+ *      reference, .pyx:101,152).  With G == 1 pay_all == pay_mine and no exchange is needed. */
+int chub_rcw_payload_doubles(void);
+int chub_rcw_max_tasks(int64_t n, int64_t K, int G);
+size_t chub_rcw_workspace_bytes(int64_t n, int64_t K, int G);
+int chub_rcw_prepare_f64(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, const void *V,
+                         int64_t K, int64_t ldv, void *workspace, int flags, int32_t *status, void *stream);
+int chub_rcw_prepare_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, const void *V,
+                         int64_t K, int64_t ldv, void *workspace, int flags, int32_t *status, void *stream);
+int chub_rcw_owner_f64(void *A_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
+                       void *workspace, double *pay_mine, int32_t *status, void *stream);
+int chub_rcw_owner_f32(void *A_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
+                       void *workspace, double *pay_mine, int32_t *status, void *stream);
+int chub_rcw_apply_f64(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
+                       void *workspace, const double *pay_all, void *V_out, int64_t ldv, int32_t *status,
+                       void *stream);
+int chub_rcw_apply_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
+                       void *workspace, const double *pay_all, void *V_out, int64_t ldv, int32_t *status,
+                       void *stream);
+
 /* ---- tuning / introspection (bench.py and tests) */
 /* Force a kernel path: 0 = automatic, 1 = single-CTA kernels only, 2 = panel
  * (multi-kernel) path, 3 = persistent dataflow kernel.  Returns the previous value. */

@@ -1,11 +1,12 @@
 """Multi-GPU parity + timing of the block-row-cyclic update (run under torchrun, one rank per GPU):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \\
-        --master-port 29511 tests/multi_gpu_rowcyclic.py [n_parity] [n_time] [updates]
+        --master-port 29511 tests/multi_gpu_rowcyclic.py [n_parity] [n_time] [updates] [K_wave]
 
 Parity: every rank builds the same seeded factor, keeps its own rows, applies 3 successive updates
 through RowCyclicFactor (NCCL broadcast of each panel's coefficients) and compares its rows with the
-oracle (tolerance 1e-12 * sqrt(n)).  Timing: n_time with per-rank generated rows.
+oracle (tolerance 1e-12 * sqrt(n)); then K successive updates through update_many (wavefront, one
+all-gather per anti-diagonal).  Timing: n_time with per-rank generated rows, both forms.
 """
 import os
 import sys
@@ -30,6 +31,7 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
     n_time = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
     updates = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+    k_wave = int(sys.argv[4]) if len(sys.argv) > 4 else 64
 
     import seeger_oracle as oracle
 
@@ -53,6 +55,25 @@ def main():
         print(f"[rowcyclic parity] n={n} world={world}: rel. Frobenius error (rank 0 rows) {err:.2e} "
               f"(bar {tol_for(np.float64, n):.1e}); all ranks ok: {int(t.item()) == 0}", flush=True)
     assert int(t.item()) == 0
+
+    # wavefront form: K successive updates in one call
+    for K in (3, 2 * ((n + 255) // 256) + 1):
+        A = torch.from_numpy(np.ascontiguousarray(L[rows])).to(dev)
+        V = np.stack([np.random.default_rng([2, u]).standard_normal(n) for u in range(K)])
+        RowCyclicFactor(A, n, rank, world).update_many(torch.from_numpy(V.copy()).to(dev))
+        L_ref = np.array(L, order="F")
+        for u in range(K):
+            oracle.update(L_ref, V[u].copy())
+        got = np.where(lower, A.cpu().numpy(), 0.0)
+        want = np.tril(L_ref)[rows]
+        err = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+        ok = err <= tol_for(np.float64, n) and bool(np.all(A.cpu().numpy()[~lower] == 0.0))
+        t = torch.tensor([0 if ok else 1], device=dev)
+        dist.all_reduce(t)
+        if rank == 0:
+            print(f"[rowcyclic wavefront parity] n={n} world={world} K={K}: rel. Frobenius error (rank 0 rows) "
+                  f"{err:.2e} (bar {tol_for(np.float64, n):.1e}); all ranks ok: {int(t.item()) == 0}", flush=True)
+        assert int(t.item()) == 0
 
     # timing at n_time, rows generated per rank
     n = n_time
@@ -84,6 +105,27 @@ def main():
         bytes_upd = 8 * n * (n + 1) + 16 * n
         print(f"[rowcyclic timing] n={n} world={world}: {per:.3f} ms/update, {bytes_upd / per / 1e6:.0f} GB/s aggregate "
               f"({bytes_upd / per / 1e6 / world:.0f} GB/s per GPU)", flush=True)
+    # wavefront: k_wave successive updates in one call (BASELINE.json configs[4]: 64)
+    gv.manual_seed(8)
+    V = torch.randn((k_wave, n), dtype=torch.float64, device=dev, generator=gv)
+    fac.update_many(V[: min(4, k_wave)], check_diag=False)  # warm-up
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    fac.update_many(V, check_diag=False)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        per = float(ms.item()) / k_wave
+        bytes_upd = 8 * n * (n + 1) + 16 * n
+        print(f"[rowcyclic wavefront timing] n={n} world={world} K={k_wave}: {per:.3f} ms/update "
+              f"({float(ms.item()):.1f} ms total), {bytes_upd / per / 1e6:.0f} GB/s aggregate "
+              f"({bytes_upd / per / 1e6 / world:.0f} GB/s per GPU)", flush=True)
+    finite = bool(torch.isfinite(A).all().item())
+    assert finite
     dist.destroy_process_group()
 
 

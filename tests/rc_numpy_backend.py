@@ -75,3 +75,77 @@ class NumpyRowCyclicBackend:
 
     def status_tensor(self):
         return self.status
+
+    # ---- wavefront over K successive updates (same slot layout as csrc/rowcyclic.cuh)
+    PAY = 5 * RC_BLOCK + 8
+
+    def _span(self, d):
+        nJ = (self.n + RC_BLOCK - 1) // RC_BLOCK
+        return max(0, d - self.K + 1), min(nJ - 1, d)
+
+    def wave_begin(self, V, V_out, check_diag):
+        self.K, self.V_out = int(V.shape[0]), V_out.numpy()
+        nJ = (self.n + RC_BLOCK - 1) // RC_BLOCK
+        self.max_tasks = max(1, -(-min(self.K, nJ) // self.world))
+        self.W = np.zeros((self.K, self.n))
+        self.W[:, self.rows] = V.numpy()[:, self.rows]
+        self.tS = np.ones((self.K, 2))
+        self.status[0] = 0
+        if check_diag and np.any(self.A[np.arange(len(self.rows)), self.rows] == 0):
+            self.status[0] = 1
+        slots = self.max_tasks * self.PAY
+        pay_all = torch.zeros(self.world * slots, dtype=torch.float64)
+        pay_mine = pay_all[:slots] if self.world == 1 else torch.zeros(slots, dtype=torch.float64)
+        return pay_mine, pay_all
+
+    def wave_owner(self, d, pay_mine):
+        Jlo, Jhi = self._span(d)
+        Jfirst = Jlo + (self.rank - Jlo) % self.world
+        buf = pay_mine.numpy()
+        for i, J in enumerate(range(Jfirst, Jhi + 1, self.world)):
+            u = d - J
+            j0, j1 = J * RC_BLOCK, min(self.n, (J + 1) * RC_BLOCK)
+            m = j1 - j0
+            loc = np.searchsorted(self.rows, np.arange(j0, j1))
+            LD = np.tril(self.A[loc, j0:j1])
+            p = np.linalg.solve(LD, self.W[u, j0:j1])
+            dg = np.diag(LD)
+            t_in, S_in = self.tS[u]
+            t_incl = t_in + np.cumsum(p * p)
+            t_excl = np.concatenate(([t_in], t_incl[:-1]))
+            sgn = np.where(dg < 0, -1.0, 1.0)
+            rinv = 1.0 / np.sqrt(t_excl * t_incl)
+            pay = buf[i * self.PAY:(i + 1) * self.PAY]
+            pay[:] = 0
+            pay[0:m] = p
+            pay[RC_BLOCK:RC_BLOCK + m] = sgn * t_excl * rinv
+            pay[2 * RC_BLOCK:2 * RC_BLOCK + m] = sgn * p * rinv
+            pay[3 * RC_BLOCK:3 * RC_BLOCK + m] = np.abs(dg) * t_incl * rinv
+            pay[4 * RC_BLOCK:4 * RC_BLOCK + m] = 0.5  # stands in for rotg's z (scratch)
+            pay[5 * RC_BLOCK], pay[5 * RC_BLOCK + 1] = t_incl[-1], S_in * np.prod(sgn)
+
+    def wave_apply(self, d, pay_all):
+        Jlo, Jhi = self._span(d)
+        buf = pay_all.numpy()
+        for J in range(Jlo, Jhi + 1):
+            u, t = d - J, J - Jlo
+            slot = (J % self.world) * self.max_tasks + t // self.world
+            pay = buf[slot * self.PAY:(slot + 1) * self.PAY]
+            j0, j1 = J * RC_BLOCK, min(self.n, (J + 1) * RC_BLOCK)
+            m = j1 - j0
+            self.tS[u] = pay[5 * RC_BLOCK], pay[5 * RC_BLOCK + 1]
+            self.V_out[u, j0:j1] = pay[4 * RC_BLOCK:4 * RC_BLOCK + m]
+            sel = np.nonzero(self.rows >= j0)[0]
+            if sel.size == 0:
+                continue
+            R = self.rows[sel]
+            w = self.W[u, R].copy()
+            for k in range(j0, j1):
+                a = k - j0
+                below = R > k
+                lo = self.A[sel, k].copy()
+                self.A[sel[below], k] = pay[RC_BLOCK + a] * lo[below] + pay[2 * RC_BLOCK + a] * w[below]
+                w[below] -= lo[below] * pay[a]
+                self.A[sel[R == k], k] = pay[3 * RC_BLOCK + a]
+            keep = R >= j1
+            self.W[u, R[keep]] = w[keep]

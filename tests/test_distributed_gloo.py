@@ -132,6 +132,22 @@ def _rc_worker(rank, world, port, tmpdir):
         err = np.linalg.norm(got - want) / np.linalg.norm(want)
         assert err <= tol_for(np.float64, n), err
         assert np.all(A_loc.numpy()[~lower] == 0.0)  # nothing above the diagonal was written
+        # K successive updates as a wavefront (one all-gather per anti-diagonal of (update, panel) tasks):
+        # same result as K calls of update(); K > number of panels and K < number of panels both occur
+        for K in (2, 7):
+            A2 = torch.from_numpy(np.ascontiguousarray(L[rows]))
+            fac2 = RowCyclicFactor(A2, n, rank, world, backend=NumpyRowCyclicBackend(A2, n, rank, world))
+            V = np.stack([np.random.default_rng([2, u]).standard_normal(n) for u in range(K)])
+            z = fac2.update_many(torch.from_numpy(V.copy()))
+            assert z.shape == (K, n) and bool(torch.all(z == 0.5))  # every rank sees every panel's scratch
+            L_ref2 = np.array(L, order="F")
+            for u in range(K):
+                oracle.update(L_ref2, V[u].copy())
+            got2 = np.where(lower, A2.numpy(), 0.0)
+            want2 = np.tril(L_ref2)[rows]
+            err2 = np.linalg.norm(got2 - want2) / np.linalg.norm(want2)
+            assert err2 <= tol_for(np.float64, n), (K, err2)
+            assert np.all(A2.numpy()[~lower] == 0.0)
         # zero on the diagonal of a row owned by rank 1: both ranks raise, nothing is modified
         before = A_loc.clone()
         if 300 in rows:
@@ -139,6 +155,12 @@ def _rc_worker(rank, world, port, tmpdir):
             before = A_loc.clone()
         try:
             fac.update(torch.from_numpy(np.ones(n)))
+            raised = False
+        except np.linalg.LinAlgError:
+            raised = True
+        assert raised and torch.equal(before, A_loc)
+        try:
+            fac.update_many(torch.from_numpy(np.ones((3, n))))
             raised = False
         except np.linalg.LinAlgError:
             raised = True

@@ -366,6 +366,39 @@ def test_rowcyclic_single_rank_matches_oracle(n):
     assert torch.equal(keep, Lz)
 
 
+@pytest.mark.parametrize("n,K", [(300, 1), (700, 5), (1000, 2), (2048, 11)])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_rowcyclic_wavefront_single_rank_matches_oracle(n, K, dtype):
+    """K successive updates as one wavefront (anti-diagonals of (update, panel) tasks) == K oracle calls;
+    the scratch vectors are rotg's z_k, as the Cython path leaves them in v."""
+    from cholupdates_b200.distributed import RowCyclicFactor
+
+    L = synth_factor(n, 33).astype(dtype)
+    L[:, 3] *= -1.0
+    V = np.stack([np.random.default_rng([9, u]).standard_normal(n) for u in range(K)]).astype(dtype)
+    A = torch.from_numpy(L.copy()).cuda()
+    A_upper = torch.triu(torch.full_like(A, float("nan")), 1)
+    A += A_upper  # the strict upper triangle must never reach the arithmetic
+    Z = RowCyclicFactor(A, n).update_many(torch.from_numpy(V.copy()).cuda())
+    L_ref = np.array(L, order="F")
+    z_ref = []
+    for u in range(K):
+        vu = V[u].copy()
+        oracle.update(L_ref, vu)
+        z_ref.append(vu)
+    got = A.cpu().numpy()
+    assert rel_fro(got, L_ref) <= tol_for(dtype, n) * (1 if dtype == np.float64 else K)
+    assert np.all(np.isnan(got[np.triu_indices(n, 1)]))
+    if dtype == np.float64:
+        np.testing.assert_allclose(Z.cpu().numpy(), np.stack(z_ref), rtol=1e-8, atol=1e-10)
+    Lz = torch.from_numpy(L.copy()).cuda()
+    Lz[n // 2, n // 2] = 0.0
+    keep = Lz.clone()
+    with pytest.raises(np.linalg.LinAlgError):
+        RowCyclicFactor(Lz, n).update_many(torch.ones((2, n), dtype=Lz.dtype, device="cuda"))
+    assert torch.equal(keep, Lz)
+
+
 def test_sharded_batched_single_process():
     from cholupdates_b200.distributed import shard_bounds, sharded_batched
 
