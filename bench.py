@@ -57,6 +57,10 @@ def measured_peaks():
 
 # ------------------------------------------------------------------- clocks sampling
 class ClockSampler:
+    """SM clock / throttle reasons sampled DURING the timed region.  NVML (nvidia_ml_py) from a
+    background thread every ~2 ms -- the timed region of the headline workload is only tens of
+    milliseconds, too short for `nvidia-smi -lms`; nvidia-smi is the fallback when NVML is missing."""
+
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -64,8 +68,48 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.gpu_index = gpu_index
         self.proc = None
+        self.thread = None
+        self.samples = []  # (t, sm_mhz, power_w, reasons_bitmask)
+        self.t_begin = self.t_end = None
+        self._stop = False
+
+    def _nvml_loop(self, nv, handle):
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                try:
+                    power = nv.nvmlDeviceGetPowerUsage(handle) / 1000.0
+                except Exception:  # noqa: BLE001
+                    power = 0.0
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                except Exception:  # noqa: BLE001
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.samples.append((time.perf_counter(), float(sm), power, int(reasons)))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import threading
+
+            import pynvml as nv
+
+            nv.nvmlInit()
+            # NVML enumerates physical GPUs: honour CUDA_VISIBLE_DEVICES if it lists indices
+            idx = self.gpu_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu_index])
+            handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.nv, self.handle = nv, handle
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.thread = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
@@ -74,7 +118,37 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
+
     def stop(self):
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            nv = self.nv
+            inside = [x for x in self.samples
+                      if self.t_begin is not None and self.t_end is not None and self.t_begin <= x[0] <= self.t_end]
+            use = inside if inside else self.samples
+            if not use:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            bits = 0
+            for x in use:
+                bits |= x[3]
+            table = [("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                     ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                     ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                     ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap")]
+            reasons = []
+            for name, a, b in table:
+                mask = getattr(nv, a, None) or getattr(nv, b, 0)
+                if bits & int(mask):
+                    reasons.append(name)
+            return {"sm_mhz": statistics.median(x[1] for x in use), "sm_max_mhz": self.sm_max,
+                    "samples": len(use), "in_timed_region": bool(inside), "source": "nvml",
+                    "power_w_max": max(x[2] for x in use), "reasons": sorted(reasons)}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -99,7 +173,7 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "samples": len(sm),
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "samples": len(sm), "source": "nvidia-smi",
                 "power_w_max": max(power), "reasons": sorted(reasons)}
 
 
@@ -320,6 +394,7 @@ def run_gpu_arm(args):
            for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record(stream)
     for i in range(args.steps):
         evs[i][0].record(stream)
@@ -329,6 +404,7 @@ def run_gpu_arm(args):
     # pre-pass (prepare + diagonal inverses), persistent kernel)
     e1.record(stream)
     barrier()
+    sampler.mark_end()
     launches = int(lib.chub_launch_count(0))
     clocks = sampler.stop()
     if args.workload == "update":
@@ -345,8 +421,19 @@ def run_gpu_arm(args):
     ms_per_step = total_ms / args.steps
     kernel_ms = statistics.mean(step_ms)  # one update (all its launches) on the device
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    # (profiles/ncu_traffic.json; null if this workload has none)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            ent = json.load(f).get(config["workload"])
+        if ent:
+            traffic, traffic_src = ent["traffic"], ent["source"]
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
                 "algorithmic_bytes": alg_bytes, "kernel_ms": kernel_ms,
                 "kernel_ms_best": min(step_ms)}
 
@@ -462,7 +549,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="update", choices=["update", "batched"])

@@ -280,6 +280,54 @@ int rc_panel_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int ran
   }
   return 0;
 }
+// ---- distributed downdate: forward substitution panel by panel, then a local sweep
+template <typename T>
+int rc_dd_panel_owner(void *A, int64_t n, int64_t ld, int G, int rank, int J, void *workspace, double *payload,
+                      int32_t *status, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  LargeWs ws = large_ws_carve(workspace, n);
+  (void)rank;
+  T *Lsh = (T *)A + ((int64_t)(J / G) - (int64_t)J) * kRcBlock * ld;
+  large_invdiag_kernel<T, CHUB_ROW_MAJOR><<<(kBig / 32 + 3) / 4, 128, 0, st>>>(Lsh, (int)n, ld, ws, status,
+                                                                                J * (kBig / 32), kBig / 32);
+  LAUNCHED();
+  large_chain_kernel<T, CHUB_ROW_MAJOR, false><<<1, kBig, 0, st>>>(Lsh, (int)n, ld, (T *)nullptr, ws, J, status);
+  LAUNCHED();
+  rc_pack_dd_kernel<T><<<1, kBig, 0, st>>>(Lsh, (int)n, ld, ws, J, payload, status);
+  LAUNCHED();
+  return 0;
+}
+template <typename T>
+int rc_dd_panel_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int J, void *workspace,
+                      const double *payload, int32_t *status, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  LargeWs ws = large_ws_carve(workspace, n);
+  rc_unpack_dd_kernel<<<1, kBig, 0, st>>>(ws, J, payload, status);  // (the owner too: it sets the signs)
+  LAUNCHED();
+  if (m_loc > 0 && (int64_t)(J + 1) * kBig < n) {
+    rc_trail_kernel<T, false><<<(unsigned)((m_loc + 127) / 128), 128, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank,
+                                                                              ws, J, status);
+    LAUNCHED();
+  }
+  return 0;
+}
+// rho^2 = 1 - p.p, the status word (CHUB_STATUS_NOT_PD leaves A untouched and v <- p), coefficients and
+// rotg's z into v -- computed redundantly (and identically) on every rank -- then the local sweep.
+template <typename T>
+int rc_dd_finish(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, void *v, void *workspace,
+                 int32_t *status, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  LargeWs ws = large_ws_carve(workspace, n);
+  large_dd_coef_kernel<T, CHUB_ROW_MAJOR><<<1, 1024, 0, st>>>((const T *)nullptr, (int)n, ld, (T *)v, ws, status);
+  LAUNCHED();
+  if (m_loc > 0) {
+    rc_dd_sweep_kernel<T><<<(unsigned)((m_loc + 127) / 128), 128, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, ws,
+                                                                          status);
+    LAUNCHED();
+  }
+  return 0;
+}
+
 // ---- wavefront over K successive updates of a block-row-cyclic factor (rowcyclic.cuh)
 template <typename T>
 int rcw_prepare(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, const void *V, int64_t K,
@@ -422,6 +470,22 @@ size_t chub_rcw_workspace_bytes(int64_t n, int64_t K, int G) {
   if (K < 0) K = 0;
   return rcw_ws_doubles(n, K, G > 0 ? G : 1) * sizeof(double);
 }
+#define DEFINE_RC_DD(SUF, T)                                                                                      \
+  int chub_rc_dd_panel_owner_##SUF(void *A, int64_t n, int64_t ld, int G, int rank, int J, void *workspace,       \
+                                   double *payload, int32_t *status, void *stream) {                              \
+    return rc_dd_panel_owner<T>(A, n, ld, G, rank, J, workspace, payload, status, stream);                        \
+  }                                                                                                               \
+  int chub_rc_dd_panel_apply_##SUF(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int J,         \
+                                   void *workspace, const double *payload, int32_t *status, void *stream) {       \
+    return rc_dd_panel_apply<T>(A, m_loc, n, ld, G, rank, J, workspace, payload, status, stream);                 \
+  }                                                                                                               \
+  int chub_rc_dd_finish_##SUF(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, void *v,            \
+                              void *workspace, int32_t *status, void *stream) {                                   \
+    return rc_dd_finish<T>(A, m_loc, n, ld, G, rank, v, workspace, status, stream);                               \
+  }
+DEFINE_RC_DD(f64, double)
+DEFINE_RC_DD(f32, float)
+
 #define DEFINE_RCW(SUF, T)                                                                                         \
   int chub_rcw_prepare_##SUF(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, const void *V,        \
                              int64_t K, int64_t ldv, void *workspace, int flags, int32_t *status, void *stream) {  \

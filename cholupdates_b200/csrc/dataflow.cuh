@@ -910,7 +910,8 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
   unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);  // [nrw][kDfStages]
   unsigned long long *cfull = full + kDfStages * 2 * kRmMaxQ;               // [kDfCoefRing]
   volatile int *prog = reinterpret_cast<volatile int *>(cfull + kDfCoefRing);  // [32] steps finished per row warp
-  volatile int *cprog = prog + 32;  // block columns whose coefficients are in the ring
+  volatile int *cprog = prog + 32;  // block columns whose coefficients (c, sigma, dn) are in the ring
+  volatile int *pprog = prog + 33;  // block columns whose p is in the ring (always >= *cprog)
   double *coef = reinterpret_cast<double *>(smem + 2048);                   // [kDfCoefRing][4][32]
   unsigned char *stages = smem + 2048 + kDfCoefRing * 4 * kPanel * 8;       // 1024-aligned
 
@@ -920,7 +921,7 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
     fence_mbar_init();
   }
   if (tid < 32) prog[tid] = tid < nrw ? 0 : 0x7fffffff;
-  if (tid == 0) *cprog = 0;
+  if (tid == 0) { *cprog = 0; *pprog = 0; }
   __syncthreads();
   if (warp > nrw) return;
 
@@ -954,6 +955,10 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
       }
       double *cf = coef + (size_t)slot * 4 * kPanel;
       cf[lane] = pk;
+      // p alone is enough for the residual w (and for the hand-over to the chain, which is on the
+      // chain <-> worker latency loop): publish it before the scan / rsqrt of the coefficients
+      __syncwarp();
+      if (lane == 0) st_release_cta_smem(pprog, pan + 1);
       if (UPDATE) {
         double incl = pk * pk;
 #pragma unroll
@@ -1050,9 +1055,7 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
       const double2 a = *reinterpret_cast<const double2 *>(cf + j);
-      const double2 c = *reinterpret_cast<const double2 *>(cf + kPanel + j);
-      const double2 d = *reinterpret_cast<const double2 *>(cf + 2 * kPanel + j);
-      pc[j] = a.x; pc[j + 1] = a.y; cc[j] = c.x; cc[j + 1] = c.y; sc[j] = d.x; sc[j + 1] = d.y;
+      pc[j] = a.x; pc[j + 1] = a.y;
     }
     double lo[8], pre[8];  // pre[j] = sum_{m<j} lo_m p_m within my segment
     double run = 0.0;
@@ -1087,6 +1090,19 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
       if (lane == 0 && (row0 & 31) == 0) DF_TRACE(0, b);
     }
     if (UPDATE) {
+      // c, sigma (and dn) of this block column: normally long there; only the hand-over step runs ahead
+      if (ld_acquire_cta_smem(cprog) <= pan) {
+        const long long t0 = clock64();
+        while (ld_acquire_cta_smem(cprog) <= pan) {
+          if (clock64() - t0 > kWatchdogCycles) { atomicMax(P.status, CHUB_STATUS_INTERNAL); break; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const double2 c = *reinterpret_cast<const double2 *>(cf + kPanel + j);
+        const double2 d = *reinterpret_cast<const double2 *>(cf + 2 * kPanel + j);
+        cc[j] = c.x; cc[j + 1] = c.y; sc[j] = d.x; sc[j + 1] = d.y;
+      }
       if (!diag_step) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] = (T)fma(cc[j], lo[j], sc[j] * (wseg - pre[j]));
@@ -1140,21 +1156,24 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
     if (two) mbar_wait(&myfull[st1], ph, P.status);
     if (prof_me) DF_PROF_ADD(1, tp);
     tp = DF_PROF_T();
-    {
-      // coefficients up to block column min(s+1, T-1): implies p_{s+1} is published, i.e. the
-      // chain has consumed everything these two steps overwrite
-      const int need = min(two ? s + 1 : s, T_ - 1) + 1;
-      if (ld_acquire_cta_smem(cprog) < need) {
+    // Step s is gated on p_s (in the ring): p_s published implies that the chain has consumed
+    // everything step s overwrites.  Each step waits for its own p only, so that the hand-over step
+    // (on the chain <-> worker latency loop) never waits for the block column after it.
+    auto wait_p = [&](int step) {
+      const int need = min(step, T_ - 1) + 1;
+      if (ld_acquire_cta_smem(pprog) < need) {
         const long long t0 = clock64();
-        while (ld_acquire_cta_smem(cprog) < need) {
+        while (ld_acquire_cta_smem(pprog) < need) {
           if (clock64() - t0 > kWatchdogCycles) { atomicMax(P.status, CHUB_STATUS_INTERNAL); break; }
         }
       }
-    }
+    };
+    wait_p(s);
     if (prof_me) DF_PROF_ADD(4, tp);
     if (prof_me && wkr == 0 && s < T_) DF_TRACE(5, s);
     tp = DF_PROF_T();
     const bool store0 = do_step(s, st);
+    if (two) wait_p(s + 1);
     const bool store1 = two ? do_step(s + 1, st1) : false;
     if (prof_me) DF_PROF_ADD(3, tp);
     if (prof_me && wkr == 0 && s < T_) DF_TRACE(6, s);
@@ -1173,10 +1192,13 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
     __syncwarp();
     const bool st0 = __any_sync(0xffffffffu, store0), st1b = __any_sync(0xffffffffu, store1);
     if (elect_one()) {
+      // progress counter for the coefficient warp (ring-slot reuse).  Every lane's coefficient reads of
+      // this pair are complete (their values went into the tile writes the fence above ordered, and the
+      // __syncwarp orders the lanes), so a plain store is enough: no second MEMBAR on the row warps' path.
+      prog[warp] = s + 1 >= last_step ? 0x7fffffff : s + 2;
       if (st0) issue_store(s, st);
       if (st1b) issue_store(s + 1, st1);
       bulk_commit();
-      st_release_cta_smem(prog + warp, s + 1 >= last_step ? 0x7fffffff : s + 2);
     }
     __syncwarp();
     st = stn;

@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(1024) large_dd_coef_kernel(const T *L, int n, 
     const double c = qk1 / qk, s = pk / qk;
     ws.c[k] = c;
     ws.sg[k] = s;
-    ws.dn[k] = L[idx<LAYOUT>(k, k, ld)] < T(0) ? -1.0 : 1.0;
+    if (L) ws.dn[k] = L[idx<LAYOUT>(k, k, ld)] < T(0) ? -1.0 : 1.0;  // (L == nullptr: ws.dn already holds the signs)
     v[k] = rotg_z<T>(T(qk1), T(pk), T(c), T(s));
   }
 }

@@ -63,7 +63,9 @@ __global__ void rc_unpack_kernel(LargeWs ws, int J, const double *buf, int32_t *
 
 // Trailing update of the local rows whose global index is >= J*256 (same arithmetic as
 // large_trail_kernel<T, ROW_MAJOR, true>; one CTA = 128 consecutive local = global rows).
-template <typename T>
+// UPDATE = false is the read-only pass of the downdate's forward substitution (w <- w - L p on the
+// rows below the panel's diagonal block; the block's own rows are finished by the chain).
+template <typename T, bool UPDATE = true>
 __global__ void __launch_bounds__(128) rc_trail_kernel(T *A, int m_loc, int n, int64_t ld, int G, int rank,
                                                        LargeWs ws, int J, const int32_t *status) {
   constexpr int NT = 128;
@@ -77,11 +79,11 @@ __global__ void __launch_bounds__(128) rc_trail_kernel(T *A, int m_loc, int n, i
   const int base = J * kBig;
   int rows = min(NT, m_loc - l0);
   if (g0 + rows > n) rows = (int)max((int64_t)0, (int64_t)n - g0);
-  if (rows <= 0 || g0 + rows <= base) return;  // entirely above the panel
+  if (rows <= 0 || g0 + rows <= base + (UPDATE ? 0 : kBig)) return;  // entirely above the panel
   const int r0 = (int)g0;
   T *L = A + ((int64_t)l0 - g0) * ld;  // so that L[R * ld + c] addresses global row R
   const int R = r0 + tid;
-  const bool valid = tid < rows && R >= base;
+  const bool valid = tid < rows && R >= base + (UPDATE ? 0 : kBig);
   double w = valid ? ws.w[R] : 0.0;
   const int cend = min(n, base + kBig);
   for (int c0 = base; c0 < cend; c0 += kPanel) {
@@ -90,8 +92,10 @@ __global__ void __launch_bounds__(128) rc_trail_kernel(T *A, int m_loc, int n, i
     __syncthreads();
     if (tid < kPanel) {
       cs[0][tid] = tid < bw ? ws.p[c0 + tid] : 0.0;
-      cs[1][tid] = tid < bw ? ws.c[c0 + tid] : 1.0;
-      cs[2][tid] = tid < bw ? ws.sg[c0 + tid] : 0.0;
+      if (UPDATE) {
+        cs[1][tid] = tid < bw ? ws.c[c0 + tid] : 1.0;
+        cs[2][tid] = tid < bw ? ws.sg[c0 + tid] : 0.0;
+      }
     }
     tile_load_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
     __syncthreads();
@@ -101,17 +105,86 @@ __global__ void __launch_bounds__(128) rc_trail_kernel(T *A, int m_loc, int n, i
         if (k < bw && c0 + k < R) {
           const int o = tile_off(tid, k);
           const double lo = (double)tile[o];
-          tile[o] = (T)(cs[1][k] * lo + cs[2][k] * w);
+          if (UPDATE) tile[o] = (T)(cs[1][k] * lo + cs[2][k] * w);
           w -= lo * cs[0][k];
         }
       }
-      if (R >= c0 && R < c0 + bw) tile[tile_off(tid, R - c0)] = (T)ws.dn[R];
+      if (UPDATE && R >= c0 && R < c0 + bw) tile[tile_off(tid, R - c0)] = (T)ws.dn[R];
     }
-    __syncthreads();
-    // rows above the panel inside this CTA (R < base) are loaded but never stored back changed
-    tile_store_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
+    if (UPDATE) {
+      __syncthreads();
+      // rows above the panel inside this CTA (R < base) are loaded but never stored back changed
+      tile_store_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
+    }
   }
   if (valid && R >= cend) ws.w[R] = w;
+}
+
+// ---- downdate: distributed forward substitution, then a purely local sweep
+// Owner of panel J: p of the panel (from the chain) and the signs of its input diagonal entries.
+template <typename T>
+__global__ void rc_pack_dd_kernel(const T *Lsh, int n, int64_t ld, LargeWs ws, int J, double *buf,
+                                  const int32_t *status) {
+  const int t = threadIdx.x;  // kBig threads
+  const int k = J * kBig + t;
+  buf[t] = k < n ? ws.p[k] : 0.0;
+  buf[3 * kBig + t] = (k < n && Lsh[(int64_t)k * ld + k] < T(0)) ? -1.0 : 1.0;
+  if (t == 7) buf[4 * kBig + 7] = (double)*status;
+}
+__global__ void rc_unpack_dd_kernel(LargeWs ws, int J, const double *buf, int32_t *status) {
+  const int t = threadIdx.x;
+  const int k = J * kBig + t;
+  ws.p[k] = buf[t];
+  ws.dn[k] = buf[3 * kBig + t];
+  if (t == 7 && buf[4 * kBig + 7] != 0.0) atomicMax(status, (int)buf[4 * kBig + 7]);
+}
+
+// Reverse sweep of the local rows (same arithmetic as large_dd_sweep_kernel<T, ROW_MAJOR>):
+// rows are independent once every rank holds all (c_k, s_k, sign_k), so there is no exchange.
+// One CTA = 128 consecutive local = global rows.
+template <typename T>
+__global__ void __launch_bounds__(128) rc_dd_sweep_kernel(T *A, int m_loc, int n, int64_t ld, int G, int rank,
+                                                          LargeWs ws, const int32_t *status) {
+  constexpr int NT = 128;
+  __shared__ double cs[3][kPanel];
+  __shared__ __align__(16) T tile[NT * kPanel];
+  if (*status != 0) return;
+  const int tid = threadIdx.x;
+  const int nblk = (m_loc + NT - 1) / NT;
+  const int l0 = (nblk - 1 - (int)blockIdx.x) * NT;  // longest rows first
+  const int64_t g0 = rc_global_row(l0, G, rank);
+  int rows = min(NT, m_loc - l0);
+  if (g0 + rows > n) rows = (int)max((int64_t)0, (int64_t)n - g0);
+  if (rows <= 0) return;
+  const int r0 = (int)g0;
+  T *L = A + ((int64_t)l0 - g0) * ld;
+  const int R = r0 + tid;
+  const bool valid = tid < rows;
+  double x = 0.0;
+  for (int c0 = ((r0 + rows - 1) / kPanel) * kPanel; c0 >= 0; c0 -= kPanel) {
+    const int bw = min(kPanel, n - c0);
+    __syncthreads();
+    if (tid < kPanel) {
+      cs[0][tid] = tid < bw ? ws.c[c0 + tid] : 1.0;
+      cs[1][tid] = tid < bw ? ws.sg[c0 + tid] : 0.0;
+      cs[2][tid] = tid < bw ? ws.dn[c0 + tid] : 1.0;
+    }
+    tile_load_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
+    __syncthreads();
+    if (valid) {
+#pragma unroll 8
+      for (int kk = kPanel - 1; kk >= 0; --kk) {
+        if (kk < bw && c0 + kk <= R) {
+          const int o = tile_off(tid, kk);
+          const double lo = (double)tile[o], c = cs[0][kk], s = cs[1][kk];
+          tile[o] = (T)(cs[2][kk] * (c * lo - s * x));
+          x = c * x + s * lo;
+        }
+      }
+    }
+    __syncthreads();
+    tile_store_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
+  }
 }
 
 // =====================================================================================

@@ -162,6 +162,51 @@ class _CudaRowCyclicBackend:
     def status_tensor(self):
         return self.status
 
+    # ---- downdate (chub_rc_dd_*)
+    def _bind_dd(self):
+        import ctypes
+
+        if getattr(self, "_dd_bound", False):
+            return
+        vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+        for suf in ("f64", "f32"):
+            f = getattr(self.lib, f"chub_rc_dd_panel_owner_{suf}")
+            f.restype, f.argtypes = ci, [vp, i64, i64, ci, ci, ci, vp, vp, vp, vp]
+            f = getattr(self.lib, f"chub_rc_dd_panel_apply_{suf}")
+            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, ci, vp, vp, vp, vp]
+            f = getattr(self.lib, f"chub_rc_dd_finish_{suf}")
+            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, vp, vp, vp, vp]
+        self._dd_bound = True
+
+    def dd_panel_owner(self, J, payload):
+        from . import _lib
+
+        self._bind_dd()
+        rc = getattr(self.lib, f"chub_rc_dd_panel_owner_{self.suf}")(
+            self.A.data_ptr(), self.n, self.A.shape[1], self.world, self.rank, J, self.ws.data_ptr(),
+            payload.data_ptr(), self.status.data_ptr(), self._stream())
+        _lib.check(rc, "chub_rc_dd_panel_owner")
+
+    def dd_panel_apply(self, J, payload):
+        from . import _lib
+
+        self._bind_dd()
+        rc = getattr(self.lib, f"chub_rc_dd_panel_apply_{self.suf}")(
+            self.A.data_ptr(), self.A.shape[0], self.n, self.A.shape[1], self.world, self.rank, J,
+            self.ws.data_ptr(), payload.data_ptr(), self.status.data_ptr(), self._stream())
+        _lib.check(rc, "chub_rc_dd_panel_apply")
+
+    def dd_finish(self):
+        """rho^2 test + coefficients (every rank, identical) and the local sweep; returns the status."""
+        from . import _lib
+
+        self._bind_dd()
+        rc = getattr(self.lib, f"chub_rc_dd_finish_{self.suf}")(
+            self.A.data_ptr(), self.A.shape[0], self.n, self.A.shape[1], self.world, self.rank,
+            self.v_out.data_ptr(), self.ws.data_ptr(), self.status.data_ptr(), self._stream())
+        _lib.check(rc, "chub_rc_dd_finish")
+        return int(self.status.item())
+
     # ---- wavefront over K successive updates (chub_rcw_*)
     def wave_begin(self, V, V_out, check_diag):
         """Allocate the step buffers, W[u] <- V[u] on the owned rows; returns (pay_mine, pay_all)."""
@@ -268,6 +313,46 @@ class RowCyclicFactor:
                 src = owner if self.group is None else dist.get_global_rank(self.group, owner)
                 dist.broadcast(payload, src=src, group=self.group)
             be.panel_apply(J, owner == self.rank, payload)
+        return v_out
+
+    def downdate(self, v, check_diag: bool = True):
+        """In-place rank-1 downdate ``L L^T - v v^T`` of the distributed factor (reference semantics:
+        ``_seeger_impl_cython.pyx:160-330``).  The forward substitution ``p = L^{-1} v`` runs panel by
+        panel (the owner of each diagonal block broadcasts the panel's ``p``; every rank updates the
+        residual of its rows below); ``rho^2 = 1 - p.p`` is then formed identically on every rank, and
+        the reverse sweep touches only local rows -- no further exchange.  Returns the
+        scratch vector (rotg's z_k; ``p`` if the result is not positive definite).  Raises
+        ``numpy.linalg.LinAlgError`` on every rank, with the factor untouched, for a zero on the
+        diagonal (``check_diag``) or when the downdated matrix is not positive definite."""
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+
+        if v.ndim != 1 or v.shape[0] != self.n:
+            raise ValueError(
+                f"The shape of the given vector `v` is incompatible with the shape of the given "
+                f"Cholesky factor `L`. Expected shape {(self.n,)} but got {tuple(v.shape)}.")
+        be = self.backend
+        multi = self.world > 1 and dist.is_available() and dist.is_initialized()
+        v_out = torch.zeros_like(v)
+        be.prepare(v, v_out, check_diag)
+        if check_diag:
+            st = be.status_tensor()
+            if multi:
+                dist.all_reduce(st, op=dist.ReduceOp.MAX, group=self.group)
+            if int(st.item()) == 1:
+                raise np.linalg.LinAlgError("The given Cholesky factor `L` contains zeros on its diagonal")
+        payload = be.new_payload()
+        for J in range((self.n + RC_BLOCK - 1) // RC_BLOCK):
+            owner = J % self.world
+            if owner == self.rank:
+                be.dd_panel_owner(J, payload)
+            if multi:
+                src = owner if self.group is None else dist.get_global_rank(self.group, owner)
+                dist.broadcast(payload, src=src, group=self.group)
+            be.dd_panel_apply(J, payload)
+        if be.dd_finish() == 2:
+            raise np.linalg.LinAlgError("The downdated matrix is not positive definite.")
         return v_out
 
     def update_many(self, V, check_diag: bool = True):

@@ -122,7 +122,7 @@ int chub_downdate_host_f32(void *L, int64_t n, int64_t ld, int layout, void *v, 
 /* Release the staging buffers the host entry points cache on the current device. */
 int chub_host_release(void);
 
-/* ---- block-row-cyclic distribution of ONE factor over G devices (update only; row-major).
+/* ---- block-row-cyclic distribution of ONE factor over G devices (row-major).
  *      New surface: the reference has no distributed mode.  Rank g stores the global
  *      256-row blocks g, g+G, g+2G, ... back to back as A_loc[m_loc][ld] (n columns).  Per
  *      256-column panel J the owner of the diagonal block (rank J mod G) forms the panel's
@@ -145,6 +145,27 @@ int chub_rc_panel_apply_f64(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, i
 int chub_rc_panel_apply_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int J,
                             int is_owner, void *workspace, const double *payload, int32_t *status,
                             void *stream);
+
+/* ---- block-row-cyclic DOWNDATE (.pyx:160-330 distributed).  After chub_rc_prepare: per
+ *      256-column panel J the owner solves its diagonal block for the panel's p = L^{-1} v
+ *      (chub_rc_dd_panel_owner -> payload: p and the signs of the input diagonal), the caller
+ *      broadcasts the payload, and every rank subtracts L[rows, panel] p from the residual of its rows
+ *      below the block (chub_rc_dd_panel_apply; read-only on A).  chub_rc_dd_finish then forms
+ *      rho^2 = 1 - p.p on every rank (identical arithmetic, no exchange): if rho^2 <= 0 the status
+ *      becomes CHUB_STATUS_NOT_PD, v <- p and A stays untouched (.pyx:255-259); otherwise
+ *      v <- rotg's z_k and the reverse sweep (.pyx:279-330) runs on the local rows. */
+int chub_rc_dd_panel_owner_f64(void *A_loc, int64_t n, int64_t ld, int G, int rank, int J, void *workspace,
+                               double *payload, int32_t *status, void *stream);
+int chub_rc_dd_panel_owner_f32(void *A_loc, int64_t n, int64_t ld, int G, int rank, int J, void *workspace,
+                               double *payload, int32_t *status, void *stream);
+int chub_rc_dd_panel_apply_f64(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int J,
+                               void *workspace, const double *payload, int32_t *status, void *stream);
+int chub_rc_dd_panel_apply_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int J,
+                               void *workspace, const double *payload, int32_t *status, void *stream);
+int chub_rc_dd_finish_f64(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, void *v,
+                          void *workspace, int32_t *status, void *stream);
+int chub_rc_dd_finish_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, void *v,
+                          void *workspace, int32_t *status, void *stream);
 
 /* ---- K successive updates of one block-row-cyclic factor as a wavefront (BASELINE.json
  *      configs[4]).  Task (u, J) = panel J of update u depends only on (u-1, J) and

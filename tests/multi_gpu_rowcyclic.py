@@ -75,6 +75,32 @@ def main():
                   f"{err:.2e} (bar {tol_for(np.float64, n):.1e}); all ranks ok: {int(t.item()) == 0}", flush=True)
         assert int(t.item()) == 0
 
+    # distributed downdate (panel-wise forward substitution + local sweep), valid and not-PD vectors
+    from helpers import downdate_vector
+    A = torch.from_numpy(np.ascontiguousarray(L[rows])).to(dev)
+    vd = downdate_vector(L, 21)
+    facd = RowCyclicFactor(A, n, rank, world)
+    facd.downdate(torch.from_numpy(vd.copy()).to(dev))
+    L_ref = np.array(L, order="F")
+    oracle.downdate(L_ref, vd.copy())
+    got = np.where(lower, A.cpu().numpy(), 0.0)
+    want = np.tril(L_ref)[rows]
+    err = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+    keep = A.clone()
+    try:
+        facd.downdate(torch.from_numpy(downdate_vector(np.tril(L_ref), 22, norm_p=1.2)).to(dev))
+        raised = False
+    except np.linalg.LinAlgError:
+        raised = True
+    ok = err <= tol_for(np.float64, n) and raised and bool(torch.equal(keep, A))
+    t = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(t)
+    if rank == 0:
+        print(f"[rowcyclic downdate parity] n={n} world={world}: rel. Frobenius error (rank 0 rows) {err:.2e} "
+              f"(bar {tol_for(np.float64, n):.1e}); not-PD raises with the factor untouched: {raised}; "
+              f"all ranks ok: {int(t.item()) == 0}", flush=True)
+    assert int(t.item()) == 0
+
     # timing at n_time, rows generated per rank
     n = n_time
     rows = rc_owned_rows(n, rank, world)
@@ -105,6 +131,24 @@ def main():
         bytes_upd = 8 * n * (n + 1) + 16 * n
         print(f"[rowcyclic timing] n={n} world={world}: {per:.3f} ms/update, {bytes_upd / per / 1e6:.0f} GB/s aggregate "
               f"({bytes_upd / per / 1e6 / world:.0f} GB/s per GPU)", flush=True)
+    # one downdate (v = 0.5 * L u / |u| is always valid)
+    u = torch.randn(n, dtype=torch.float64, device=dev, generator=gv)
+    u = 0.5 * u / u.norm()
+    vloc = torch.zeros(n, dtype=torch.float64, device=dev)
+    vloc[rt] = A @ u  # the rows of L u this rank owns
+    dist.all_reduce(vloc)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0.record()
+    fac.downdate(vloc, check_diag=False)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"[rowcyclic downdate timing] n={n} world={world}: {float(ms.item()):.3f} ms per downdate", flush=True)
+
     # wavefront: k_wave successive updates in one call (BASELINE.json configs[4]: 64)
     gv.manual_seed(8)
     V = torch.randn((k_wave, n), dtype=torch.float64, device=dev, generator=gv)

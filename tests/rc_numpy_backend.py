@@ -76,6 +76,44 @@ class NumpyRowCyclicBackend:
     def status_tensor(self):
         return self.status
 
+    # ---- downdate: forward substitution panel by panel, then the local reverse sweep
+    def dd_panel_owner(self, J, payload):
+        j0, j1 = J * RC_BLOCK, min(self.n, (J + 1) * RC_BLOCK)
+        m = j1 - j0
+        loc = np.searchsorted(self.rows, np.arange(j0, j1))
+        LD = np.tril(self.A[loc, j0:j1])
+        buf = payload.numpy()
+        buf[:] = 0
+        buf[0:m] = np.linalg.solve(LD, self.w[j0:j1])
+        buf[3 * RC_BLOCK:3 * RC_BLOCK + m] = np.where(np.diag(LD) < 0, -1.0, 1.0)
+
+    def dd_panel_apply(self, J, payload):
+        j0, j1 = J * RC_BLOCK, min(self.n, (J + 1) * RC_BLOCK)
+        m = j1 - j0
+        buf = payload.numpy()
+        self.p[j0:j1], self.dn[j0:j1] = buf[0:m], buf[3 * RC_BLOCK:3 * RC_BLOCK + m]
+        sel = np.nonzero(self.rows >= j1)[0]
+        if sel.size:
+            self.w[self.rows[sel]] -= self.A[sel, j0:j1] @ self.p[j0:j1]
+
+    def dd_finish(self):
+        rho_sq = 1.0 - float(self.p @ self.p)
+        if rho_sq <= 0:
+            self.v_out[:] = self.p
+            self.status[0] = 2
+            return 2
+        suffix = np.concatenate((np.cumsum((self.p * self.p)[::-1])[::-1], [0.0]))
+        q = np.sqrt(rho_sq + suffix)  # q[k]^2 = rho^2 + sum_{j >= k} p_j^2
+        c, s = q[1:] / q[:-1], self.p / q[:-1]
+        for i, R in enumerate(self.rows):
+            x = 0.0
+            for k in range(R, -1, -1):
+                lo = self.A[i, k]
+                self.A[i, k] = self.dn[k] * (c[k] * lo - s[k] * x)
+                x = c[k] * x + s[k] * lo
+        self.v_out[:] = 0.25  # stands in for rotg's z (scratch)
+        return 0
+
     # ---- wavefront over K successive updates (same slot layout as csrc/rowcyclic.cuh)
     PAY = 5 * RC_BLOCK + 8
 

@@ -148,6 +148,27 @@ def _rc_worker(rank, world, port, tmpdir):
             err2 = np.linalg.norm(got2 - want2) / np.linalg.norm(want2)
             assert err2 <= tol_for(np.float64, n), (K, err2)
             assert np.all(A2.numpy()[~lower] == 0.0)
+        # distributed downdate: panel-wise forward substitution + local sweep == the oracle's downdate
+        from helpers import downdate_vector
+        A3 = torch.from_numpy(np.ascontiguousarray(L[rows]))
+        fac3 = RowCyclicFactor(A3, n, rank, world, backend=NumpyRowCyclicBackend(A3, n, rank, world))
+        vd = downdate_vector(L, 11)
+        fac3.downdate(torch.from_numpy(vd.copy()))
+        L_ref3 = np.array(L, order="F")
+        oracle.downdate(L_ref3, vd.copy())
+        got3 = np.where(lower, A3.numpy(), 0.0)
+        want3 = np.tril(L_ref3)[rows]
+        err3 = np.linalg.norm(got3 - want3) / np.linalg.norm(want3)
+        assert err3 <= tol_for(np.float64, n), err3
+        assert np.all(A3.numpy()[~lower] == 0.0)
+        # not positive definite: every rank raises, the factor is untouched
+        keep3 = A3.clone()
+        try:
+            fac3.downdate(torch.from_numpy(downdate_vector(np.tril(L_ref3), 12, norm_p=1.2)))
+            raised = False
+        except np.linalg.LinAlgError as exc:
+            raised = "not positive definite" in str(exc)
+        assert raised and torch.equal(keep3, A3)
         # zero on the diagonal of a row owned by rank 1: both ranks raise, nothing is modified
         before = A_loc.clone()
         if 300 in rows:

@@ -399,6 +399,33 @@ def test_rowcyclic_wavefront_single_rank_matches_oracle(n, K, dtype):
     assert torch.equal(keep, Lz)
 
 
+@pytest.mark.parametrize("n", [300, 1000, 2048])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_rowcyclic_downdate_single_rank_matches_oracle(n, dtype):
+    """Distributed downdate driver on one rank: panel-wise forward substitution, rho^2 test, local sweep."""
+    from cholupdates_b200.distributed import RowCyclicFactor
+
+    L = synth_factor(n, 35).astype(dtype)
+    L[:, 3] *= -1.0  # a negative input diagonal entry: the column's sign flip must survive (.pyx:319-326)
+    v = downdate_vector(L, 36)
+    A = torch.from_numpy(L.copy()).cuda()
+    A += torch.triu(torch.full_like(A, float("nan")), 1)
+    z = RowCyclicFactor(A, n).downdate(torch.from_numpy(v.copy()).cuda())
+    L_ref, z_ref = np.array(L, order="F"), v.copy()
+    oracle.downdate(L_ref, z_ref)
+    got = A.cpu().numpy()
+    assert rel_fro(got, L_ref) <= tol_for(dtype, n) * (1 if dtype == np.float64 else 30)
+    assert np.all(np.isnan(got[np.triu_indices(n, 1)]))
+    if dtype == np.float64:
+        np.testing.assert_allclose(z.cpu().numpy(), z_ref, rtol=1e-8, atol=1e-10)
+    # ||L^{-1} v|| = 1.2: LinAlgError, factor untouched (test_downdate.py:155-175)
+    keep = A.clone()
+    bad = downdate_vector(np.tril(L_ref).astype(dtype), 37, norm_p=1.2)
+    with pytest.raises(np.linalg.LinAlgError, match="not positive definite"):
+        RowCyclicFactor(A, n).downdate(torch.from_numpy(bad).cuda())
+    assert torch.equal(torch.tril(keep), torch.tril(A))
+
+
 def test_sharded_batched_single_process():
     from cholupdates_b200.distributed import shard_bounds, sharded_batched
 
