@@ -69,20 +69,35 @@ template <typename T, bool UPDATE>
 int launch_small(T *L, int64_t n, int64_t ld, int64_t stride_L, int layout, T *v, int64_t stride_v,
                  int64_t batch, int flags, int32_t *status, cudaStream_t st) {
   SmallArgs<T> a{L, v, status, (int)n, ld, stride_L, stride_v, flags};
-  const size_t smem = UPDATE ? small_update_smem<T>((int)n, layout) : small_downdate_smem<T>((int)n, layout);
-  auto go = [&](auto kern) -> int {
+  // Threads per factor.  A single factor wants the whole CTA on its trailing rows; a large batch is
+  // throughput-bound, and narrow CTAs (more factors resident per SM, nobody idling behind the one
+  // warp that walks the diagonal block) hide the sequential chain behind other factors.  Measured at
+  // 8192 x n=256 fp64: update 1.23 ms (128 threads) / 1.18 (64) / 0.96 (32); downdate 1.76 / 1.67 / 1.84.
+  // (Tried and dropped: register-direct trailing rows, 4 lanes per row -- 1.33-1.54 ms.)
+  int nt = kSmallNT;
+  if (const char *e = getenv("CHUB_SMALL_NT")) nt = atoi(e);
+  else if (batch >= 2048) nt = UPDATE ? kSmallNTBatched : kSmallNTBatchedDd;
+  auto go = [&](auto kern, int threads) -> int {
+    const size_t smem = UPDATE ? small_update_smem<T>((int)n, layout, threads) : small_downdate_smem<T>((int)n, layout, threads);
     if (smem > 48 * 1024)
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)batch, kSmallNT, smem, st>>>(a);
+    kern<<<(unsigned)batch, threads, smem, st>>>(a);
     LAUNCHED();
     return 0;
   };
-  if (UPDATE) {
-    if (layout == CHUB_ROW_MAJOR) return go(small_update_kernel<T, CHUB_ROW_MAJOR, kSmallNT>);
-    return go(small_update_kernel<T, CHUB_COL_MAJOR, kSmallNT>);
-  }
-  if (layout == CHUB_ROW_MAJOR) return go(small_downdate_kernel<T, CHUB_ROW_MAJOR, kSmallNT>);
-  return go(small_downdate_kernel<T, CHUB_COL_MAJOR, kSmallNT>);
+#define CHUB_SMALL_GO(NT)                                                                        \
+  do {                                                                                           \
+    if (UPDATE) {                                                                                \
+      if (layout == CHUB_ROW_MAJOR) return go(small_update_kernel<T, CHUB_ROW_MAJOR, NT>, NT);   \
+      return go(small_update_kernel<T, CHUB_COL_MAJOR, NT>, NT);                                 \
+    }                                                                                            \
+    if (layout == CHUB_ROW_MAJOR) return go(small_downdate_kernel<T, CHUB_ROW_MAJOR, NT>, NT);   \
+    return go(small_downdate_kernel<T, CHUB_COL_MAJOR, NT>, NT);                                 \
+  } while (0)
+  if (nt == 32) CHUB_SMALL_GO(32);
+  if (nt == 64) CHUB_SMALL_GO(64);
+  CHUB_SMALL_GO(kSmallNT);
+#undef CHUB_SMALL_GO
 }
 
 // ---- launch-per-panel path

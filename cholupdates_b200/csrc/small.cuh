@@ -27,6 +27,8 @@ struct SmallArgs {
 };
 
 constexpr int kSmallNT = 128;    // threads per CTA (= rows per staged tile)
+constexpr int kSmallNTBatched = 32;     // large batches, update: one warp per factor (launch_small, api.cu)
+constexpr int kSmallNTBatchedDd = 64;   // large batches, downdate: two warps per factor (measured best)
 constexpr int kSmallMaxN = 2048;  // shared-memory bound of the downdate kernel
 
 template <typename T, int LAYOUT, int NT>
@@ -183,9 +185,9 @@ __global__ void __launch_bounds__(NT) small_update_kernel(SmallArgs<T> a) {
 }
 
 template <typename T>
-inline size_t small_update_smem(int n, int layout) {
+inline size_t small_update_smem(int n, int layout, int nt = kSmallNT) {
   size_t n_pad = (n + 31) & ~31;
-  return (n_pad + 4 * kPanel + (layout == CHUB_ROW_MAJOR ? (size_t)kSmallNT * kPanel : 0)) * sizeof(T);
+  return (n_pad + 4 * kPanel + (layout == CHUB_ROW_MAJOR ? (size_t)nt * kPanel : 0)) * sizeof(T);
 }
 
 // ---------------------------------------------------------------- downdate
@@ -366,10 +368,10 @@ __global__ void __launch_bounds__(NT) small_downdate_kernel(SmallArgs<T> a) {
 }
 
 template <typename T>
-inline size_t small_downdate_smem(int n, int layout) {
+inline size_t small_downdate_smem(int n, int layout, int nt = kSmallNT) {
   size_t n_pad = (n + 31) & ~31;
-  return (n_pad + 2 + kSmallNT) * sizeof(double) +
-         (4 * n_pad + (layout == CHUB_ROW_MAJOR ? (size_t)kSmallNT * kPanel : 0)) * sizeof(T);
+  return (n_pad + 2 + nt) * sizeof(double) +
+         (4 * n_pad + (layout == CHUB_ROW_MAJOR ? (size_t)nt * kPanel : 0)) * sizeof(T);
 }
 
 }  // namespace chub
