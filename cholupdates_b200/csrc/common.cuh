@@ -35,6 +35,10 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;\n" ::: "memory");
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+}
+
 // global (row-major) -> swizzled shared tile of [rows][32]; complete after the caller's
 // __syncthreads() (the wait for this thread's copies is inside)
 template <typename T, int NT>

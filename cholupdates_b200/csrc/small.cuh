@@ -31,6 +31,16 @@ constexpr int kSmallNTBatched = 32;     // large batches, update: one warp per f
 constexpr int kSmallNTBatchedDd = 64;   // large batches, downdate: two warps per factor (measured best)
 constexpr int kSmallMaxN = 2048;  // shared-memory bound of the downdate kernel
 
+// L2 prefetch of the 32-column segment [pc, pc + 32) of row pr (row-major), if it exists.
+template <typename T>
+__device__ __forceinline__ void prefetch_row_l2(const T *L, int64_t ld, int n, int pr, int pc) {
+  if (pr < n && pc < n) {
+    const T *q = L + (int64_t)pr * ld + pc;
+    prefetch_l2(q);
+    if (kPanel * sizeof(T) > 128 && pc + 16 < n) prefetch_l2(q + 16);
+  }
+}
+
 template <typename T, int LAYOUT, int NT>
 __device__ __forceinline__ bool small_zero_diag(const T *L, int n, int64_t ld) {
   int bad = 0;
@@ -62,6 +72,7 @@ __global__ void __launch_bounds__(NT) small_update_kernel(SmallArgs<T> a) {
     }
   }
   for (int i = tid; i < n; i += NT) nu[i] = v[i];
+  if (LAYOUT == CHUB_ROW_MAJOR) prefetch_row_l2<T>(L, ld, n, kPanel + tid, 0);  // first trailing tile
   __syncthreads();
 
   for (int c0 = 0; c0 < n; c0 += kPanel) {
@@ -151,6 +162,15 @@ __global__ void __launch_bounds__(NT) small_update_kernel(SmallArgs<T> a) {
       for (int r0 = rbeg; r0 < n; r0 += NT) {
         const int rows = min(NT, n - r0);
         tile_load_rm<T, NT>(tile, L, ld, r0, rows, c0, kPanel);
+        {
+          // The tiles of a factor are visited one after the other with a DRAM round trip each: pull the
+          // next tile (same panel, or the next panel's diagonal block + first trailing rows) into L2
+          // while this one is processed.  thread = row of that tile.
+          const bool last = r0 + NT >= n;
+          const int pc = last ? c0 + kPanel : c0;
+          for (int pr = (last ? rbeg : r0 + NT) + tid, rep = 0; rep < (last && NT < 64 ? 2 : 1); ++rep, pr += NT)
+            prefetch_row_l2<T>(L, ld, n, pr, pc);
+        }
         __syncthreads();
         if (tid < rows) {
           T w = nu[r0 + tid];
@@ -251,6 +271,10 @@ __global__ void __launch_bounds__(NT) small_downdate_kernel(SmallArgs<T> a) {
       for (int r0 = rbeg; r0 < n; r0 += NT) {
         const int rows = min(NT, n - r0);
         tile_load_rm<T, NT>(tile, L, ld, r0, rows, c0, kPanel);
+        {  // next tile -> L2 (same panel, else the next panel's diagonal block and first trailing rows)
+          const bool last = r0 + NT >= n;
+          prefetch_row_l2<T>(L, ld, n, (last ? rbeg : r0 + NT) + tid, last ? c0 + kPanel : c0);
+        }
         __syncthreads();
         if (tid < rows) {
           T w = p[r0 + tid];
@@ -327,6 +351,11 @@ __global__ void __launch_bounds__(NT) small_downdate_kernel(SmallArgs<T> a) {
       for (int r0 = c0; r0 < n; r0 += NT) {
         const int rows = min(NT, n - r0);
         tile_load_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
+        {  // next tile -> L2 (same panel, else the top of the panel to the left)
+          const bool last = r0 + NT >= n;
+          if (!last) prefetch_row_l2<T>(L, ld, n, r0 + NT + tid, c0);
+          else if (c0 >= kPanel) prefetch_row_l2<T>(L, ld, n, c0 - kPanel + tid, c0 - kPanel);
+        }
         __syncthreads();
         if (tid < rows) {
           const int i = r0 + tid;
