@@ -388,9 +388,18 @@ int rcw_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, in
   int Jlo, Jhi;
   rcw_span(n, K, d, &Jlo, &Jhi);
   if (Jhi < Jlo) return 0;
-  dim3 grid((unsigned)((m_loc > 0 ? m_loc + 127 : 128) / 128), (unsigned)(Jhi - Jlo + 1));
-  rcw_trail_kernel<T><<<grid, 128, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, wv, (int)d, Jlo,
-                                            rcw_max_tasks(n, K, G), pay_all, (T *)V_out, ldv, status);
+  int nt = kRcwTrailNT;
+  if (const char *e = getenv("CHUB_RCW_NT")) nt = atoi(e);
+  dim3 grid((unsigned)((m_loc > 0 ? m_loc + nt - 1 : nt) / nt), (unsigned)(Jhi - Jlo + 1));
+  if (nt == 32)
+    rcw_trail_kernel<T, 32><<<grid, 32, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, wv, (int)d, Jlo,
+                                                 rcw_max_tasks(n, K, G), pay_all, (T *)V_out, ldv, status);
+  else if (nt == 64)
+    rcw_trail_kernel<T, 64><<<grid, 64, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, wv, (int)d, Jlo,
+                                                 rcw_max_tasks(n, K, G), pay_all, (T *)V_out, ldv, status);
+  else
+    rcw_trail_kernel<T, 128><<<grid, 128, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, wv, (int)d, Jlo,
+                                                   rcw_max_tasks(n, K, G), pay_all, (T *)V_out, ldv, status);
   LAUNCHED();
   return 0;
 }

@@ -89,6 +89,7 @@ int copy_tri(char *dst, const char *src, int64_t n, int64_t ld_dst, int64_t ld_s
 // touches its own 256 columns (plus the n-vector w), so a panel can be finished and shipped back as
 // soon as it has arrived; PCIe runs full duplex and the update costs about one H2D of the triangle.
 constexpr int64_t kStreamMinN = 2048;
+constexpr int64_t kXferCols = 512;  // columns per host <-> device transfer panel (measured: 256 24.7 ms, 512 24.0, 1024 27.7 at n = 16384)
 
 template <typename T, int LAYOUT>
 int run_host_update_streamed(HostCache &c, T *Lh, int64_t n, int64_t ld, T *vh, int32_t *status) {
@@ -103,7 +104,12 @@ int run_host_update_streamed(HostCache &c, T *Lh, int64_t n, int64_t ld, T *vh, 
     c.ws_bytes = need_ws;
   }
   const int nJ = (ni + kBig - 1) / kBig;
-  while ((int)c.ev_in.size() < nJ + 1) {
+  // Transfer panels are wider than the kernels' 256-column panels: a 2-D copy of 2 KB rows runs well
+  // below the PCIe rate; beyond 512 columns the coarser pipeline costs more than it gains (CHUB_HOST_XFER_COLS overrides).
+  int64_t xfer = kXferCols;
+  if (const char *e = getenv("CHUB_HOST_XFER_COLS")) xfer = std::max<int64_t>(kBig, atoll(e) / kBig * kBig);
+  const int nP = (int)((n + xfer - 1) / xfer);
+  while ((int)c.ev_in.size() < nP + 1) {
     cudaEvent_t a, b;
     HCK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
     HCK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
@@ -117,9 +123,9 @@ int run_host_update_streamed(HostCache &c, T *Lh, int64_t n, int64_t ld, T *vh, 
   HCK(cudaMemsetAsync(c.status, 0, sizeof(int32_t), c.st));
   HCK(cudaMemcpyAsync(vd, vh, (size_t)n * es, cudaMemcpyHostToDevice, c.st));
   large_prepare_kernel<T, LAYOUT><<<(ni + 255) / 256, 256, 0, c.st>>>(Ld, ni, ldd, vd, ws, 0, c.status);
-  for (int J = 0; J < nJ; ++J) {
-    const int64_t j0 = (int64_t)J * kBig;
-    const int64_t bw = std::min<int64_t>(kBig, n - j0);
+  for (int P = 0; P < nP; ++P) {
+    const int64_t j0 = (int64_t)P * xfer;
+    const int64_t bw = std::min<int64_t>(xfer, n - j0);
     // rectangle rows [j0, n) x columns [j0, j0 + bw)
     size_t off_d, off_h, width, height;
     if (LAYOUT == CHUB_ROW_MAJOR) {
@@ -131,16 +137,19 @@ int run_host_update_streamed(HostCache &c, T *Lh, int64_t n, int64_t ld, T *vh, 
     }
     HCK(cudaMemcpy2DAsync(Ld + off_d, (size_t)ldd * es, Lh + off_h, (size_t)ld * es, width, height,
                           cudaMemcpyHostToDevice, c.st_in));
-    HCK(cudaEventRecord(c.ev_in[J], c.st_in));
-    HCK(cudaStreamWaitEvent(c.st, c.ev_in[J], 0));
-    large_invdiag_kernel<T, LAYOUT><<<(kBig / 32 + 3) / 4, 128, 0, c.st>>>(Ld, ni, ldd, ws, c.status,
-                                                                           (int)(j0 / 32), kBig / 32);
-    large_chain_kernel<T, LAYOUT, true><<<1, kBig, 0, c.st>>>(Ld, ni, ldd, vd, ws, J, c.status);
-    large_trail_kernel<T, LAYOUT, true><<<(unsigned)((n - j0 + 127) / 128), 128, 0, c.st>>>(Ld, ni, ldd, ws, J,
-                                                                                           c.status);
+    HCK(cudaEventRecord(c.ev_in[P], c.st_in));
+    HCK(cudaStreamWaitEvent(c.st, c.ev_in[P], 0));
+    for (int J = (int)(j0 / kBig); J < nJ && (int64_t)J * kBig < j0 + bw; ++J) {
+      const int64_t c0 = (int64_t)J * kBig;
+      large_invdiag_kernel<T, LAYOUT><<<(kBig / 32 + 3) / 4, 128, 0, c.st>>>(Ld, ni, ldd, ws, c.status,
+                                                                             (int)(c0 / 32), kBig / 32);
+      large_chain_kernel<T, LAYOUT, true><<<1, kBig, 0, c.st>>>(Ld, ni, ldd, vd, ws, J, c.status);
+      large_trail_kernel<T, LAYOUT, true><<<(unsigned)((n - c0 + 127) / 128), 128, 0, c.st>>>(Ld, ni, ldd, ws, J,
+                                                                                             c.status);
+    }
     HCK(cudaGetLastError());
-    HCK(cudaEventRecord(c.ev_done[J], c.st));
-    HCK(cudaStreamWaitEvent(c.st_out, c.ev_done[J], 0));
+    HCK(cudaEventRecord(c.ev_done[P], c.st));
+    HCK(cudaStreamWaitEvent(c.st_out, c.ev_done[P], 0));
     HCK(cudaMemcpy2DAsync(Lh + off_h, (size_t)ld * es, Ld + off_d, (size_t)ldd * es, width, height,
                           cudaMemcpyDeviceToHost, c.st_out));
   }

@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(128) rc_dd_sweep_kernel(T *A, int m_loc, int n
 //                      local rows below it
 // K + nJ - 1 steps replace K * nJ per-panel broadcasts; the per-step latency is amortised over up
 // to min(K, nJ) panels of streaming work.  Same arithmetic as the per-panel kernels above.
+constexpr int kRcwTrailNT = 128;           // rows per CTA of the trail kernel (32 / 64 / 128)
 constexpr int kRcwPayload = 5 * kBig + 8;  // p, c, sigma, dn, z, scal[8] ({t, S} leaving the panel)
 
 struct RcWave {
@@ -276,12 +277,11 @@ __global__ void __launch_bounds__(kBig) rcw_owner_kernel(const T *A, int n, int6
 
 // Trailing update for every task of anti-diagonal d: blockIdx.y = t <-> J = Jlo + t, u = d - J; its
 // payload sits in slot (J mod G) * max_tasks + t / G of the gathered buffer (the owner's tasks are
-// Jfirst, Jfirst + G, ... with Jfirst - Jlo < G).  blockIdx.x = 128 consecutive local rows.
-template <typename T>
-__global__ void __launch_bounds__(128) rcw_trail_kernel(T *A, int m_loc, int n, int64_t ld, int G, int rank, RcWave wv,
-                                                        int d, int Jlo, int max_tasks, const double *pay_all,
-                                                        T *V_out, int64_t ldv, const int32_t *status) {
-  constexpr int NT = 128;
+// Jfirst, Jfirst + G, ... with Jfirst - Jlo < G).  blockIdx.x = NT consecutive local rows.
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, int64_t ld, int G, int rank, RcWave wv,
+                                                       int d, int Jlo, int max_tasks, const double *pay_all,
+                                                       T *V_out, int64_t ldv, const int32_t *status) {
   __shared__ double cs[3][kPanel];
   __shared__ __align__(16) T tile[NT * kPanel];
   if (*status != 0) return;
@@ -319,6 +319,11 @@ __global__ void __launch_bounds__(128) rcw_trail_kernel(T *A, int m_loc, int n, 
       cs[2][tid] = tid < bw ? pay[2 * kBig + a] : 0.0;
     }
     tile_load_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
+    if (tid < rows && c0 + kPanel < cend) {  // next block column of my row -> L2 while this one is processed
+      const T *q = L + (int64_t)R * ld + c0 + kPanel;
+      prefetch_l2(q);
+      if (kPanel * sizeof(T) > 128) prefetch_l2(q + 16);
+    }
     __syncthreads();
     if (valid) {
 #pragma unroll 8
