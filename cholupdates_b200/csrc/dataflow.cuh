@@ -58,6 +58,10 @@ constexpr int kDfD = CHUB_DF_D;         // v3 (row-major): band depth in block c
 constexpr int kDfStages = 6;            // worker tile ring
 constexpr int kDfSlots = CHUB_DF_SLOTS;  // v3: chain prefetch ring (block columns)
 constexpr int kDfCoefRing = CHUB_DF_RING;  // v3: coefficient ring
+#ifndef CHUB_DF_PF
+#define CHUB_DF_PF 6
+#endif
+constexpr int kDfPf = CHUB_DF_PF;       // v3: chain L2 prefetch distance beyond the ring (block columns)
 constexpr int kV2D = 4;         // v2 (column-major) keeps its own, shallower configuration
 constexpr int kV2Slots = 4;
 constexpr int kV2CoefRing = 8;
@@ -132,6 +136,10 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, const void *smem_src) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n"
                ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+// tensor-map TMA prefetch of a box into L2 (no shared-memory destination, nothing to wait for)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 // exactly one lane of a converged warp (the compiler then keeps TMA operands on the uniform path)
 __device__ __forceinline__ bool elect_one() {
@@ -850,6 +858,13 @@ __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsign
       }
     } else if (warp == kDfD + 1) {
       if (elect_one()) issue_slot(j + kDfSlots - 1);
+    } else if (kDfPf > 0) {
+      // the spare warp: the ring's lead (kDfSlots-1 block columns) is shorter than the DRAM latency
+      // while every SM streams, so the band tiles of block column j + kDfSlots-1 + kDfPf go to L2 now
+      const int jp = j + kDfSlots - 1 + kDfPf;
+      const int np = min(kDfD, T_ - 1 - jp);
+      if (lane < np * HALVES)
+        tma_prefetch_2d(tmap32, jp * kPanel + (lane % HALVES) * BOXC, (jp + 1 + lane / HALVES) * kPanel);
     }
     tp = DF_PROF_T();
     named_sync(1, 256);
