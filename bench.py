@@ -328,6 +328,7 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
+    sampler.start()  # early: the first NVML queries are slow, and the timed region is short
     stream = torch.cuda.current_stream()
 
     if args.workload == "update":
@@ -385,7 +386,6 @@ def run_gpu_arm(args):
         metric = METRIC_BATCHED
 
     # ---- warm-up, then K timed steps (device-timed with events on the launching stream)
-    sampler.start()  # clocks are sampled from the warm-up on, so that the short timed region is covered
     for i in range(args.warmup):
         step(i)
     barrier()

@@ -40,13 +40,18 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
 }
 
 // global (row-major) -> swizzled shared tile of [rows][32]; complete after the caller's
-// __syncthreads() (the wait for this thread's copies is inside)
+// __syncthreads() (the wait for this thread's copies is inside).  Warp w moves rows w, w + NT/32, ...
+// (lane = column: one coalesced 32-element row segment per instruction, pointer stepped by whole rows).
 template <typename T, int NT>
 __device__ __forceinline__ void tile_load_rm(T *tile, const T *L, int64_t ld, int r0, int rows,
                                              int c0, int bw) {
-  for (int e = threadIdx.x; e < rows * kPanel; e += NT) {
-    int rr = e >> 5, cc = e & 31;
-    if (cc < bw) cp_async_elem(tile + tile_off(rr, cc), L + (int64_t)(r0 + rr) * ld + c0 + cc);
+  constexpr int NW = NT / 32;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane < bw) {
+    const T *g = L + (int64_t)(r0 + w) * ld + c0 + lane;
+    const int64_t step = (int64_t)NW * ld;
+#pragma unroll 8
+    for (int rr = w; rr < rows; rr += NW, g += step) cp_async_elem(tile + tile_off(rr, lane), g);
   }
   cp_async_wait_all();
 }
@@ -54,10 +59,15 @@ __device__ __forceinline__ void tile_load_rm(T *tile, const T *L, int64_t ld, in
 template <typename T, int NT>
 __device__ __forceinline__ void tile_store_rm(const T *tile, T *L, int64_t ld, int r0, int rows,
                                               int c0, int bw) {
+  constexpr int NW = NT / 32;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane < bw) {
+    T *g = L + (int64_t)(r0 + w) * ld + c0 + lane;
+    const int64_t step = (int64_t)NW * ld;
+    const int dlim = c0 + lane - r0;  // store row rr only if rr >= dlim  (column <= row)
 #pragma unroll 8
-  for (int e = threadIdx.x; e < rows * kPanel; e += NT) {
-    int rr = e >> 5, cc = e & 31;
-    if (cc < bw && c0 + cc <= r0 + rr) L[(int64_t)(r0 + rr) * ld + c0 + cc] = tile[tile_off(rr, cc)];
+    for (int rr = w; rr < rows; rr += NW, g += step)
+      if (rr >= dlim) *g = tile[tile_off(rr, lane)];
   }
 }
 

@@ -325,7 +325,19 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
       if (kPanel * sizeof(T) > 128) prefetch_l2(q + 16);
     }
     __syncthreads();
-    if (valid) {
+    if (bw == kPanel && c0 + kPanel <= r0) {
+      // the whole tile lies strictly below the diagonal (the common case): no per-entry predicates
+      if (tid < rows) {
+        T *trow = tile + tid * kPanel;
+        const int sw = tid & 31;
+#pragma unroll
+        for (int k = 0; k < kPanel; ++k) {
+          const double lo = (double)trow[k ^ sw];
+          trow[k ^ sw] = (T)fma(cs[1][k], lo, cs[2][k] * w);
+          w = fma(-lo, cs[0][k], w);
+        }
+      }
+    } else if (valid) {
 #pragma unroll 8
       for (int k = 0; k < kPanel; ++k) {
         if (k < bw && c0 + k < R) {

@@ -282,10 +282,14 @@ class RowCyclicFactor:
             raise ValueError("`A_local` must be row-major contiguous.")
         self.backend = backend if backend is not None else _CudaRowCyclicBackend(A_local, self.n, rank, world_size)
 
-    def update(self, v, check_diag: bool = True):
-        """In-place update of the distributed factor.  Returns the scratch vector (rotg's z_k for the
-        panels this rank owned).  Raises ``numpy.linalg.LinAlgError`` on every rank if ``check_diag``
-        finds a zero on the diagonal anywhere (nothing is modified in that case)."""
+    def update(self, v, check_diag: bool = True, per_panel: bool = False):
+        """In-place update of the distributed factor.  Returns the scratch vector (rotg's z_k).
+        Raises ``numpy.linalg.LinAlgError`` on every rank if ``check_diag`` finds a zero on the
+        diagonal anywhere (nothing is modified in that case).
+
+        One vector is the K = 1 case of ``update_many`` (one fused owner kernel, one all-gather and one
+        trail kernel per panel); ``per_panel=True`` runs the older launch-per-panel pieces
+        (``chub_rc_panel_owner`` / broadcast / ``chub_rc_panel_apply``), kept for comparison."""
         import numpy as np
         import torch
         import torch.distributed as dist
@@ -294,6 +298,8 @@ class RowCyclicFactor:
             raise ValueError(
                 f"The shape of the given vector `v` is incompatible with the shape of the given "
                 f"Cholesky factor `L`. Expected shape {(self.n,)} but got {tuple(v.shape)}.")
+        if not per_panel and hasattr(self.backend, "wave_begin"):
+            return self.update_many(v.reshape(1, -1), check_diag=check_diag)[0]
         be = self.backend
         multi = self.world > 1 and dist.is_available() and dist.is_initialized()
         v_out = torch.zeros_like(v)

@@ -148,9 +148,9 @@ int chub_rc_panel_apply_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, i
 
 /* ---- block-row-cyclic DOWNDATE (.pyx:160-330 distributed).  After chub_rc_prepare: per
  *      256-column panel J the owner solves its diagonal block for the panel's p = L^{-1} v
- *      (chub_rc_dd_panel_owner -> payload: p and the signs of the input diagonal), the caller
+ *      (chub_rc_dd_panel_owner_* -> payload: p and the signs of the input diagonal), the caller
  *      broadcasts the payload, and every rank subtracts L[rows, panel] p from the residual of its rows
- *      below the block (chub_rc_dd_panel_apply; read-only on A).  chub_rc_dd_finish then forms
+ *      below the block (chub_rc_dd_panel_apply_*; read-only on A).  chub_rc_dd_finish then forms
  *      rho^2 = 1 - p.p on every rank (identical arithmetic, no exchange): if rho^2 <= 0 the status
  *      becomes CHUB_STATUS_NOT_PD, v <- p and A stays untouched (.pyx:255-259); otherwise
  *      v <- rotg's z_k and the reverse sweep (.pyx:279-330) runs on the local rows. */
@@ -170,10 +170,10 @@ int chub_rc_dd_finish_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int
 /* ---- K successive updates of one block-row-cyclic factor as a wavefront (BASELINE.json
  *      configs[4]).  Task (u, J) = panel J of update u depends only on (u-1, J) and
  *      (u, J-1), so the tasks of an anti-diagonal d = u + J are independent.  Per step d the caller
- *      runs chub_rcw_owner (this rank's tasks -> pay_mine: chub_rcw_max_tasks() slots of
+ *      runs chub_rcw_owner_* for this rank's tasks (-> pay_mine: chub_rcw_max_tasks() slots of
  *      chub_rcw_payload_doubles() doubles), ONE all-gather of pay_mine into pay_all
- *      (G * max_tasks slots, rank-major), then chub_rcw_apply (all tasks of the step on the local
- *      rows): K + ceil(n/256) - 1 exchanges instead of K * ceil(n/256).  V / V_out: K vectors of n
+ *      (G * max_tasks slots, rank-major), then chub_rcw_apply_* for all tasks of the step on the local
+ *      rows: K + ceil(n/256) - 1 exchanges instead of K * ceil(n/256).  V / V_out: K vectors of n
  *      elements, leading dimension ldv (V_out may be NULL; it receives rotg's z_k, as v does in the
  *      reference, .pyx:101,152).  With G == 1 pay_all == pay_mine and no exchange is needed. */
 int chub_rcw_payload_doubles(void);

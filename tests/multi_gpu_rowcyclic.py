@@ -42,7 +42,7 @@ def main():
     L_ref = np.array(L, order="F")
     for u in range(3):
         v = np.random.default_rng([1, u]).standard_normal(n)
-        fac.update(torch.from_numpy(v.copy()).to(dev))
+        fac.update(torch.from_numpy(v.copy()).to(dev), per_panel=(u == 1))  # both single-update forms
         oracle.update(L_ref, v.copy())
     lower = np.arange(n)[None, :] <= rows[:, None]
     got = np.where(lower, A.cpu().numpy(), 0.0)
@@ -114,23 +114,26 @@ def main():
     gv = torch.Generator(device=dev)
     gv.manual_seed(7)  # same vectors on every rank
     vs = torch.randn((updates + 1, n), dtype=torch.float64, device=dev, generator=gv)
-    fac.update(vs[updates], check_diag=False)  # warm-up
-    dist.barrier()
-    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for u in range(updates):
-        fac.update(vs[u], check_diag=False)
-    e1.record()
-    dist.barrier()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        per = float(ms.item()) / updates
-        bytes_upd = 8 * n * (n + 1) + 16 * n
-        print(f"[rowcyclic timing] n={n} world={world}: {per:.3f} ms/update, {bytes_upd / per / 1e6:.0f} GB/s aggregate "
-              f"({bytes_upd / per / 1e6 / world:.0f} GB/s per GPU)", flush=True)
+    for per_panel in (True, False):
+        fac.update(vs[updates], check_diag=False, per_panel=per_panel)  # warm-up
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for u in range(updates):
+            fac.update(vs[u], check_diag=False, per_panel=per_panel)
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            per = float(ms.item()) / updates
+            bytes_upd = 8 * n * (n + 1) + 16 * n
+            print(f"[rowcyclic timing] n={n} world={world} single update, "
+                  f"{'launch-per-panel + broadcast' if per_panel else 'K=1 wavefront (fused owner kernel + all-gather)'}: "
+                  f"{per:.3f} ms/update, {bytes_upd / per / 1e6:.0f} GB/s aggregate "
+                  f"({bytes_upd / per / 1e6 / world:.0f} GB/s per GPU)", flush=True)
     # one downdate (v = 0.5 * L u / |u| is always valid)
     u = torch.randn(n, dtype=torch.float64, device=dev, generator=gv)
     u = 0.5 * u / u.norm()

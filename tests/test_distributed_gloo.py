@@ -124,7 +124,7 @@ def _rc_worker(rank, world, port, tmpdir):
         L_ref = np.array(L, order="F")
         for u in range(3):  # successive updates, as in BASELINE.json configs[4]
             v = np.random.default_rng([1, u]).standard_normal(n)
-            fac.update(torch.from_numpy(v.copy()))
+            fac.update(torch.from_numpy(v.copy()), per_panel=(u == 1))  # both single-update forms
             oracle.update(L_ref, v.copy())
         lower = np.arange(n)[None, :] <= rows[:, None]  # lower triangle in GLOBAL row indices
         got = np.where(lower, A_loc.numpy(), 0.0)

@@ -353,7 +353,7 @@ def test_rowcyclic_single_rank_matches_oracle(n):
     L_ref = np.array(L, order="F")
     for u in range(2):
         v = np.random.default_rng([7, u]).standard_normal(n)
-        fac.update(torch.from_numpy(v.copy()).cuda())
+        fac.update(torch.from_numpy(v.copy()).cuda(), per_panel=(u == 0))  # both single-update forms
         oracle.update(L_ref, v.copy())
     got = A.cpu().numpy()
     assert rel_fro(got, L_ref) <= tol_for(np.float64, n)
