@@ -260,6 +260,19 @@ class _CudaRowCyclicBackend:
         _lib.check(rc, "chub_rcw_apply")
 
 
+def _check_vector_like(A, x, what: str) -> None:
+    """dtype / device agreement between the local rows and a vector argument (the reference's dtype
+    checks, _seeger.py:243-258, for the distributed entry points)."""
+    import torch
+
+    if A.dtype not in (torch.float32, torch.float64):
+        raise TypeError(f"The local rows must be single or double precision (given: {A.dtype}).")
+    if x.dtype != A.dtype:
+        raise TypeError(f"`{what}` must have the dtype of the factor ({A.dtype}), but got {x.dtype}.")
+    if x.device != A.device:
+        raise ValueError(f"`{what}` must live on the device of the factor ({A.device}), but is on {x.device}.")
+
+
 class RowCyclicFactor:
     """A Cholesky factor of order ``n`` distributed block-row-cyclically: this rank holds
     ``A_local`` = the rows ``rc_owned_rows(n, rank, world)`` (all ``n`` columns, row-major).
@@ -282,14 +295,18 @@ class RowCyclicFactor:
             raise ValueError("`A_local` must be row-major contiguous.")
         self.backend = backend if backend is not None else _CudaRowCyclicBackend(A_local, self.n, rank, world_size)
 
-    def update(self, v, check_diag: bool = True, per_panel: bool = False):
-        """In-place update of the distributed factor.  Returns the scratch vector (rotg's z_k).
-        Raises ``numpy.linalg.LinAlgError`` on every rank if ``check_diag`` finds a zero on the
-        diagonal anywhere (nothing is modified in that case).
+    def update(self, v, check_diag: bool = True, per_panel=None):
+        """In-place update of the distributed factor.  Returns the scratch vector (rotg's z_k; with
+        ``per_panel`` only for the panels this rank owned).  Raises ``numpy.linalg.LinAlgError`` on
+        every rank if ``check_diag`` finds a zero on the diagonal anywhere (nothing is modified).
 
-        One vector is the K = 1 case of ``update_many`` (one fused owner kernel, one all-gather and one
-        trail kernel per panel); ``per_panel=True`` runs the older launch-per-panel pieces
-        (``chub_rc_panel_owner`` / broadcast / ``chub_rc_panel_apply``), kept for comparison."""
+        ``per_panel=True``: per 256-column panel the owner's kernels, one broadcast, the apply kernels
+        (``chub_rc_panel_owner`` / ``chub_rc_panel_apply``).  ``per_panel=False``: the K = 1 case of
+        ``update_many`` (one fused owner kernel, one all-gather, one trail kernel per panel).  Both are
+        bound by per-panel host / launch / collective latency; measured on 8 B200 at n = 65536 the
+        broadcast form is faster (27 ms vs 64 ms: ``all_gather_into_tensor`` costs more host time per
+        call than ``broadcast``), so it is the default whenever there is an exchange.  Successive
+        vectors belong in ``update_many`` (1.25 ms per update at K = 64)."""
         import numpy as np
         import torch
         import torch.distributed as dist
@@ -298,6 +315,11 @@ class RowCyclicFactor:
             raise ValueError(
                 f"The shape of the given vector `v` is incompatible with the shape of the given "
                 f"Cholesky factor `L`. Expected shape {(self.n,)} but got {tuple(v.shape)}.")
+        _check_vector_like(self.A, v, "v")
+        if not v.is_contiguous():
+            raise ValueError("`v` must be contiguous.")
+        if per_panel is None:
+            per_panel = self.world > 1
         if not per_panel and hasattr(self.backend, "wave_begin"):
             return self.update_many(v.reshape(1, -1), check_diag=check_diag)[0]
         be = self.backend
@@ -338,6 +360,9 @@ class RowCyclicFactor:
             raise ValueError(
                 f"The shape of the given vector `v` is incompatible with the shape of the given "
                 f"Cholesky factor `L`. Expected shape {(self.n,)} but got {tuple(v.shape)}.")
+        _check_vector_like(self.A, v, "v")
+        if not v.is_contiguous():
+            raise ValueError("`v` must be contiguous.")
         be = self.backend
         multi = self.world > 1 and dist.is_available() and dist.is_initialized()
         v_out = torch.zeros_like(v)
@@ -379,8 +404,9 @@ class RowCyclicFactor:
         if V.ndim != 2 or V.shape[1] != self.n:
             raise ValueError(
                 f"`V` must hold one vector per row, expected shape (K, {self.n}) but got {tuple(V.shape)}.")
+        _check_vector_like(self.A, V, "V")
         K = int(V.shape[0])
-        V_out = torch.zeros_like(V)
+        V_out = torch.zeros_like(V, memory_format=torch.contiguous_format)
         if K == 0:
             return V_out
         if V.stride(1) != 1:

@@ -141,3 +141,35 @@ def test_layout_detection():
     assert _seeger._layout_of(np.zeros((4, 4), order="F")) == _lib.COL_MAJOR
     assert _seeger._layout_of(np.zeros((8, 8))[::2, ::2]) is None
     assert _seeger._layout_of(np.zeros((1, 1))) in (_lib.ROW_MAJOR, _lib.COL_MAJOR)
+
+
+def test_rowcyclic_argument_checks_need_no_gpu():
+    """Shape / dtype / contiguity checks of the distributed entry points fire before any device work."""
+    import torch
+
+    from cholupdates_b200.distributed import RowCyclicFactor
+
+    class _NoBackend:
+        pass
+
+    n = 300
+    A = torch.eye(n, dtype=torch.float64)
+    fac = RowCyclicFactor(A, n, backend=_NoBackend())
+    with pytest.raises(ValueError):
+        RowCyclicFactor(torch.eye(n)[:100], n, backend=_NoBackend())  # wrong number of local rows
+    with pytest.raises(ValueError):
+        fac.update(torch.ones(n + 1, dtype=torch.float64))
+    with pytest.raises(TypeError):
+        fac.update(torch.ones(n, dtype=torch.float32))
+    with pytest.raises(TypeError):
+        fac.downdate(torch.ones(n, dtype=torch.float32))
+    with pytest.raises(ValueError):
+        fac.downdate(torch.ones(2 * n, dtype=torch.float64)[::2])
+    with pytest.raises(ValueError):
+        fac.update_many(torch.ones((2, n + 1), dtype=torch.float64))
+    with pytest.raises(TypeError):
+        fac.update_many(torch.ones((2, n), dtype=torch.float32))
+    with pytest.raises(ValueError):
+        fac.update_many(torch.ones((n, 2), dtype=torch.float64).t())
+    assert fac.update_many(torch.ones((0, n), dtype=torch.float64)).shape == (0, n)
+
