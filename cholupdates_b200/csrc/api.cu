@@ -368,23 +368,28 @@ inline void rcw_span(int64_t n, int64_t K, int64_t d, int *Jlo, int *Jhi) {
 }
 template <typename T>
 int rcw_owner(void *A, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d, void *workspace,
-              double *pay_mine, int32_t *status, void *stream) {
+              double *pay_mine, const void *peer_table, void *mailbox, int64_t epoch, int32_t *status, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   RcWave wv = rcw_carve(workspace, n, K, G);
+  RcwP2P pp{(double *const *)peer_table, (double *)mailbox, (long long)epoch, rcw_max_tasks(n, K, G)};
   int Jlo, Jhi;
   rcw_span(n, K, d, &Jlo, &Jhi);
   const int Jfirst = Jlo + (((rank - Jlo) % G) + G) % G;
-  if (Jfirst > Jhi) return 0;
-  const int count = (Jhi - Jfirst) / G + 1;
-  rcw_owner_kernel<T><<<count, kBig, 0, st>>>((const T *)A, (int)n, ld, G, wv, (int)d, Jfirst, pay_mine, status);
+  const int count = Jfirst > Jhi ? 0 : (Jhi - Jfirst) / G + 1;
+  if (count == 0 && !peer_table) return 0;
+  // (P2P mode: a rank without a task at this step still raises its flags -- one CTA)
+  rcw_owner_kernel<T><<<count > 0 ? count : 1, kBig, 0, st>>>((const T *)A, (int)n, ld, G, rank, wv, (int)d, Jfirst,
+                                                              pay_mine, pp, count, status);
   LAUNCHED();
   return 0;
 }
 template <typename T>
 int rcw_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
-              void *workspace, const double *pay_all, void *V_out, int64_t ldv, int32_t *status, void *stream) {
+              void *workspace, const double *pay_all, const void *peer_table, void *mailbox, void *V_out,
+              int64_t ldv, int64_t epoch, int32_t *status, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   RcWave wv = rcw_carve(workspace, n, K, G);
+  RcwP2P pp{(double *const *)peer_table, (double *)mailbox, (long long)epoch, rcw_max_tasks(n, K, G)};
   int Jlo, Jhi;
   rcw_span(n, K, d, &Jlo, &Jhi);
   if (Jhi < Jlo) return 0;
@@ -393,13 +398,13 @@ int rcw_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, in
   dim3 grid((unsigned)((m_loc > 0 ? m_loc + nt - 1 : nt) / nt), (unsigned)(Jhi - Jlo + 1));
   if (nt == 32)
     rcw_trail_kernel<T, 32><<<grid, 32, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, wv, (int)d, Jlo,
-                                                 rcw_max_tasks(n, K, G), pay_all, (T *)V_out, ldv, status);
+                                                 pp.max_tasks, pay_all, (T *)V_out, ldv, pp, status);
   else if (nt == 64)
     rcw_trail_kernel<T, 64><<<grid, 64, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, wv, (int)d, Jlo,
-                                                 rcw_max_tasks(n, K, G), pay_all, (T *)V_out, ldv, status);
+                                                 pp.max_tasks, pay_all, (T *)V_out, ldv, pp, status);
   else
     rcw_trail_kernel<T, 128><<<grid, 128, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, wv, (int)d, Jlo,
-                                                   rcw_max_tasks(n, K, G), pay_all, (T *)V_out, ldv, status);
+                                                   pp.max_tasks, pay_all, (T *)V_out, ldv, pp, status);
   LAUNCHED();
   return 0;
 }
@@ -487,6 +492,41 @@ int chub_rc_panel_apply_f32(void *A, int64_t m_loc, int64_t n, int64_t ld, int G
   return rc_panel_apply<float>(A, m_loc, n, ld, G, rank, J, is_owner, workspace, payload, status, stream);
 }
 
+// ---- peer-memory plumbing for the P2P exchange (cudaIpc: one process per GPU)
+size_t chub_rcw_mailbox_bytes(int64_t n, int64_t K, int G) {
+  if (n < 0) n = 0;
+  if (K < 1) K = 1;
+  return rcw_mailbox_doubles(n, K, G > 0 ? G : 1) * sizeof(double);
+}
+int chub_p2p_alloc(size_t bytes, void **ptr) {
+  if (!ptr) return (int)cudaErrorInvalidValue;
+  CK(cudaMalloc(ptr, bytes));
+  CK(cudaMemset(*ptr, 0, bytes));
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+int chub_p2p_free(void *ptr) {
+  if (ptr) CK(cudaFree(ptr));
+  return 0;
+}
+int chub_p2p_export(void *ptr, void *handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, sizeof(h));
+  return 0;
+}
+int chub_p2p_import(const void *handle64, void **peer_ptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  CK(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int chub_p2p_close(void *peer_ptr) {
+  if (peer_ptr) CK(cudaIpcCloseMemHandle(peer_ptr));
+  return 0;
+}
+
 int chub_rcw_payload_doubles(void) { return kRcwPayload; }
 int chub_rcw_max_tasks(int64_t n, int64_t K, int G) { return rcw_max_tasks(n, K, G > 0 ? G : 1); }
 size_t chub_rcw_workspace_bytes(int64_t n, int64_t K, int G) {
@@ -517,12 +557,26 @@ DEFINE_RC_DD(f32, float)
   }                                                                                                                \
   int chub_rcw_owner_##SUF(void *A, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d, void *workspace, \
                            double *pay_mine, int32_t *status, void *stream) {                                      \
-    return rcw_owner<T>(A, n, ld, G, rank, K, d, workspace, pay_mine, status, stream);                             \
+    return rcw_owner<T>(A, n, ld, G, rank, K, d, workspace, pay_mine, nullptr, nullptr, 0, status, stream);        \
   }                                                                                                                \
   int chub_rcw_apply_##SUF(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,   \
                            void *workspace, const double *pay_all, void *V_out, int64_t ldv, int32_t *status,      \
                            void *stream) {                                                                         \
-    return rcw_apply<T>(A, m_loc, n, ld, G, rank, K, d, workspace, pay_all, V_out, ldv, status, stream);           \
+    return rcw_apply<T>(A, m_loc, n, ld, G, rank, K, d, workspace, pay_all, nullptr, nullptr, V_out, ldv, 0,       \
+                        status, stream);                                                                           \
+  }                                                                                                                \
+  int chub_rcw_owner_p2p_##SUF(void *A, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,              \
+                               void *workspace, double *pay_mine, const void *peer_table, void *mailbox,           \
+                               int64_t epoch, int32_t *status, void *stream) {                                     \
+    if (!peer_table || !mailbox) return (int)cudaErrorInvalidValue;                                                \
+    return rcw_owner<T>(A, n, ld, G, rank, K, d, workspace, pay_mine, peer_table, mailbox, epoch, status, stream); \
+  }                                                                                                                \
+  int chub_rcw_apply_p2p_##SUF(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K,          \
+                               int64_t d, void *workspace, const void *peer_table, void *mailbox, void *V_out,     \
+                               int64_t ldv, int64_t epoch, int32_t *status, void *stream) {                        \
+    if (!peer_table || !mailbox) return (int)cudaErrorInvalidValue;                                                \
+    return rcw_apply<T>(A, m_loc, n, ld, G, rank, K, d, workspace, (const double *)mailbox, peer_table, mailbox,   \
+                        V_out, ldv, epoch, status, stream);                                                        \
   }
 DEFINE_RCW(f64, double)
 DEFINE_RCW(f32, float)

@@ -233,6 +233,55 @@ inline RcWave rcw_carve(void *base, int64_t n, int64_t K, int G) {
   return wv;
 }
 
+// ---- exchange over NVLink peer memory instead of NCCL (one process per GPU, cudaIpc-mapped mailboxes).
+// Every rank owns a MAILBOX: for each parity q of the global step count and each sender rank r, max_tasks payload
+// slots plus one flag.  The owner kernel of step d stores its payloads straight into every peer's
+// mailbox (plain stores over NVLink), and its last CTA then raises flag[q][rank] = epoch + d + 1 on
+// every peer (fence.sys, then the flag: payload before flag).  The trail kernel's CTAs spin (acquire) on
+// the flag of the task's owner in their OWN mailbox before they read the payload.  Every rank raises
+// its flag on every peer at EVERY step (also when it owns no task), and one CTA of every trail kernel
+// waits for all G flags: no rank can be more than one step ahead of another, which is what makes two
+// parities enough.  No NCCL call, no host synchronisation between steps: 2 launches per step.
+struct RcwP2P {
+  double *const *peer_mail;  // device array [G]: mailbox base of every rank as mapped here (nullptr = NCCL mode)
+  double *mail;              // this rank's own mailbox
+  long long epoch;           // global step of this call's step 0 (monotonic across calls): step d has
+                             // parity (epoch + d) & 1 and flag value epoch + d + 1
+  int max_tasks;
+};
+// Mailbox layout (doubles): [ long long flag[2][G] | int counter, padding (8) | payload slots [2][G][max_tasks] ].
+// The flags sit at a fixed place, so calls with different K (different max_tasks) can share a mailbox
+// that was sized for the largest one.
+inline size_t rcw_mailbox_doubles(int64_t n, int64_t K, int G) {
+  return (size_t)2 * G + 8 + (size_t)2 * G * rcw_max_tasks(n, K, G) * kRcwPayload;
+}
+__host__ __device__ inline size_t rcw_mail_slot(int q, int r, int i, int G, int max_tasks) {
+  return (size_t)2 * G + 8 + ((size_t)(q * G + r) * max_tasks + i) * kRcwPayload;
+}
+__host__ __device__ inline size_t rcw_mail_flags(int G, int max_tasks) {
+  (void)G; (void)max_tasks;
+  return 0;  // long long flag[2][G], then an int counter
+}
+__device__ __forceinline__ void st_release_sys_s64(long long *p, long long x) {
+  asm volatile("st.release.sys.global.s64 [%0], %1;\n" ::"l"(p), "l"(x) : "memory");
+}
+__device__ __forceinline__ long long ld_acquire_sys_s64(const long long *p) {
+  long long x;
+  asm volatile("ld.acquire.sys.global.s64 %0, [%1];\n" : "=l"(x) : "l"(p) : "memory");
+  return x;
+}
+// Spin until *flag >= want (thread 0 of a CTA); watchdog -> CHUB_STATUS_INTERNAL instead of a hang.
+__device__ __forceinline__ void rcw_wait_flag(const long long *flag, long long want, int32_t *status) {
+  if (ld_acquire_sys_s64(flag) >= want) return;
+  const long long t0 = clock64();
+  while (ld_acquire_sys_s64(flag) < want) {
+    if (clock64() - t0 > 4000000000LL || *(volatile int32_t *)status == CHUB_STATUS_INTERNAL) {
+      atomicMax(status, CHUB_STATUS_INTERNAL);
+      return;
+    }
+  }
+}
+
 // W[u] <- V[u] on the owned rows, check_diag on the owned diagonal entries, {t, S} <- {1, 1}.
 template <typename T>
 __global__ void rcw_prepare_kernel(const T *A, int m_loc, int n, int64_t ld, int G, int rank, const T *V,
@@ -255,11 +304,19 @@ __global__ void rcw_prepare_kernel(const T *A, int m_loc, int n, int64_t ld, int
 
 // One CTA (256 threads) per task of this rank on anti-diagonal d: J = Jfirst + blockIdx.x * G,
 // u = d - J.  Writes the task's payload into pay_mine[blockIdx.x].
+// P2P mode (pp.peer_mail != nullptr): `count` = number of tasks (0: this CTA only raises the flags).
 template <typename T>
-__global__ void __launch_bounds__(kBig) rcw_owner_kernel(const T *A, int n, int64_t ld, int G, RcWave wv, int d,
-                                                         int Jfirst, double *pay_mine, const int32_t *status) {
+__global__ void __launch_bounds__(kBig) rcw_owner_kernel(const T *A, int n, int64_t ld, int G, int rank, RcWave wv,
+                                                         int d, int Jfirst, double *pay_mine, RcwP2P pp, int count,
+                                                         int32_t *status) {
   if (*status != 0) return;
   const int i = blockIdx.x;
+  if (pp.peer_mail && count == 0) {  // nothing to compute at this step: heartbeat only
+    if (threadIdx.x < G)
+      st_release_sys_s64(reinterpret_cast<long long *>(pp.peer_mail[threadIdx.x] + rcw_mail_flags(G, pp.max_tasks)) +
+                             (int)((pp.epoch + d) & 1) * G + rank, pp.epoch + d + 1);
+    return;
+  }
   const int J = Jfirst + i * G, u = d - J;
   // the diagonal block of panel J is local block J / G; shift the base so that GLOBAL row indices work
   const T *Lsh = A + ((int64_t)(J / G) - (int64_t)J) * kRcBlock * ld;
@@ -273,6 +330,30 @@ __global__ void __launch_bounds__(kBig) rcw_owner_kernel(const T *A, int n, int6
   double *pay = pay_mine + (int64_t)i * kRcwPayload;
   chain_body<T, CHUB_ROW_MAJOR, true>(Lsh, n, ld, J, X, wv.W + (int64_t)u * wv.n_pad, pay, pay + kBig, pay + 2 * kBig,
                                       pay + 3 * kBig, (T *)nullptr, pay + 4 * kBig, wv.scal + u * 8, pay + 5 * kBig);
+  if (!pp.peer_mail) return;
+  // ---- push the payload into every rank's mailbox (own included), then the flags
+  __syncthreads();
+  const int q = (int)((pp.epoch + d) & 1);
+  for (int g = 0; g < G; ++g) {
+    double *dst = pp.peer_mail[g] + rcw_mail_slot(q, rank, i, G, pp.max_tasks);
+    for (int e = threadIdx.x; e < kRcwPayload; e += kBig) dst[e] = pay[e];
+  }
+  __threadfence_system();  // my stores are performed system-wide before I am counted as done
+  __syncthreads();
+  __shared__ int last;
+  int *counter = reinterpret_cast<int *>(reinterpret_cast<long long *>(pp.mail + rcw_mail_flags(G, pp.max_tasks)) + 2 * G);
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(counter, 1);
+    last = (done == count - 1);
+    if (last) *counter = 0;  // (the next owner kernel of this rank starts after this one has ended)
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    if (threadIdx.x < G)
+      st_release_sys_s64(reinterpret_cast<long long *>(pp.peer_mail[threadIdx.x] + rcw_mail_flags(G, pp.max_tasks)) +
+                             q * G + rank, pp.epoch + d + 1);
+  }
 }
 
 // Trailing update for every task of anti-diagonal d: blockIdx.y = t <-> J = Jlo + t, u = d - J; its
@@ -281,7 +362,7 @@ __global__ void __launch_bounds__(kBig) rcw_owner_kernel(const T *A, int n, int6
 template <typename T, int NT>
 __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, int64_t ld, int G, int rank, RcWave wv,
                                                        int d, int Jlo, int max_tasks, const double *pay_all,
-                                                       T *V_out, int64_t ldv, const int32_t *status) {
+                                                       T *V_out, int64_t ldv, RcwP2P pp, int32_t *status) {
   __shared__ double cs[3][kPanel];
   __shared__ __align__(16) T tile[NT * kPanel];
   if (*status != 0) return;
@@ -289,11 +370,32 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
   const int J = Jlo + (int)blockIdx.y, u = d - J;
   const double *pay = pay_all + ((int64_t)(J % G) * max_tasks + blockIdx.y / G) * kRcwPayload;
   const int base = J * kBig;
+  if (pp.peer_mail) {
+    // P2P mode: the payload arrives in my mailbox; CTAs with nothing to do leave without waiting, except
+    // (0, 0) which waits for the flags of ALL ranks (the one-step bound on how far ranks drift apart)
+    const int l0e = blockIdx.x * NT;
+    bool work = blockIdx.x == 0;
+    if (!work && l0e < m_loc) {
+      const int64_t g0e = rc_global_row(l0e, G, rank);
+      const int64_t rows_e = min((int64_t)min(NT, m_loc - l0e), (int64_t)n - g0e);
+      work = rows_e > 0 && g0e + rows_e > base;
+    }
+    if (!work) return;
+    const int q = (int)((pp.epoch + d) & 1);
+    const long long *flags = reinterpret_cast<const long long *>(pp.mail + rcw_mail_flags(G, max_tasks)) + q * G;
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+      if (tid < G) rcw_wait_flag(flags + tid, pp.epoch + d + 1, status);
+    } else if (tid == 0) {
+      rcw_wait_flag(flags + J % G, pp.epoch + d + 1, status);
+    }
+    __syncthreads();
+    pay = pp.mail + rcw_mail_slot(q, J % G, blockIdx.y / G, G, max_tasks);
+  }
   if (blockIdx.x == 0) {  // unpack what the next panel of update u and the caller need
-    if (tid < 2) wv.scal[u * 8 + tid] = pay[5 * kBig + tid];
+    if (tid < 2) wv.scal[u * 8 + tid] = __ldcg(pay + 5 * kBig + tid);
     if (V_out)
       for (int k = tid; k < kBig; k += NT)
-        if (base + k < n) V_out[(int64_t)u * ldv + base + k] = (T)pay[4 * kBig + k];
+        if (base + k < n) V_out[(int64_t)u * ldv + base + k] = (T)__ldcg(pay + 4 * kBig + k);
   }
   const int l0 = blockIdx.x * NT;
   if (l0 >= m_loc) return;
@@ -314,9 +416,9 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
     __syncthreads();
     if (tid < kPanel) {
       const int a = c0 - base + tid;
-      cs[0][tid] = tid < bw ? pay[a] : 0.0;
-      cs[1][tid] = tid < bw ? pay[kBig + a] : 1.0;
-      cs[2][tid] = tid < bw ? pay[2 * kBig + a] : 0.0;
+      cs[0][tid] = tid < bw ? __ldcg(pay + a) : 0.0;  // (L2 loads: in P2P mode other GPUs wrote the payload)
+      cs[1][tid] = tid < bw ? __ldcg(pay + kBig + a) : 1.0;
+      cs[2][tid] = tid < bw ? __ldcg(pay + 2 * kBig + a) : 0.0;
     }
     tile_load_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
     if (tid < rows && c0 + kPanel < cend) {  // next block column of my row -> L2 while this one is processed
@@ -347,7 +449,7 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
           w -= lo * cs[0][k];
         }
       }
-      if (R >= c0 && R < c0 + bw) tile[tile_off(tid, R - c0)] = (T)pay[3 * kBig + R - base];
+      if (R >= c0 && R < c0 + bw) tile[tile_off(tid, R - c0)] = (T)__ldcg(pay + 3 * kBig + R - base);
     }
     __syncthreads();
     // rows above the panel inside this CTA (R < base) are loaded but stored back unchanged

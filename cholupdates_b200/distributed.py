@@ -242,6 +242,87 @@ class _CudaRowCyclicBackend:
         _lib.check(rc, "chub_rcw_prepare")
         return pay_mine, pay_all
 
+    # ---- exchange over NVLink peer memory (cudaIpc mailboxes) instead of NCCL
+    def p2p_ready(self, group=None) -> bool:
+        """Set up the mailboxes once (collective: every rank must call it); True if every rank could map
+        every peer's mailbox.  CHUB_RC_P2P=0 disables the peer-memory exchange."""
+        import ctypes
+        import os
+
+        import torch.distributed as dist
+
+        if getattr(self, "_p2p_state", None) is not None:
+            return self._p2p_state
+        torch, lib = self.torch, self.lib
+        vp, i64, ci, sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_size_t
+        lib.chub_rcw_mailbox_bytes.restype, lib.chub_rcw_mailbox_bytes.argtypes = sz, [i64, i64, ci]
+        lib.chub_p2p_alloc.restype, lib.chub_p2p_alloc.argtypes = ci, [sz, ctypes.POINTER(vp)]
+        lib.chub_p2p_export.restype, lib.chub_p2p_export.argtypes = ci, [vp, vp]
+        lib.chub_p2p_import.restype, lib.chub_p2p_import.argtypes = ci, [vp, ctypes.POINTER(vp)]
+        for suf in ("f64", "f32"):
+            f = getattr(lib, f"chub_rcw_owner_p2p_{suf}")
+            f.restype, f.argtypes = ci, [vp, i64, i64, ci, ci, i64, i64, vp, vp, vp, vp, i64, vp, vp]
+            f = getattr(lib, f"chub_rcw_apply_p2p_{suf}")
+            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, i64, i64, vp, vp, vp, vp, i64, i64, vp, vp]
+        ok = os.environ.get("CHUB_RC_P2P", "1") != "0"
+        ptrs = [0] * self.world
+        if ok:
+            n_panels = (self.n + RC_BLOCK - 1) // RC_BLOCK
+            nbytes = int(lib.chub_rcw_mailbox_bytes(self.n, n_panels, self.world))  # enough for every K
+            mine = vp()
+            ok = lib.chub_p2p_alloc(nbytes, ctypes.byref(mine)) == 0
+            handle = (ctypes.c_ubyte * 64)()
+            ok = ok and lib.chub_p2p_export(mine, handle) == 0
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle) if ok else None, group=group)
+        if ok and all(h is not None for h in handles):
+            ptrs[self.rank] = mine.value
+            for g, h in enumerate(handles):
+                if g == self.rank:
+                    continue
+                peer = vp()
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                if lib.chub_p2p_import(buf, ctypes.byref(peer)) != 0:
+                    ok = False
+                    break
+                ptrs[g] = peer.value
+        else:
+            ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.A.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        ok = bool(int(flag.item()))
+        if ok:
+            self.mailbox = mine.value
+            self.peer_table = torch.tensor(ptrs, dtype=torch.int64, device=self.A.device)
+            self.epoch = 0
+        self._p2p_state = ok
+        return ok
+
+    def wave_owner_p2p(self, d, pay_mine):
+        from . import _lib
+
+        rc = getattr(self.lib, f"chub_rcw_owner_p2p_{self.suf}")(
+            self.A.data_ptr(), self.n, self.A.shape[1], self.world, self.rank, self.K, d,
+            self.wave_ws.data_ptr(), pay_mine.data_ptr(), self.peer_table.data_ptr(), self.mailbox, self.epoch,
+            self.status.data_ptr(), self._stream())
+        _lib.check(rc, "chub_rcw_owner_p2p")
+
+    def wave_apply_p2p(self, d):
+        from . import _lib
+
+        rc = getattr(self.lib, f"chub_rcw_apply_p2p_{self.suf}")(
+            self.A.data_ptr(), self.A.shape[0], self.n, self.A.shape[1], self.world, self.rank, self.K, d,
+            self.wave_ws.data_ptr(), self.peer_table.data_ptr(), self.mailbox, self.V_out.data_ptr(),
+            self.V_out.stride(0), self.epoch, self.status.data_ptr(), self._stream())
+        _lib.check(rc, "chub_rcw_apply_p2p")
+
+    def wave_end_p2p(self, steps):
+        """Advance the epoch; one status read (a peer that never arrived trips the device watchdog)."""
+        self.epoch += steps
+        if int(self.status.item()) == 3:
+            raise RuntimeError("cholupdates_b200: a peer did not deliver its panel coefficients "
+                               "(device watchdog, CHUB_STATUS_INTERNAL)")
+
     def wave_owner(self, d, pay_mine):
         from . import _lib
 
@@ -303,10 +384,11 @@ class RowCyclicFactor:
         ``per_panel=True``: per 256-column panel the owner's kernels, one broadcast, the apply kernels
         (``chub_rc_panel_owner`` / ``chub_rc_panel_apply``).  ``per_panel=False``: the K = 1 case of
         ``update_many`` (one fused owner kernel, one all-gather, one trail kernel per panel).  Both are
-        bound by per-panel host / launch / collective latency; measured on 8 B200 at n = 65536 the
-        broadcast form is faster (27 ms vs 64 ms: ``all_gather_into_tensor`` costs more host time per
-        call than ``broadcast``), so it is the default whenever there is an exchange.  Successive
-        vectors belong in ``update_many`` (1.25 ms per update at K = 64)."""
+        bound by per-panel launch / exchange latency.  With NCCL the broadcast form is the faster one
+        (8 B200, n = 65536: 27 ms vs 64 ms -- ``all_gather_into_tensor`` costs more host time per call
+        than ``broadcast``); when the ranks can map each other's mailboxes (``update_many``'s
+        peer-memory exchange) the wavefront form needs no collective at all and is the default.
+        Successive vectors belong in ``update_many``."""
         import numpy as np
         import torch
         import torch.distributed as dist
@@ -319,7 +401,9 @@ class RowCyclicFactor:
         if not v.is_contiguous():
             raise ValueError("`v` must be contiguous.")
         if per_panel is None:
-            per_panel = self.world > 1
+            # with an exchange: the wavefront code only if it can use peer memory (no collective per panel)
+            per_panel = self.world > 1 and not (hasattr(self.backend, "p2p_ready")
+                                                and self.backend.p2p_ready(self.group))
         if not per_panel and hasattr(self.backend, "wave_begin"):
             return self.update_many(v.reshape(1, -1), check_diag=check_diag)[0]
         be = self.backend
@@ -386,7 +470,7 @@ class RowCyclicFactor:
             raise np.linalg.LinAlgError("The downdated matrix is not positive definite.")
         return v_out
 
-    def update_many(self, V, check_diag: bool = True):
+    def update_many(self, V, check_diag: bool = True, p2p=None):
         """Apply the K successive rank-1 updates ``V[0], V[1], ...`` (``V``: ``(K, n)``, identical on
         every rank) in place -- the same result as K calls of ``update``, scheduled as a wavefront.
 
@@ -396,7 +480,10 @@ class RowCyclicFactor:
         applies them to its local rows.  ``K + ceil(n/256) - 1`` exchanges replace ``K * ceil(n/256)``
         broadcasts.  Returns the ``(K, n)`` scratch vectors (rotg's z_k, complete on
         every rank).  Raises ``LinAlgError`` on every rank, with nothing modified, if ``check_diag``
-        finds a zero on the input diagonal."""
+        finds a zero on the input diagonal.
+
+        ``p2p``: None = exchange over NVLink peer memory when every rank can map every peer's mailbox
+        (one node, cudaIpc), else NCCL all-gather; False = NCCL; True = peer memory or raise."""
         import numpy as np
         import torch
         import torch.distributed as dist
@@ -420,7 +507,18 @@ class RowCyclicFactor:
                 dist.all_reduce(st, op=dist.ReduceOp.MAX, group=self.group)
             if int(st.item()) == 1:
                 raise np.linalg.LinAlgError("The given Cholesky factor `L` contains zeros on its diagonal")
-        for d in range(K + (self.n + RC_BLOCK - 1) // RC_BLOCK - 1):
+        steps = K + (self.n + RC_BLOCK - 1) // RC_BLOCK - 1
+        if multi and p2p is not False and hasattr(be, "p2p_ready") and be.p2p_ready(self.group):
+            # exchange over NVLink peer memory: the owner kernel stores the coefficients into every
+            # peer's mailbox, the trail kernel waits for them there -- 2 launches per step, no collective
+            for d in range(steps):
+                be.wave_owner_p2p(d, pay_mine)
+                be.wave_apply_p2p(d)
+            be.wave_end_p2p(steps)
+            return V_out
+        if p2p is True and multi:
+            raise RuntimeError("cholupdates_b200: the peer-memory exchange is not available on this group")
+        for d in range(steps):
             be.wave_owner(d, pay_mine)
             if multi:
                 dist.all_gather_into_tensor(pay_all, pay_mine, group=self.group)

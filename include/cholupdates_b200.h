@@ -194,6 +194,35 @@ int chub_rcw_apply_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G,
                        void *workspace, const double *pay_all, void *V_out, int64_t ldv, int32_t *status,
                        void *stream);
 
+/* ---- the same wavefront with the exchange over NVLink peer memory instead of a collective
+ *      (one process per GPU).  Every rank allocates a mailbox (chub_p2p_alloc of
+ *      chub_rcw_mailbox_bytes), exports its cudaIpc handle (64 bytes), imports the peers' handles
+ *      and passes the G mapped base pointers (own mailbox at index `rank`) as a DEVICE array
+ *      `peer_table`.  Per step the owner kernel stores its payloads straight into every peer's mailbox
+ *      and raises a flag there; the trail kernel waits for the flags in its own mailbox: 2 launches
+ *      per step, no collective, no host synchronisation.  `epoch` = number of steps of all earlier
+ *      calls on this mailbox (identical on every rank); every rank must call owner and apply for
+ *      every step d = 0 .. K + ceil(n/256) - 2.  A peer that never arrives trips a device watchdog
+ *      (CHUB_STATUS_INTERNAL) instead of hanging. */
+size_t chub_rcw_mailbox_bytes(int64_t n, int64_t K, int G);
+int chub_p2p_alloc(size_t bytes, void **ptr);
+int chub_p2p_free(void *ptr);
+int chub_p2p_export(void *ptr, void *handle64);
+int chub_p2p_import(const void *handle64, void **peer_ptr);
+int chub_p2p_close(void *peer_ptr);
+int chub_rcw_owner_p2p_f64(void *A_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
+                           void *workspace, double *pay_mine, const void *peer_table, void *mailbox,
+                           int64_t epoch, int32_t *status, void *stream);
+int chub_rcw_owner_p2p_f32(void *A_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
+                           void *workspace, double *pay_mine, const void *peer_table, void *mailbox,
+                           int64_t epoch, int32_t *status, void *stream);
+int chub_rcw_apply_p2p_f64(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K,
+                           int64_t d, void *workspace, const void *peer_table, void *mailbox, void *V_out,
+                           int64_t ldv, int64_t epoch, int32_t *status, void *stream);
+int chub_rcw_apply_p2p_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K,
+                           int64_t d, void *workspace, const void *peer_table, void *mailbox, void *V_out,
+                           int64_t ldv, int64_t epoch, int32_t *status, void *stream);
+
 /* ---- tuning / introspection (bench.py and tests) */
 /* Force a kernel path: 0 = automatic, 1 = single-CTA kernels only, 2 = panel
  * (multi-kernel) path, 3 = persistent dataflow kernel.  Returns the previous value. */

@@ -57,10 +57,16 @@ def main():
     assert int(t.item()) == 0
 
     # wavefront form: K successive updates in one call
-    for K in (3, 2 * ((n + 255) // 256) + 1):
+    facw = None
+    for K, p2p in ((3, None), (2 * ((n + 255) // 256) + 1, None), (5, False), (4, None)):
         A = torch.from_numpy(np.ascontiguousarray(L[rows])).to(dev)
         V = np.stack([np.random.default_rng([2, u]).standard_normal(n) for u in range(K)])
-        RowCyclicFactor(A, n, rank, world).update_many(torch.from_numpy(V.copy()).to(dev))
+        if facw is None:
+            facw = RowCyclicFactor(A, n, rank, world)  # one factor object: the mailbox epochs carry over
+        else:
+            facw.A.copy_(A)
+            A = facw.A
+        facw.update_many(torch.from_numpy(V.copy()).to(dev), p2p=p2p)
         L_ref = np.array(L, order="F")
         for u in range(K):
             oracle.update(L_ref, V[u].copy())
@@ -71,7 +77,8 @@ def main():
         t = torch.tensor([0 if ok else 1], device=dev)
         dist.all_reduce(t)
         if rank == 0:
-            print(f"[rowcyclic wavefront parity] n={n} world={world} K={K}: rel. Frobenius error (rank 0 rows) "
+            mode = "NCCL all-gather" if p2p is False else ("peer-memory exchange" if getattr(facw.backend, "_p2p_state", False) else "NCCL all-gather (no peer access)")
+            print(f"[rowcyclic wavefront parity] n={n} world={world} K={K} {mode}: rel. Frobenius error (rank 0 rows) "
                   f"{err:.2e} (bar {tol_for(np.float64, n):.1e}); all ranks ok: {int(t.item()) == 0}", flush=True)
         assert int(t.item()) == 0
 
@@ -131,7 +138,7 @@ def main():
             per = float(ms.item()) / updates
             bytes_upd = 8 * n * (n + 1) + 16 * n
             print(f"[rowcyclic timing] n={n} world={world} single update, "
-                  f"{'launch-per-panel + broadcast' if per_panel else 'K=1 wavefront (fused owner kernel + all-gather)'}: "
+                  f"{'launch-per-panel + broadcast' if per_panel else 'K=1 wavefront'}: "
                   f"{per:.3f} ms/update, {bytes_upd / per / 1e6:.0f} GB/s aggregate "
                   f"({bytes_upd / per / 1e6 / world:.0f} GB/s per GPU)", flush=True)
     # one downdate (v = 0.5 * L u / |u| is always valid)
@@ -155,22 +162,24 @@ def main():
     # wavefront: k_wave successive updates in one call (BASELINE.json configs[4]: 64)
     gv.manual_seed(8)
     V = torch.randn((k_wave, n), dtype=torch.float64, device=dev, generator=gv)
-    fac.update_many(V[: min(4, k_wave)], check_diag=False)  # warm-up
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0.record()
-    fac.update_many(V, check_diag=False)
-    e1.record()
-    dist.barrier()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        per = float(ms.item()) / k_wave
-        bytes_upd = 8 * n * (n + 1) + 16 * n
-        print(f"[rowcyclic wavefront timing] n={n} world={world} K={k_wave}: {per:.3f} ms/update "
-              f"({float(ms.item()):.1f} ms total), {bytes_upd / per / 1e6:.0f} GB/s aggregate "
-              f"({bytes_upd / per / 1e6 / world:.0f} GB/s per GPU)", flush=True)
+    for p2p in (False, None):
+        fac.update_many(V[: min(4, k_wave)], check_diag=False, p2p=p2p)  # warm-up
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        fac.update_many(V, check_diag=False, p2p=p2p)
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            per = float(ms.item()) / k_wave
+            bytes_upd = 8 * n * (n + 1) + 16 * n
+            mode = "NCCL all-gather" if p2p is False else ("peer-memory exchange" if getattr(fac.backend, "_p2p_state", False) else "NCCL all-gather (no peer access)")
+            print(f"[rowcyclic wavefront timing] n={n} world={world} K={k_wave} {mode}: {per:.3f} ms/update "
+                  f"({float(ms.item()):.1f} ms total), {bytes_upd / per / 1e6:.0f} GB/s aggregate "
+                  f"({bytes_upd / per / 1e6 / world:.0f} GB/s per GPU)", flush=True)
     finite = bool(torch.isfinite(A).all().item())
     assert finite
     dist.destroy_process_group()
