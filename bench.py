@@ -239,6 +239,10 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "rowcyclic":
+        print(json.dumps({"impl": "reference", "unavailable": "the n=65536 workload needs a 34 GB host factor and "
+                          "about 2 s per update on the reference; its reference arm is --workload update"}), flush=True)
+        return
     n = N_BIG if args.workload == "update" else N_SMALL
     cores = os.cpu_count()
     if args.workload == "update":
@@ -546,13 +550,131 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------- row-cyclic workload
+def run_rowcyclic(args):
+    """BASELINE.json configs[4]: ONE n = 65536 fp64 factor distributed block-row-cyclically over the N
+    GPUs of the job, 64 successive rank-1 updates per step (RowCyclicFactor.update_many: wavefront over
+    (update, panel) tasks, coefficients exchanged over NVLink peer memory or NCCL).  n is fixed, so
+    the scaling over N is strong."""
+    import torch
+    import torch.distributed as dist
+
+    from cholupdates_b200 import _lib
+    from cholupdates_b200.distributed import RowCyclicFactor, rc_owned_rows
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.require_device()
+    peak, peak_src = measured_peaks()
+    n, K = args.n or 65536, args.k
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rows = torch.from_numpy(rc_owned_rows(n, rank, world)).to(dev)
+    A = torch.empty((rows.numel(), n), dtype=torch.float64, device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(4321 + rank)
+    cols = torch.arange(n, device=dev)
+    for lo in range(0, rows.numel(), 2048):  # in chunks: no second copy of the local rows
+        r = rows[lo:lo + 2048]
+        blk = torch.randn((r.numel(), n), dtype=torch.float64, device=dev, generator=g).mul_(1.0 / np.sqrt(n))
+        blk.masked_fill_(cols[None, :] > r[:, None], 0.0)
+        blk[torch.arange(r.numel(), device=dev), r] = 1.0 + torch.rand(r.numel(), dtype=torch.float64, device=dev, generator=g)
+        A[lo:lo + 2048] = blk
+    del blk
+    fac = RowCyclicFactor(A, n, rank, world)
+    gv = torch.Generator(device=dev)
+    gv.manual_seed(7)  # the same vectors on every rank
+    V_bank = torch.randn((2, K, n), dtype=torch.float64, device=dev, generator=gv)
+    p2p = None if args.exchange == "auto" else (args.exchange == "p2p")
+
+    for i in range(max(args.warmup, 1)):
+        fac.update_many(V_bank[i % 2], check_diag=False, p2p=p2p)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lib = _lib.load()
+    lib.chub_launch_count(1)
+    sampler.mark_begin()
+    e0.record()
+    for i in range(args.steps):
+        fac.update_many(V_bank[i % 2], check_diag=False, p2p=p2p)
+    e1.record()
+    barrier()
+    sampler.mark_end()
+    launches = int(lib.chub_launch_count(0))
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_update = total_ms / (args.steps * K)
+    alg_bytes = algorithmic_bytes_update(n)
+    per_gpu = alg_bytes / world / (ms_per_update * 1e-3) / 1e9
+
+    # e2e: the K vectors come from pinned host memory and the K scratch vectors go back every step; the
+    # 34 GB factor is the resident state of this workload (it never fits a per-step PCIe round trip)
+    Vh = torch.empty((K, n), dtype=torch.float64, pin_memory=True).copy_(V_bank[0])
+    Zh = torch.empty((K, n), dtype=torch.float64, pin_memory=True)
+    Vd = torch.empty((K, n), dtype=torch.float64, device=dev)
+    reps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(reps):
+        Vd.copy_(Vh, non_blocking=True)
+        Z = fac.update_many(Vd, check_diag=False, p2p=p2p)
+        Zh.copy_(Z, non_blocking=True)
+        torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    finite = bool(torch.isfinite(A[:4]).all().item())
+    if rank == 0:
+        mode = "single GPU (no exchange)" if world == 1 else (
+            "peer memory (cudaIpc mailboxes)" if getattr(fac.backend, "_p2p_state", False) and p2p is not False
+            else "NCCL all-gather")
+        line = {
+            "metric": f"successive rank-1 updates/s of one n={n} fp64 factor, block-row-cyclic over the job's GPUs ({K} per step)",
+            "value": args.steps * K / (total_ms * 1e-3), "unit": "updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": total_ms / args.steps,
+            "ms_per_update": ms_per_update, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"rowcyclic_n{n}_k{K}_f64", "n": n, "updates_per_step": K, "exchange": mode,
+                       "l2": "inputs_larger_than_L2", "parallelism": f"block-row-cyclic x{world} (256-row blocks)",
+                       "result_finite": finite},
+            "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s per GPU",
+                         "frac": per_gpu / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": alg_bytes, "note": "one read + one write of the triangle per update, split over the GPUs"},
+            "cpu_baseline": None,
+            "e2e": {"value": reps * K / float(te.item()), "unit": "updates/s", "steps": reps,
+                    "h2d_bytes_per_step": K * n * 8, "d2h_bytes_per_step": K * n * 8,
+                    "api": "RowCyclicFactor.update_many(V copied from pinned host memory; scratch vectors copied back)"},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="update", choices=["update", "batched"])
+    ap.add_argument("--workload", default="update", choices=["update", "batched", "rowcyclic"])
+    ap.add_argument("--rc-n", dest="n", type=int, default=0, help="rowcyclic: order of the factor (default 65536)")
+    ap.add_argument("--rc-k", dest="k", type=int, default=64, help="rowcyclic: successive updates per step")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="rowcyclic: coefficient exchange")
     ap.add_argument("--layout", default="C", choices=["C", "F"])
     ap.add_argument("--path", type=int, default=0, help="force kernel path (1 small, 2 panel, 3 dataflow)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -560,6 +682,10 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "rowcyclic":
+        if "--steps" not in sys.argv:
+            args.steps = 3
+        run_rowcyclic(args)
     else:
         run_gpu_arm(args)
 
