@@ -378,8 +378,9 @@ int rcw_owner(void *A, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_
   const int count = Jfirst > Jhi ? 0 : (Jhi - Jfirst) / G + 1;
   if (count == 0 && !peer_table) return 0;
   // (P2P mode: a rank without a task at this step still raises its flags -- one CTA)
-  rcw_owner_kernel<T><<<count > 0 ? count : 1, kBig, 0, st>>>((const T *)A, (int)n, ld, G, rank, wv, (int)d, Jfirst,
-                                                              pay_mine, pp, count, status);
+  CK(cudaFuncSetAttribute(rcw_owner_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRcwOwnerSmem));
+  rcw_owner_kernel<T><<<count > 0 ? count : 1, kBig, kRcwOwnerSmem, st>>>((const T *)A, (int)n, ld, G, rank, wv, (int)d,
+                                                                          Jfirst, pay_mine, pp, count, status);
   LAUNCHED();
   return 0;
 }

@@ -90,11 +90,24 @@ __global__ void large_prepare_kernel(const T *L, int n, int64_t ld, const T *v, 
 // by forward substitution (reciprocal diagonal precomputed, two accumulators per dot product so
 // that the dependent FMA chain is half as long).  Blocks that stick out of the matrix are padded
 // with the identity.  Must be called by all 4 warps of a 128-thread CTA (static shared memory).
+// Core: one warp, staging area `Lw` = [32][33] doubles + `Rw` = [32] doubles of shared memory.
+template <typename T, int LAYOUT>
+__device__ __forceinline__ void invdiag_block_smem(const T *L, int n, int64_t ld, double *X, int blk,
+                                                   double (*Lw)[kPanel + 1], double *Rw);
+constexpr int kInvStageDoubles = kPanel * (kPanel + 1) + kPanel;  // per warp
+
 template <typename T, int LAYOUT>
 __device__ __forceinline__ void invdiag_block_to(const T *L, int n, int64_t ld, double *X, int blk) {
   __shared__ double Ls[4][kPanel][kPanel + 1];
   __shared__ double Rd[4][kPanel];
-  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 3;
+  const int warp = (threadIdx.x >> 5) & 3;
+  invdiag_block_smem<T, LAYOUT>(L, n, ld, X, blk, Ls[warp], Rd[warp]);
+}
+
+template <typename T, int LAYOUT>
+__device__ __forceinline__ void invdiag_block_smem(const T *L, int n, int64_t ld, double *X, int blk,
+                                                   double (*Lw)[kPanel + 1], double *Rw) {
+  const int lane = threadIdx.x & 31;
   const int nb = (n + 31) / 32;
   if (blk >= nb) return;
   const int c0 = blk * kPanel;
@@ -104,10 +117,10 @@ __device__ __forceinline__ void invdiag_block_to(const T *L, int n, int64_t ld, 
     if (LAYOUT == CHUB_ROW_MAJOR) { i = r; j = lane; } else { i = lane; j = r; }
     double x = (i == j) ? 1.0 : 0.0;
     if (c0 + i < n && c0 + j < n && j <= i) x = (double)L[idx<LAYOUT>(c0 + i, c0 + j, ld)];
-    Ls[warp][i][j] = x;
+    Lw[i][j] = x;
   }
   __syncwarp();
-  Rd[warp][lane] = 1.0 / Ls[warp][lane][lane];
+  Rw[lane] = 1.0 / Lw[lane][lane];
   __syncwarp();
   double x[kPanel];
   const int j = lane;
@@ -116,10 +129,10 @@ __device__ __forceinline__ void invdiag_block_to(const T *L, int n, int64_t ld, 
     double a0 = (i == j) ? 1.0 : 0.0, a1 = 0.0;
 #pragma unroll
     for (int m = 0; m < kPanel; m += 2) {
-      if (m < i) a0 -= Ls[warp][i][m] * x[m];          // x[m] = 0 for m < j
-      if (m + 1 < i) a1 -= Ls[warp][i][m + 1] * x[m + 1];
+      if (m < i) a0 -= Lw[i][m] * x[m];          // x[m] = 0 for m < j
+      if (m + 1 < i) a1 -= Lw[i][m + 1] * x[m + 1];
     }
-    x[i] = (i >= j) ? (a0 + a1) * Rd[warp][i] : 0.0;
+    x[i] = (i >= j) ? (a0 + a1) * Rw[i] : 0.0;
   }
 #pragma unroll
   for (int i = 0; i < kPanel; ++i) X[i * kXStride + j] = x[i];
@@ -166,17 +179,28 @@ __device__ __forceinline__ void chain_body(const T *L, int n, int64_t ld, int J,
   double wv = valid ? w_in[R] : 0.0;
   pall[a] = 0.0;
   const int rr = a >> 3, part = a & 7;  // mat-vec role: row rr of the block, columns 4*part..+3
+  // this thread's 32 entries of L[R][c0 .. c0+31] (needed only by rows below the block); the segment of
+  // block s+1 is loaded while the mat-vec and the FMAs of block s run
+  double lrow[kPanel], lnext[kPanel];
+  {
+    const bool below0 = valid && R >= base + kPanel;
+#pragma unroll
+    for (int k = 0; k < kPanel; ++k) lnext[k] = below0 ? (double)L[idx<LAYOUT>(R, base + k, ld)] : 0.0;
+  }
   for (int s = 0; s < kBig / kPanel; ++s) {
     const int c0 = base + s * kPanel;
     if (c0 >= n) break;  // uniform
     const double *X = Xp + (int64_t)s * kXBlock + rr * kXStride + part * 4;
     const double x0 = X[0], x1 = X[1], x2 = X[2], x3 = X[3];
-    // prefetch this thread's 32 entries of L[R][c0 .. c0+31] (needed only by rows below the block)
     const bool below = valid && R >= c0 + kPanel;
-    double lrow[kPanel];
 #pragma unroll
-    for (int k = 0; k < kPanel; ++k)
-      lrow[k] = below ? (double)L[idx<LAYOUT>(R, c0 + k, ld)] : 0.0;
+    for (int k = 0; k < kPanel; ++k) lrow[k] = lnext[k];
+    {
+      const int c1 = c0 + kPanel;
+      const bool below1 = s + 1 < kBig / kPanel && c1 < n && valid && R >= c1 + kPanel;
+#pragma unroll
+      for (int k = 0; k < kPanel; ++k) lnext[k] = below1 ? (double)L[idx<LAYOUT>(R, c1 + k, ld)] : 0.0;
+    }
     if (warp == s) wsm[lane] = wv;
     __syncthreads();
     double acc = x0 * wsm[part * 4] + x1 * wsm[part * 4 + 1] + x2 * wsm[part * 4 + 2] +

@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(128) rc_dd_sweep_kernel(T *A, int m_loc, int n
 //                      local rows below it
 // K + nJ - 1 steps replace K * nJ per-panel broadcasts; the per-step latency is amortised over up
 // to min(K, nJ) panels of streaming work.  Same arithmetic as the per-panel kernels above.
+constexpr size_t kRcwOwnerSmem = (size_t)(kBig / kPanel) * kInvStageDoubles * sizeof(double);  // 69 632 B
 constexpr int kRcwTrailNT = 128;           // rows per CTA of the trail kernel (32 / 64 / 128)
 constexpr int kRcwPayload = 5 * kBig + 8;  // p, c, sigma, dn, z, scal[8] ({t, S} leaving the panel)
 
@@ -322,10 +323,13 @@ __global__ void __launch_bounds__(kBig) rcw_owner_kernel(const T *A, int n, int6
   const T *Lsh = A + ((int64_t)(J / G) - (int64_t)J) * kRcBlock * ld;
   double *X = wv.X + (int64_t)i * (kBig / kPanel) * kXBlock;
   const int warp = threadIdx.x >> 5;
-  // the 8 inverse diagonal blocks, four warps at a time (invdiag_block_to's shared staging holds 4)
-  if (warp < 4) invdiag_block_to<T, CHUB_ROW_MAJOR>(Lsh, n, ld, X + (int64_t)warp * kXBlock, J * (kBig / kPanel) + warp);
-  __syncthreads();
-  if (warp >= 4) invdiag_block_to<T, CHUB_ROW_MAJOR>(Lsh, n, ld, X + (int64_t)warp * kXBlock, J * (kBig / kPanel) + warp);
+  // the 8 inverse diagonal blocks at once, one warp each (staging in dynamic shared memory)
+  extern __shared__ __align__(16) double rcw_stage[];  // [8][kInvStageDoubles]
+  {
+    double *stg = rcw_stage + (size_t)warp * kInvStageDoubles;
+    invdiag_block_smem<T, CHUB_ROW_MAJOR>(Lsh, n, ld, X + (int64_t)warp * kXBlock, J * (kBig / kPanel) + warp,
+                                          reinterpret_cast<double (*)[kPanel + 1]>(stg), stg + kPanel * (kPanel + 1));
+  }
   __syncthreads();
   double *pay = pay_mine + (int64_t)i * kRcwPayload;
   chain_body<T, CHUB_ROW_MAJOR, true>(Lsh, n, ld, J, X, wv.W + (int64_t)u * wv.n_pad, pay, pay + kBig, pay + 2 * kBig,
@@ -363,7 +367,8 @@ template <typename T, int NT>
 __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, int64_t ld, int G, int rank, RcWave wv,
                                                        int d, int Jlo, int max_tasks, const double *pay_all,
                                                        T *V_out, int64_t ldv, RcwP2P pp, int32_t *status) {
-  __shared__ double cs[3][kPanel];
+  __shared__ __align__(16) double cp[kPanel];    // p_k
+  __shared__ __align__(16) double2 ccs[kPanel];  // (c_k, sigma_k): one 16-byte load per column
   __shared__ __align__(16) T tile[NT * kPanel];
   if (*status != 0) return;
   const int tid = threadIdx.x;
@@ -416,9 +421,8 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
     __syncthreads();
     if (tid < kPanel) {
       const int a = c0 - base + tid;
-      cs[0][tid] = tid < bw ? __ldcg(pay + a) : 0.0;  // (L2 loads: in P2P mode other GPUs wrote the payload)
-      cs[1][tid] = tid < bw ? __ldcg(pay + kBig + a) : 1.0;
-      cs[2][tid] = tid < bw ? __ldcg(pay + 2 * kBig + a) : 0.0;
+      cp[tid] = tid < bw ? __ldcg(pay + a) : 0.0;  // (L2 loads: in P2P mode other GPUs wrote the payload)
+      ccs[tid] = make_double2(tid < bw ? __ldcg(pay + kBig + a) : 1.0, tid < bw ? __ldcg(pay + 2 * kBig + a) : 0.0);
     }
     tile_load_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
     if (tid < rows && c0 + kPanel < cend) {  // next block column of my row -> L2 while this one is processed
@@ -433,10 +437,15 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
         T *trow = tile + tid * kPanel;
         const int sw = tid & 31;
 #pragma unroll
-        for (int k = 0; k < kPanel; ++k) {
-          const double lo = (double)trow[k ^ sw];
-          trow[k ^ sw] = (T)fma(cs[1][k], lo, cs[2][k] * w);
-          w = fma(-lo, cs[0][k], w);
+        for (int k = 0; k < kPanel; k += 2) {  // 3 coefficient loads of 16 bytes per 2 columns
+          const double2 p2 = *reinterpret_cast<const double2 *>(cp + k);
+          const double2 q0 = ccs[k], q1 = ccs[k + 1];
+          const double l0 = (double)trow[k ^ sw];
+          trow[k ^ sw] = (T)fma(q0.x, l0, q0.y * w);
+          w = fma(-l0, p2.x, w);
+          const double l1 = (double)trow[(k + 1) ^ sw];
+          trow[(k + 1) ^ sw] = (T)fma(q1.x, l1, q1.y * w);
+          w = fma(-l1, p2.y, w);
         }
       }
     } else if (valid) {
@@ -445,8 +454,8 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
         if (k < bw && c0 + k < R) {
           const int o = tile_off(tid, k);
           const double lo = (double)tile[o];
-          tile[o] = (T)(cs[1][k] * lo + cs[2][k] * w);
-          w -= lo * cs[0][k];
+          tile[o] = (T)(ccs[k].x * lo + ccs[k].y * w);
+          w -= lo * cp[k];
         }
       }
       if (R >= c0 && R < c0 + bw) tile[tile_off(tid, R - c0)] = (T)__ldcg(pay + 3 * kBig + R - base);
