@@ -387,7 +387,7 @@ int rcw_owner(void *A, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_
 template <typename T>
 int rcw_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
               void *workspace, const double *pay_all, const void *peer_table, void *mailbox, void *V_out,
-              int64_t ldv, int64_t epoch, int32_t *status, void *stream) {
+              int64_t ldv, int64_t epoch, int rows_mode, int32_t *status, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   RcWave wv = rcw_carve(workspace, n, K, G);
   RcwP2P pp{(double *const *)peer_table, (double *)mailbox, (long long)epoch, rcw_max_tasks(n, K, G)};
@@ -396,16 +396,20 @@ int rcw_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, in
   if (Jhi < Jlo) return 0;
   int nt = kRcwTrailNT;
   if (const char *e = getenv("CHUB_RCW_NT")) nt = atoi(e);
-  dim3 grid((unsigned)((m_loc > 0 ? m_loc + nt - 1 : nt) / nt), (unsigned)(Jhi - Jlo + 1));
+  if (nt != 32 && nt != 64) nt = 128;
+  if (rows_mode < 0 || rows_mode > 2) return (int)cudaErrorInvalidValue;
+  // head of the look-ahead split: only the CTAs of the two 256-row blocks J and J+1 of every task
+  const unsigned gx = rows_mode == 1 ? (unsigned)(2 * kRcBlock / nt) : (unsigned)((m_loc > 0 ? m_loc + nt - 1 : nt) / nt);
+  dim3 grid(gx, (unsigned)(Jhi - Jlo + 1));
   if (nt == 32)
     rcw_trail_kernel<T, 32><<<grid, 32, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, wv, (int)d, Jlo,
-                                                 pp.max_tasks, pay_all, (T *)V_out, ldv, pp, status);
+                                                 pp.max_tasks, pay_all, (T *)V_out, ldv, pp, rows_mode, status);
   else if (nt == 64)
     rcw_trail_kernel<T, 64><<<grid, 64, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, wv, (int)d, Jlo,
-                                                 pp.max_tasks, pay_all, (T *)V_out, ldv, pp, status);
+                                                 pp.max_tasks, pay_all, (T *)V_out, ldv, pp, rows_mode, status);
   else
     rcw_trail_kernel<T, 128><<<grid, 128, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, wv, (int)d, Jlo,
-                                                   pp.max_tasks, pay_all, (T *)V_out, ldv, pp, status);
+                                                   pp.max_tasks, pay_all, (T *)V_out, ldv, pp, rows_mode, status);
   LAUNCHED();
   return 0;
 }
@@ -561,10 +565,10 @@ DEFINE_RC_DD(f32, float)
     return rcw_owner<T>(A, n, ld, G, rank, K, d, workspace, pay_mine, nullptr, nullptr, 0, status, stream);        \
   }                                                                                                                \
   int chub_rcw_apply_##SUF(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,   \
-                           void *workspace, const double *pay_all, void *V_out, int64_t ldv, int32_t *status,      \
-                           void *stream) {                                                                         \
+                           void *workspace, const double *pay_all, void *V_out, int64_t ldv, int rows_mode,        \
+                           int32_t *status, void *stream) {                                                        \
     return rcw_apply<T>(A, m_loc, n, ld, G, rank, K, d, workspace, pay_all, nullptr, nullptr, V_out, ldv, 0,       \
-                        status, stream);                                                                           \
+                        rows_mode, status, stream);                                                                \
   }                                                                                                                \
   int chub_rcw_owner_p2p_##SUF(void *A, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,              \
                                void *workspace, double *pay_mine, const void *peer_table, void *mailbox,           \
@@ -574,10 +578,10 @@ DEFINE_RC_DD(f32, float)
   }                                                                                                                \
   int chub_rcw_apply_p2p_##SUF(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K,          \
                                int64_t d, void *workspace, const void *peer_table, void *mailbox, void *V_out,     \
-                               int64_t ldv, int64_t epoch, int32_t *status, void *stream) {                        \
+                               int64_t ldv, int64_t epoch, int rows_mode, int32_t *status, void *stream) {         \
     if (!peer_table || !mailbox) return (int)cudaErrorInvalidValue;                                                \
     return rcw_apply<T>(A, m_loc, n, ld, G, rank, K, d, workspace, (const double *)mailbox, peer_table, mailbox,   \
-                        V_out, ldv, epoch, status, stream);                                                        \
+                        V_out, ldv, epoch, rows_mode, status, stream);                                             \
   }
 DEFINE_RCW(f64, double)
 DEFINE_RCW(f32, float)

@@ -243,6 +243,7 @@ inline RcWave rcw_carve(void *base, int64_t n, int64_t K, int G) {
 // its flag on every peer at EVERY step (also when it owns no task), and one CTA of every trail kernel
 // waits for all G flags: no rank can be more than one step ahead of another, which is what makes two
 // parities enough.  No NCCL call, no host synchronisation between steps: 2 launches per step.
+constexpr int kRcwSets = 4;
 struct RcwP2P {
   double *const *peer_mail;  // device array [G]: mailbox base of every rank as mapped here (nullptr = NCCL mode)
   double *mail;              // this rank's own mailbox
@@ -250,18 +251,20 @@ struct RcwP2P {
                              // parity (epoch + d) & 1 and flag value epoch + d + 1
   int max_tasks;
 };
-// Mailbox layout (doubles): [ long long flag[2][G] | int counter, padding (8) | payload slots [2][G][max_tasks] ].
+// Mailbox layout (doubles): [ long long flag[4][G] | int counter, padding (8) | payload slots [4][G][max_tasks] ].
+// Four sets (global step & 3): with the look-ahead split the bulk of step d's trail may still be reading
+// its payloads while the payloads of step d+2 arrive (never those of step d+3, see distributed.py).
 // The flags sit at a fixed place, so calls with different K (different max_tasks) can share a mailbox
 // that was sized for the largest one.
 inline size_t rcw_mailbox_doubles(int64_t n, int64_t K, int G) {
-  return (size_t)2 * G + 8 + (size_t)2 * G * rcw_max_tasks(n, K, G) * kRcwPayload;
+  return (size_t)kRcwSets * G + 8 + (size_t)kRcwSets * G * rcw_max_tasks(n, K, G) * kRcwPayload;
 }
 __host__ __device__ inline size_t rcw_mail_slot(int q, int r, int i, int G, int max_tasks) {
-  return (size_t)2 * G + 8 + ((size_t)(q * G + r) * max_tasks + i) * kRcwPayload;
+  return (size_t)kRcwSets * G + 8 + ((size_t)(q * G + r) * max_tasks + i) * kRcwPayload;
 }
 __host__ __device__ inline size_t rcw_mail_flags(int G, int max_tasks) {
   (void)G; (void)max_tasks;
-  return 0;  // long long flag[2][G], then an int counter
+  return 0;  // long long flag[kRcwSets][G], then an int counter
 }
 __device__ __forceinline__ void st_release_sys_s64(long long *p, long long x) {
   asm volatile("st.release.sys.global.s64 [%0], %1;\n" ::"l"(p), "l"(x) : "memory");
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(kBig) rcw_owner_kernel(const T *A, int n, int6
   if (pp.peer_mail && count == 0) {  // nothing to compute at this step: heartbeat only
     if (threadIdx.x < G)
       st_release_sys_s64(reinterpret_cast<long long *>(pp.peer_mail[threadIdx.x] + rcw_mail_flags(G, pp.max_tasks)) +
-                             (int)((pp.epoch + d) & 1) * G + rank, pp.epoch + d + 1);
+                             (int)((pp.epoch + d) & (kRcwSets - 1)) * G + rank, pp.epoch + d + 1);
     return;
   }
   const int J = Jfirst + i * G, u = d - J;
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(kBig) rcw_owner_kernel(const T *A, int n, int6
   if (!pp.peer_mail) return;
   // ---- push the payload into every rank's mailbox (own included), then the flags
   __syncthreads();
-  const int q = (int)((pp.epoch + d) & 1);
+  const int q = (int)((pp.epoch + d) & (kRcwSets - 1));
   for (int g = 0; g < G; ++g) {
     double *dst = pp.peer_mail[g] + rcw_mail_slot(q, rank, i, G, pp.max_tasks);
     for (int e = threadIdx.x; e < kRcwPayload; e += kBig) dst[e] = pay[e];
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(kBig) rcw_owner_kernel(const T *A, int n, int6
   __threadfence_system();  // my stores are performed system-wide before I am counted as done
   __syncthreads();
   __shared__ int last;
-  int *counter = reinterpret_cast<int *>(reinterpret_cast<long long *>(pp.mail + rcw_mail_flags(G, pp.max_tasks)) + 2 * G);
+  int *counter = reinterpret_cast<int *>(reinterpret_cast<long long *>(pp.mail + rcw_mail_flags(G, pp.max_tasks)) + kRcwSets * G);
   if (threadIdx.x == 0) {
     const int done = atomicAdd(counter, 1);
     last = (done == count - 1);
@@ -366,7 +369,8 @@ __global__ void __launch_bounds__(kBig) rcw_owner_kernel(const T *A, int n, int6
 template <typename T, int NT>
 __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, int64_t ld, int G, int rank, RcWave wv,
                                                        int d, int Jlo, int max_tasks, const double *pay_all,
-                                                       T *V_out, int64_t ldv, RcwP2P pp, int32_t *status) {
+                                                       T *V_out, int64_t ldv, RcwP2P pp, int rows_mode,
+                                                       int32_t *status) {
   __shared__ __align__(16) double cp[kPanel];    // p_k
   __shared__ __align__(16) double2 ccs[kPanel];  // (c_k, sigma_k): one 16-byte load per column
   __shared__ __align__(16) T tile[NT * kPanel];
@@ -375,20 +379,37 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
   const int J = Jlo + (int)blockIdx.y, u = d - J;
   const double *pay = pay_all + ((int64_t)(J % G) * max_tasks + blockIdx.y / G) * kRcwPayload;
   const int base = J * kBig;
+  // Which local rows does this CTA take?  rows_mode 0: all rows below the panel's top (blockIdx.x = NT
+  // consecutive local rows).  Look-ahead split: 1 = HEAD, only the two 256-row blocks J and J+1 (what
+  // the owner kernel of the next step needs; blockIdx.x < 2 * 256 / NT), 2 = BULK, blocks >= J+2.
+  int l0 = blockIdx.x * NT;
+  bool have_rows = l0 < m_loc;
+  if (rows_mode == 1) {
+    constexpr int per = kRcBlock / NT;  // CTAs per 256-row block
+    const int B = J + (int)blockIdx.x / per;
+    have_rows = blockIdx.x < 2 * per && B % G == rank && (int64_t)B * kRcBlock < n;
+    l0 = (B / G) * kRcBlock + ((int)blockIdx.x % per) * NT;
+    have_rows = have_rows && l0 < m_loc;
+  }
+  int64_t g0 = 0;
+  int rows = 0;
+  if (have_rows) {
+    g0 = rc_global_row(l0, G, rank);
+    rows = min(NT, m_loc - l0);
+    if (g0 + rows > n) rows = (int)max((int64_t)0, (int64_t)n - g0);
+    // entirely above the panel (or, for the bulk, not below the head)?
+    have_rows = rows > 0 && g0 + rows > (rows_mode == 2 ? base + 2 * kRcBlock : base);
+  }
+  // CTA x = 0 of every task also unpacks: {t, S} for the next panel of update u (modes 0, 1) and the
+  // scratch vector for the caller (modes 0, 2)
+  const bool unpack = blockIdx.x == 0;
+  if (!have_rows && !unpack) return;
   if (pp.peer_mail) {
-    // P2P mode: the payload arrives in my mailbox; CTAs with nothing to do leave without waiting, except
-    // (0, 0) which waits for the flags of ALL ranks (the one-step bound on how far ranks drift apart)
-    const int l0e = blockIdx.x * NT;
-    bool work = blockIdx.x == 0;
-    if (!work && l0e < m_loc) {
-      const int64_t g0e = rc_global_row(l0e, G, rank);
-      const int64_t rows_e = min((int64_t)min(NT, m_loc - l0e), (int64_t)n - g0e);
-      work = rows_e > 0 && g0e + rows_e > base;
-    }
-    if (!work) return;
-    const int q = (int)((pp.epoch + d) & 1);
+    // P2P mode: the payload arrives in my mailbox.  CTA (0, 0) of the head (or of the unsplit kernel)
+    // waits for the flags of ALL ranks -- the one-step bound on how far ranks drift apart.
+    const int q = (int)((pp.epoch + d) & (kRcwSets - 1));
     const long long *flags = reinterpret_cast<const long long *>(pp.mail + rcw_mail_flags(G, max_tasks)) + q * G;
-    if (blockIdx.x == 0 && blockIdx.y == 0) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && rows_mode != 2) {
       if (tid < G) rcw_wait_flag(flags + tid, pp.epoch + d + 1, status);
     } else if (tid == 0) {
       rcw_wait_flag(flags + J % G, pp.epoch + d + 1, status);
@@ -396,18 +417,13 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
     __syncthreads();
     pay = pp.mail + rcw_mail_slot(q, J % G, blockIdx.y / G, G, max_tasks);
   }
-  if (blockIdx.x == 0) {  // unpack what the next panel of update u and the caller need
-    if (tid < 2) wv.scal[u * 8 + tid] = __ldcg(pay + 5 * kBig + tid);
-    if (V_out)
+  if (unpack) {
+    if (rows_mode != 2 && tid < 2) wv.scal[u * 8 + tid] = __ldcg(pay + 5 * kBig + tid);
+    if (rows_mode != 1 && V_out)
       for (int k = tid; k < kBig; k += NT)
         if (base + k < n) V_out[(int64_t)u * ldv + base + k] = (T)__ldcg(pay + 4 * kBig + k);
   }
-  const int l0 = blockIdx.x * NT;
-  if (l0 >= m_loc) return;
-  const int64_t g0 = rc_global_row(l0, G, rank);
-  int rows = min(NT, m_loc - l0);
-  if (g0 + rows > n) rows = (int)max((int64_t)0, (int64_t)n - g0);
-  if (rows <= 0 || g0 + rows <= base) return;  // entirely above the panel
+  if (!have_rows) return;
   const int r0 = (int)g0;
   T *L = A + ((int64_t)l0 - g0) * ld;  // so that L[R * ld + c] addresses global row R
   const int R = r0 + tid;

@@ -225,7 +225,7 @@ class _CudaRowCyclicBackend:
             f = getattr(lib, f"chub_rcw_owner_{suf}")
             f.restype, f.argtypes = ci, [vp, i64, i64, ci, ci, i64, i64, vp, vp, vp, vp]
             f = getattr(lib, f"chub_rcw_apply_{suf}")
-            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, i64, i64, vp, vp, vp, i64, vp, vp]
+            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, i64, i64, vp, vp, vp, i64, ci, vp, vp]
         K, dev = int(V.shape[0]), self.A.device
         self.K, self.V_out = K, V_out
         need = int(lib.chub_rcw_workspace_bytes(self.n, K, self.world))
@@ -263,7 +263,7 @@ class _CudaRowCyclicBackend:
             f = getattr(lib, f"chub_rcw_owner_p2p_{suf}")
             f.restype, f.argtypes = ci, [vp, i64, i64, ci, ci, i64, i64, vp, vp, vp, vp, i64, vp, vp]
             f = getattr(lib, f"chub_rcw_apply_p2p_{suf}")
-            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, i64, i64, vp, vp, vp, vp, i64, i64, vp, vp]
+            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, i64, i64, vp, vp, vp, vp, i64, i64, ci, vp, vp]
         ok = os.environ.get("CHUB_RC_P2P", "1") != "0"
         ptrs = [0] * self.world
         if ok:
@@ -307,14 +307,21 @@ class _CudaRowCyclicBackend:
             self.status.data_ptr(), self._stream())
         _lib.check(rc, "chub_rcw_owner_p2p")
 
-    def wave_apply_p2p(self, d):
+    def wave_apply_p2p(self, d, rows_mode=0):
         from . import _lib
 
         rc = getattr(self.lib, f"chub_rcw_apply_p2p_{self.suf}")(
             self.A.data_ptr(), self.A.shape[0], self.n, self.A.shape[1], self.world, self.rank, self.K, d,
             self.wave_ws.data_ptr(), self.peer_table.data_ptr(), self.mailbox, self.V_out.data_ptr(),
-            self.V_out.stride(0), self.epoch, self.status.data_ptr(), self._stream())
+            self.V_out.stride(0), self.epoch, rows_mode, self.status.data_ptr(), self._stream())
         _lib.check(rc, "chub_rcw_apply_p2p")
+
+    def lookahead_streams(self):
+        """(head, bulk): a high-priority stream for owner + head kernels and one for the bulk of the trail."""
+        if getattr(self, "_la_streams", None) is None:
+            dev = self.A.device
+            self._la_streams = (self.torch.cuda.Stream(device=dev, priority=-1), self.torch.cuda.Stream(device=dev))
+        return self._la_streams
 
     def wave_end_p2p(self, steps):
         """Advance the epoch; one status read (a peer that never arrived trips the device watchdog)."""
@@ -331,13 +338,13 @@ class _CudaRowCyclicBackend:
             self.wave_ws.data_ptr(), pay_mine.data_ptr(), self.status.data_ptr(), self._stream())
         _lib.check(rc, "chub_rcw_owner")
 
-    def wave_apply(self, d, pay_all):
+    def wave_apply(self, d, pay_all, rows_mode=0):
         from . import _lib
 
         rc = getattr(self.lib, f"chub_rcw_apply_{self.suf}")(
             self.A.data_ptr(), self.A.shape[0], self.n, self.A.shape[1], self.world, self.rank, self.K, d,
             self.wave_ws.data_ptr(), pay_all.data_ptr(), self.V_out.data_ptr(), self.V_out.stride(0),
-            self.status.data_ptr(), self._stream())
+            rows_mode, self.status.data_ptr(), self._stream())
         _lib.check(rc, "chub_rcw_apply")
 
 
@@ -470,7 +477,7 @@ class RowCyclicFactor:
             raise np.linalg.LinAlgError("The downdated matrix is not positive definite.")
         return v_out
 
-    def update_many(self, V, check_diag: bool = True, p2p=None):
+    def update_many(self, V, check_diag: bool = True, p2p=None, lookahead=None):
         """Apply the K successive rank-1 updates ``V[0], V[1], ...`` (``V``: ``(K, n)``, identical on
         every rank) in place -- the same result as K calls of ``update``, scheduled as a wavefront.
 
@@ -483,7 +490,9 @@ class RowCyclicFactor:
         finds a zero on the input diagonal.
 
         ``p2p``: None = exchange over NVLink peer memory when every rank can map every peer's mailbox
-        (one node, cudaIpc), else NCCL all-gather; False = NCCL; True = peer memory or raise."""
+        (one node, cudaIpc), else NCCL all-gather; False = NCCL; True = peer memory or raise.
+        ``lookahead``: None = split every step's trail into head and bulk on two streams when there is
+        no collective in the loop (peer-memory exchange or a single rank) and K > 1; False = one stream."""
         import numpy as np
         import torch
         import torch.distributed as dist
@@ -508,7 +517,58 @@ class RowCyclicFactor:
             if int(st.item()) == 1:
                 raise np.linalg.LinAlgError("The given Cholesky factor `L` contains zeros on its diagonal")
         steps = K + (self.n + RC_BLOCK - 1) // RC_BLOCK - 1
-        if multi and p2p is not False and hasattr(be, "p2p_ready") and be.p2p_ready(self.group):
+        use_p2p = multi and p2p is not False and hasattr(be, "p2p_ready") and be.p2p_ready(self.group)
+        if lookahead is None:
+            lookahead = K > 1
+        if (use_p2p or not multi) and lookahead and hasattr(be, "lookahead_streams"):
+            # Look-ahead split (no collective on this path, so the steps need no host synchronisation):
+            # the owner kernel of step d+1 depends only on the HEAD of step d's trail -- the two 256-row
+            # blocks J, J+1 of every task -- so owner + head run on a high-priority stream while the
+            # BULK of step d (blocks >= J+2) streams on a second one.  Dependencies across the streams:
+            # head(d+1) reads the residual of block J+2 that bulk(d) wrote (event); bulk(d+1) needs only
+            # bulk(d) (stream order) and the payloads of step d+1 (flags in the mailbox / event).
+            # bulk(d) may still read its payloads while those of step d+2 arrive -- never those of
+            # step d+3, because head(d+1) waits for bulk(d) before this rank's owner(d+2) can raise the
+            # flags the other ranks' step d+3 depends on: four payload sets (global step & 3) suffice.
+            cur = torch.cuda.current_stream(self.A.device)
+            s_head, s_bulk = be.lookahead_streams()
+            start = torch.cuda.Event()
+            start.record(cur)
+            s_head.wait_event(start)
+            s_bulk.wait_event(start)
+            ev_bulk = [torch.cuda.Event(), torch.cuda.Event()]
+            ev_owner = [torch.cuda.Event(), torch.cuda.Event()]
+            # single rank: the payloads of step d are still read by bulk(d) while owner(d+1) writes -> two buffers
+            pay2 = [pay_mine, torch.empty_like(pay_mine)]
+            for d in range(steps):
+                with torch.cuda.stream(s_head):
+                    if use_p2p:
+                        be.wave_owner_p2p(d, pay_mine)
+                    else:
+                        be.wave_owner(d, pay2[d % 2])
+                        ev_owner[d % 2].record(s_head)
+                    if d > 0:
+                        s_head.wait_event(ev_bulk[(d - 1) % 2])
+                    if use_p2p:
+                        be.wave_apply_p2p(d, 1)
+                    else:
+                        be.wave_apply(d, pay2[d % 2], 1)
+                with torch.cuda.stream(s_bulk):
+                    if use_p2p:
+                        be.wave_apply_p2p(d, 2)
+                    else:
+                        s_bulk.wait_event(ev_owner[d % 2])
+                        be.wave_apply(d, pay2[d % 2], 2)
+                    ev_bulk[d % 2].record(s_bulk)
+            done_h, done_b = torch.cuda.Event(), torch.cuda.Event()
+            done_h.record(s_head)
+            done_b.record(s_bulk)
+            cur.wait_event(done_h)
+            cur.wait_event(done_b)
+            if use_p2p:
+                be.wave_end_p2p(steps)
+            return V_out
+        if use_p2p:
             # exchange over NVLink peer memory: the owner kernel stores the coefficients into every
             # peer's mailbox, the trail kernel waits for them there -- 2 launches per step, no collective
             for d in range(steps):

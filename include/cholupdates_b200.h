@@ -175,7 +175,11 @@ int chub_rc_dd_finish_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int
  *      (G * max_tasks slots, rank-major), then chub_rcw_apply_* for all tasks of the step on the local
  *      rows: K + ceil(n/256) - 1 exchanges instead of K * ceil(n/256).  V / V_out: K vectors of n
  *      elements, leading dimension ldv (V_out may be NULL; it receives rotg's z_k, as v does in the
- *      reference, .pyx:101,152).  With G == 1 pay_all == pay_mine and no exchange is needed. */
+ *      reference, .pyx:101,152).  With G == 1 pay_all == pay_mine and no exchange is needed.
+ *      rows_mode of the apply calls: 0 = all local rows of every task; look-ahead split: 1 = only the
+ *      two 256-row blocks J, J+1 of every task (all that the owner call of step d+1 depends on),
+ *      2 = the blocks below.  Mode 2 of step d may run on a second stream concurrently with the owner
+ *      and mode-1 calls of step d+1; the mode-1 call of step d+1 must wait for mode 2 of step d. */
 int chub_rcw_payload_doubles(void);
 int chub_rcw_max_tasks(int64_t n, int64_t K, int G);
 size_t chub_rcw_workspace_bytes(int64_t n, int64_t K, int G);
@@ -188,11 +192,11 @@ int chub_rcw_owner_f64(void *A_loc, int64_t n, int64_t ld, int G, int rank, int6
 int chub_rcw_owner_f32(void *A_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
                        void *workspace, double *pay_mine, int32_t *status, void *stream);
 int chub_rcw_apply_f64(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
-                       void *workspace, const double *pay_all, void *V_out, int64_t ldv, int32_t *status,
-                       void *stream);
+                       void *workspace, const double *pay_all, void *V_out, int64_t ldv, int rows_mode,
+                       int32_t *status, void *stream);
 int chub_rcw_apply_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
-                       void *workspace, const double *pay_all, void *V_out, int64_t ldv, int32_t *status,
-                       void *stream);
+                       void *workspace, const double *pay_all, void *V_out, int64_t ldv, int rows_mode,
+                       int32_t *status, void *stream);
 
 /* ---- the same wavefront with the exchange over NVLink peer memory instead of a collective
  *      (one process per GPU).  Every rank allocates a mailbox (chub_p2p_alloc of
@@ -218,10 +222,10 @@ int chub_rcw_owner_p2p_f32(void *A_loc, int64_t n, int64_t ld, int G, int rank, 
                            int64_t epoch, int32_t *status, void *stream);
 int chub_rcw_apply_p2p_f64(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K,
                            int64_t d, void *workspace, const void *peer_table, void *mailbox, void *V_out,
-                           int64_t ldv, int64_t epoch, int32_t *status, void *stream);
+                           int64_t ldv, int64_t epoch, int rows_mode, int32_t *status, void *stream);
 int chub_rcw_apply_p2p_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K,
                            int64_t d, void *workspace, const void *peer_table, void *mailbox, void *V_out,
-                           int64_t ldv, int64_t epoch, int32_t *status, void *stream);
+                           int64_t ldv, int64_t epoch, int rows_mode, int32_t *status, void *stream);
 
 /* ---- tuning / introspection (bench.py and tests) */
 /* Force a kernel path: 0 = automatic, 1 = single-CTA kernels only, 2 = panel
