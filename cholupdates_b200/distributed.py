@@ -546,7 +546,7 @@ class RowCyclicFactor:
                         be.wave_owner_p2p(d, pay_mine)
                     else:
                         be.wave_owner(d, pay2[d % 2])
-                        ev_owner[d % 2].record(s_head)
+                    ev_owner[d % 2].record(s_head)
                     if d > 0:
                         s_head.wait_event(ev_bulk[(d - 1) % 2])
                     if use_p2p:
@@ -554,10 +554,14 @@ class RowCyclicFactor:
                     else:
                         be.wave_apply(d, pay2[d % 2], 1)
                 with torch.cuda.stream(s_bulk):
+                    # bulk(d) never starts before this rank's own owner(d) has run.  Single rank: that is
+                    # where the payloads come from.  Peer memory: a bulk kernel whose CTAs spin on a
+                    # peer's flag may fill every SM; if it could get ahead of its own head stream, two
+                    # ranks could starve each other's owner kernels (seen as a watchdog trip at n = 32768).
+                    s_bulk.wait_event(ev_owner[d % 2])
                     if use_p2p:
                         be.wave_apply_p2p(d, 2)
                     else:
-                        s_bulk.wait_event(ev_owner[d % 2])
                         be.wave_apply(d, pay2[d % 2], 2)
                     ev_bulk[d % 2].record(s_bulk)
             done_h, done_b = torch.cuda.Event(), torch.cuda.Event()
