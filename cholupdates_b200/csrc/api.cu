@@ -368,7 +368,8 @@ inline void rcw_span(int64_t n, int64_t K, int64_t d, int *Jlo, int *Jhi) {
 }
 template <typename T>
 int rcw_owner(void *A, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d, void *workspace,
-              double *pay_mine, const void *peer_table, void *mailbox, int64_t epoch, int32_t *status, void *stream) {
+              double *pay_mine, const void *peer_table, void *mailbox, int64_t epoch, int solve_only,
+              int32_t *status, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   RcWave wv = rcw_carve(workspace, n, K, G);
   RcwP2P pp{(double *const *)peer_table, (double *)mailbox, (long long)epoch, rcw_max_tasks(n, K, G)};
@@ -378,16 +379,17 @@ int rcw_owner(void *A, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_
   const int count = Jfirst > Jhi ? 0 : (Jhi - Jfirst) / G + 1;
   if (count == 0 && !peer_table) return 0;
   // (P2P mode: a rank without a task at this step still raises its flags -- one CTA)
-  CK(cudaFuncSetAttribute(rcw_owner_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRcwOwnerSmem));
-  rcw_owner_kernel<T><<<count > 0 ? count : 1, kBig, kRcwOwnerSmem, st>>>((const T *)A, (int)n, ld, G, rank, wv, (int)d,
-                                                                          Jfirst, pay_mine, pp, count, status);
+  auto kern = solve_only ? rcw_owner_kernel<T, false> : rcw_owner_kernel<T, true>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRcwOwnerSmem));
+  kern<<<count > 0 ? count : 1, kBig, kRcwOwnerSmem, st>>>((const T *)A, (int)n, ld, G, rank, wv, (int)d, Jfirst,
+                                                           pay_mine, pp, count, status);
   LAUNCHED();
   return 0;
 }
 template <typename T>
 int rcw_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
               void *workspace, const double *pay_all, const void *peer_table, void *mailbox, void *V_out,
-              int64_t ldv, int64_t epoch, int rows_mode, int32_t *status, void *stream) {
+              int64_t ldv, int64_t epoch, int rows_mode, void *solve_ws, int32_t *status, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   RcWave wv = rcw_carve(workspace, n, K, G);
   RcwP2P pp{(double *const *)peer_table, (double *)mailbox, (long long)epoch, rcw_max_tasks(n, K, G)};
@@ -398,18 +400,30 @@ int rcw_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, in
   if (const char *e = getenv("CHUB_RCW_NT")) nt = atoi(e);
   if (nt != 32 && nt != 64) nt = 128;
   if (rows_mode < 0 || rows_mode > 2) return (int)cudaErrorInvalidValue;
+  // solve_ws != NULL: forward substitution only (downdate); p and the diagonal signs go into its p / dn
+  double *p_out = nullptr, *dn_out = nullptr;
+  if (solve_ws) {
+    LargeWs lw = large_ws_carve(solve_ws, n);
+    p_out = lw.p;
+    dn_out = lw.dn;
+  }
   // head of the look-ahead split: only the CTAs of the two 256-row blocks J and J+1 of every task
   const unsigned gx = rows_mode == 1 ? (unsigned)(2 * kRcBlock / nt) : (unsigned)((m_loc > 0 ? m_loc + nt - 1 : nt) / nt);
   dim3 grid(gx, (unsigned)(Jhi - Jlo + 1));
-  if (nt == 32)
-    rcw_trail_kernel<T, 32><<<grid, 32, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, wv, (int)d, Jlo,
-                                                 pp.max_tasks, pay_all, (T *)V_out, ldv, pp, rows_mode, status);
-  else if (nt == 64)
-    rcw_trail_kernel<T, 64><<<grid, 64, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, wv, (int)d, Jlo,
-                                                 pp.max_tasks, pay_all, (T *)V_out, ldv, pp, rows_mode, status);
-  else
-    rcw_trail_kernel<T, 128><<<grid, 128, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, wv, (int)d, Jlo,
-                                                   pp.max_tasks, pay_all, (T *)V_out, ldv, pp, rows_mode, status);
+#define CHUB_TRAIL_GO(NTV, UPD)                                                                                      \
+  rcw_trail_kernel<T, NTV, UPD><<<grid, NTV, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, wv, (int)d, Jlo,      \
+                                                      pp.max_tasks, pay_all, (T *)V_out, ldv, pp, rows_mode, p_out,  \
+                                                      dn_out, status)
+  if (solve_ws) {
+    if (nt == 32) CHUB_TRAIL_GO(32, false);
+    else if (nt == 64) CHUB_TRAIL_GO(64, false);
+    else CHUB_TRAIL_GO(128, false);
+  } else {
+    if (nt == 32) CHUB_TRAIL_GO(32, true);
+    else if (nt == 64) CHUB_TRAIL_GO(64, true);
+    else CHUB_TRAIL_GO(128, true);
+  }
+#undef CHUB_TRAIL_GO
   LAUNCHED();
   return 0;
 }
@@ -561,27 +575,30 @@ DEFINE_RC_DD(f32, float)
     return rcw_prepare<T>(A, m_loc, n, ld, G, rank, V, K, ldv, workspace, flags, status, stream);                  \
   }                                                                                                                \
   int chub_rcw_owner_##SUF(void *A, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d, void *workspace, \
-                           double *pay_mine, int32_t *status, void *stream) {                                      \
-    return rcw_owner<T>(A, n, ld, G, rank, K, d, workspace, pay_mine, nullptr, nullptr, 0, status, stream);        \
+                           double *pay_mine, int solve_only, int32_t *status, void *stream) {                      \
+    return rcw_owner<T>(A, n, ld, G, rank, K, d, workspace, pay_mine, nullptr, nullptr, 0, solve_only, status,     \
+                        stream);                                                                                   \
   }                                                                                                                \
   int chub_rcw_apply_##SUF(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,   \
                            void *workspace, const double *pay_all, void *V_out, int64_t ldv, int rows_mode,        \
-                           int32_t *status, void *stream) {                                                        \
+                           void *solve_ws, int32_t *status, void *stream) {                                        \
     return rcw_apply<T>(A, m_loc, n, ld, G, rank, K, d, workspace, pay_all, nullptr, nullptr, V_out, ldv, 0,       \
-                        rows_mode, status, stream);                                                                \
+                        rows_mode, solve_ws, status, stream);                                                      \
   }                                                                                                                \
   int chub_rcw_owner_p2p_##SUF(void *A, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,              \
                                void *workspace, double *pay_mine, const void *peer_table, void *mailbox,           \
-                               int64_t epoch, int32_t *status, void *stream) {                                     \
+                               int64_t epoch, int solve_only, int32_t *status, void *stream) {                     \
     if (!peer_table || !mailbox) return (int)cudaErrorInvalidValue;                                                \
-    return rcw_owner<T>(A, n, ld, G, rank, K, d, workspace, pay_mine, peer_table, mailbox, epoch, status, stream); \
+    return rcw_owner<T>(A, n, ld, G, rank, K, d, workspace, pay_mine, peer_table, mailbox, epoch, solve_only,      \
+                        status, stream);                                                                           \
   }                                                                                                                \
   int chub_rcw_apply_p2p_##SUF(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K,          \
                                int64_t d, void *workspace, const void *peer_table, void *mailbox, void *V_out,     \
-                               int64_t ldv, int64_t epoch, int rows_mode, int32_t *status, void *stream) {         \
+                               int64_t ldv, int64_t epoch, int rows_mode, void *solve_ws, int32_t *status,         \
+                               void *stream) {                                                                     \
     if (!peer_table || !mailbox) return (int)cudaErrorInvalidValue;                                                \
     return rcw_apply<T>(A, m_loc, n, ld, G, rank, K, d, workspace, (const double *)mailbox, peer_table, mailbox,   \
-                        V_out, ldv, epoch, rows_mode, status, stream);                                             \
+                        V_out, ldv, epoch, rows_mode, solve_ws, status, stream);                                   \
   }
 DEFINE_RCW(f64, double)
 DEFINE_RCW(f32, float)

@@ -309,7 +309,9 @@ __global__ void rcw_prepare_kernel(const T *A, int m_loc, int n, int64_t ld, int
 // One CTA (256 threads) per task of this rank on anti-diagonal d: J = Jfirst + blockIdx.x * G,
 // u = d - J.  Writes the task's payload into pay_mine[blockIdx.x].
 // P2P mode (pp.peer_mail != nullptr): `count` = number of tasks (0: this CTA only raises the flags).
-template <typename T>
+// UPDATE = false: forward substitution only (the downdate's p = L^{-1} v): the payload carries p and the
+// signs of the panel's input diagonal entries (slot of L'_kk).
+template <typename T, bool UPDATE = true>
 __global__ void __launch_bounds__(kBig) rcw_owner_kernel(const T *A, int n, int64_t ld, int G, int rank, RcWave wv,
                                                          int d, int Jfirst, double *pay_mine, RcwP2P pp, int count,
                                                          int32_t *status) {
@@ -335,8 +337,12 @@ __global__ void __launch_bounds__(kBig) rcw_owner_kernel(const T *A, int n, int6
   }
   __syncthreads();
   double *pay = pay_mine + (int64_t)i * kRcwPayload;
-  chain_body<T, CHUB_ROW_MAJOR, true>(Lsh, n, ld, J, X, wv.W + (int64_t)u * wv.n_pad, pay, pay + kBig, pay + 2 * kBig,
-                                      pay + 3 * kBig, (T *)nullptr, pay + 4 * kBig, wv.scal + u * 8, pay + 5 * kBig);
+  chain_body<T, CHUB_ROW_MAJOR, UPDATE>(Lsh, n, ld, J, X, wv.W + (int64_t)u * wv.n_pad, pay, pay + kBig, pay + 2 * kBig,
+                                        pay + 3 * kBig, (T *)nullptr, pay + 4 * kBig, wv.scal + u * 8, pay + 5 * kBig);
+  if (!UPDATE) {
+    const int R = J * kBig + (int)threadIdx.x;
+    pay[3 * kBig + threadIdx.x] = (R < n && Lsh[(int64_t)R * ld + R] < T(0)) ? -1.0 : 1.0;
+  }
   if (!pp.peer_mail) return;
   // ---- push the payload into every rank's mailbox (own included), then the flags
   __syncthreads();
@@ -366,11 +372,14 @@ __global__ void __launch_bounds__(kBig) rcw_owner_kernel(const T *A, int n, int6
 // Trailing update for every task of anti-diagonal d: blockIdx.y = t <-> J = Jlo + t, u = d - J; its
 // payload sits in slot (J mod G) * max_tasks + t / G of the gathered buffer (the owner's tasks are
 // Jfirst, Jfirst + G, ... with Jfirst - Jlo < G).  blockIdx.x = NT consecutive local rows.
-template <typename T, int NT>
+// UPDATE = false: the read-only pass of the downdate's forward substitution (w <- w - L p on the rows
+// below the panel's diagonal block); the unpacking CTA stores p and the diagonal signs of the panel into
+// the n-vectors p_out / dn_out (what the rho^2 test and the sweep read) instead of {t, S} and V_out.
+template <typename T, int NT, bool UPDATE = true>
 __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, int64_t ld, int G, int rank, RcWave wv,
                                                        int d, int Jlo, int max_tasks, const double *pay_all,
                                                        T *V_out, int64_t ldv, RcwP2P pp, int rows_mode,
-                                                       int32_t *status) {
+                                                       double *p_out, double *dn_out, int32_t *status) {
   __shared__ __align__(16) double cp[kPanel];    // p_k
   __shared__ __align__(16) double2 ccs[kPanel];  // (c_k, sigma_k): one 16-byte load per column
   __shared__ __align__(16) T tile[NT * kPanel];
@@ -398,7 +407,7 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
     rows = min(NT, m_loc - l0);
     if (g0 + rows > n) rows = (int)max((int64_t)0, (int64_t)n - g0);
     // entirely above the panel (or, for the bulk, not below the head)?
-    have_rows = rows > 0 && g0 + rows > (rows_mode == 2 ? base + 2 * kRcBlock : base);
+    have_rows = rows > 0 && g0 + rows > (rows_mode == 2 ? base + 2 * kRcBlock : (UPDATE ? base : base + kRcBlock));
   }
   // CTA x = 0 of every task also unpacks: {t, S} for the next panel of update u (modes 0, 1) and the
   // scratch vector for the caller (modes 0, 2)
@@ -417,17 +426,23 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
     __syncthreads();
     pay = pp.mail + rcw_mail_slot(q, J % G, blockIdx.y / G, G, max_tasks);
   }
-  if (unpack) {
+  if (unpack && UPDATE) {
     if (rows_mode != 2 && tid < 2) wv.scal[u * 8 + tid] = __ldcg(pay + 5 * kBig + tid);
     if (rows_mode != 1 && V_out)
       for (int k = tid; k < kBig; k += NT)
         if (base + k < n) V_out[(int64_t)u * ldv + base + k] = (T)__ldcg(pay + 4 * kBig + k);
   }
+  if (unpack && !UPDATE && rows_mode != 1)
+    for (int k = tid; k < kBig; k += NT)
+      if (base + k < n) {
+        p_out[base + k] = __ldcg(pay + k);
+        dn_out[base + k] = __ldcg(pay + 3 * kBig + k);
+      }
   if (!have_rows) return;
   const int r0 = (int)g0;
   T *L = A + ((int64_t)l0 - g0) * ld;  // so that L[R * ld + c] addresses global row R
   const int R = r0 + tid;
-  const bool valid = tid < rows && R >= base;
+  const bool valid = tid < rows && R >= (UPDATE ? base : base + kRcBlock);
   double *wu = wv.W + (int64_t)u * wv.n_pad;
   double w = valid ? wu[R] : 0.0;
   const int cend = min(n, base + kBig);
@@ -438,7 +453,8 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
     if (tid < kPanel) {
       const int a = c0 - base + tid;
       cp[tid] = tid < bw ? __ldcg(pay + a) : 0.0;  // (L2 loads: in P2P mode other GPUs wrote the payload)
-      ccs[tid] = make_double2(tid < bw ? __ldcg(pay + kBig + a) : 1.0, tid < bw ? __ldcg(pay + 2 * kBig + a) : 0.0);
+      if (UPDATE)
+        ccs[tid] = make_double2(tid < bw ? __ldcg(pay + kBig + a) : 1.0, tid < bw ? __ldcg(pay + 2 * kBig + a) : 0.0);
     }
     tile_load_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
     if (tid < rows && c0 + kPanel < cend) {  // next block column of my row -> L2 while this one is processed
@@ -455,13 +471,18 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
 #pragma unroll
         for (int k = 0; k < kPanel; k += 2) {  // 3 coefficient loads of 16 bytes per 2 columns
           const double2 p2 = *reinterpret_cast<const double2 *>(cp + k);
-          const double2 q0 = ccs[k], q1 = ccs[k + 1];
           const double l0 = (double)trow[k ^ sw];
-          trow[k ^ sw] = (T)fma(q0.x, l0, q0.y * w);
-          w = fma(-l0, p2.x, w);
           const double l1 = (double)trow[(k + 1) ^ sw];
-          trow[(k + 1) ^ sw] = (T)fma(q1.x, l1, q1.y * w);
-          w = fma(-l1, p2.y, w);
+          if (UPDATE) {
+            const double2 q0 = ccs[k], q1 = ccs[k + 1];
+            trow[k ^ sw] = (T)fma(q0.x, l0, q0.y * w);
+            w = fma(-l0, p2.x, w);
+            trow[(k + 1) ^ sw] = (T)fma(q1.x, l1, q1.y * w);
+            w = fma(-l1, p2.y, w);
+          } else {
+            w = fma(-l0, p2.x, w);
+            w = fma(-l1, p2.y, w);
+          }
         }
       }
     } else if (valid) {
@@ -470,15 +491,17 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
         if (k < bw && c0 + k < R) {
           const int o = tile_off(tid, k);
           const double lo = (double)tile[o];
-          tile[o] = (T)(ccs[k].x * lo + ccs[k].y * w);
+          if (UPDATE) tile[o] = (T)(ccs[k].x * lo + ccs[k].y * w);
           w -= lo * cp[k];
         }
       }
-      if (R >= c0 && R < c0 + bw) tile[tile_off(tid, R - c0)] = (T)__ldcg(pay + 3 * kBig + R - base);
+      if (UPDATE && R >= c0 && R < c0 + bw) tile[tile_off(tid, R - c0)] = (T)__ldcg(pay + 3 * kBig + R - base);
     }
-    __syncthreads();
-    // rows above the panel inside this CTA (R < base) are loaded but stored back unchanged
-    tile_store_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
+    if (UPDATE) {
+      __syncthreads();
+      // rows above the panel inside this CTA (R < base) are loaded but stored back unchanged
+      tile_store_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
+    }
   }
   if (valid && R >= cend) wu[R] = w;
 }

@@ -223,9 +223,9 @@ class _CudaRowCyclicBackend:
             f = getattr(lib, f"chub_rcw_prepare_{suf}")
             f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, vp, i64, i64, vp, ci, vp, vp]
             f = getattr(lib, f"chub_rcw_owner_{suf}")
-            f.restype, f.argtypes = ci, [vp, i64, i64, ci, ci, i64, i64, vp, vp, vp, vp]
+            f.restype, f.argtypes = ci, [vp, i64, i64, ci, ci, i64, i64, vp, vp, ci, vp, vp]
             f = getattr(lib, f"chub_rcw_apply_{suf}")
-            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, i64, i64, vp, vp, vp, i64, ci, vp, vp]
+            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, i64, i64, vp, vp, vp, i64, ci, vp, vp, vp]
         K, dev = int(V.shape[0]), self.A.device
         self.K, self.V_out = K, V_out
         need = int(lib.chub_rcw_workspace_bytes(self.n, K, self.world))
@@ -261,9 +261,9 @@ class _CudaRowCyclicBackend:
         lib.chub_p2p_import.restype, lib.chub_p2p_import.argtypes = ci, [vp, ctypes.POINTER(vp)]
         for suf in ("f64", "f32"):
             f = getattr(lib, f"chub_rcw_owner_p2p_{suf}")
-            f.restype, f.argtypes = ci, [vp, i64, i64, ci, ci, i64, i64, vp, vp, vp, vp, i64, vp, vp]
+            f.restype, f.argtypes = ci, [vp, i64, i64, ci, ci, i64, i64, vp, vp, vp, vp, i64, ci, vp, vp]
             f = getattr(lib, f"chub_rcw_apply_p2p_{suf}")
-            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, i64, i64, vp, vp, vp, vp, i64, i64, ci, vp, vp]
+            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, i64, i64, vp, vp, vp, vp, i64, i64, ci, vp, vp, vp]
         ok = os.environ.get("CHUB_RC_P2P", "1") != "0"
         ptrs = [0] * self.world
         if ok:
@@ -298,22 +298,23 @@ class _CudaRowCyclicBackend:
         self._p2p_state = ok
         return ok
 
-    def wave_owner_p2p(self, d, pay_mine):
+    def wave_owner_p2p(self, d, pay_mine, solve_only=False):
         from . import _lib
 
         rc = getattr(self.lib, f"chub_rcw_owner_p2p_{self.suf}")(
             self.A.data_ptr(), self.n, self.A.shape[1], self.world, self.rank, self.K, d,
             self.wave_ws.data_ptr(), pay_mine.data_ptr(), self.peer_table.data_ptr(), self.mailbox, self.epoch,
-            self.status.data_ptr(), self._stream())
+            1 if solve_only else 0, self.status.data_ptr(), self._stream())
         _lib.check(rc, "chub_rcw_owner_p2p")
 
-    def wave_apply_p2p(self, d, rows_mode=0):
+    def wave_apply_p2p(self, d, rows_mode=0, solve_only=False):
         from . import _lib
 
         rc = getattr(self.lib, f"chub_rcw_apply_p2p_{self.suf}")(
             self.A.data_ptr(), self.A.shape[0], self.n, self.A.shape[1], self.world, self.rank, self.K, d,
             self.wave_ws.data_ptr(), self.peer_table.data_ptr(), self.mailbox, self.V_out.data_ptr(),
-            self.V_out.stride(0), self.epoch, rows_mode, self.status.data_ptr(), self._stream())
+            self.V_out.stride(0), self.epoch, rows_mode, self.ws.data_ptr() if solve_only else None,
+            self.status.data_ptr(), self._stream())
         _lib.check(rc, "chub_rcw_apply_p2p")
 
     def lookahead_streams(self):
@@ -330,22 +331,25 @@ class _CudaRowCyclicBackend:
             raise RuntimeError("cholupdates_b200: a peer did not deliver its panel coefficients "
                                "(device watchdog, CHUB_STATUS_INTERNAL)")
 
-    def wave_owner(self, d, pay_mine):
+    def wave_owner(self, d, pay_mine, solve_only=False):
         from . import _lib
 
         rc = getattr(self.lib, f"chub_rcw_owner_{self.suf}")(
             self.A.data_ptr(), self.n, self.A.shape[1], self.world, self.rank, self.K, d,
-            self.wave_ws.data_ptr(), pay_mine.data_ptr(), self.status.data_ptr(), self._stream())
+            self.wave_ws.data_ptr(), pay_mine.data_ptr(), 1 if solve_only else 0, self.status.data_ptr(),
+            self._stream())
         _lib.check(rc, "chub_rcw_owner")
 
-    def wave_apply(self, d, pay_all, rows_mode=0):
+    def wave_apply(self, d, pay_all, rows_mode=0, solve_only=False):
         from . import _lib
 
         rc = getattr(self.lib, f"chub_rcw_apply_{self.suf}")(
             self.A.data_ptr(), self.A.shape[0], self.n, self.A.shape[1], self.world, self.rank, self.K, d,
             self.wave_ws.data_ptr(), pay_all.data_ptr(), self.V_out.data_ptr(), self.V_out.stride(0),
-            rows_mode, self.status.data_ptr(), self._stream())
+            rows_mode, self.ws.data_ptr() if solve_only else None, self.status.data_ptr(), self._stream())
         _lib.check(rc, "chub_rcw_apply")
+
+    supports_wave_solve = True  # the forward substitution of the downdate can run on the wavefront kernels
 
 
 def _check_vector_like(A, x, what: str) -> None:
@@ -434,7 +438,7 @@ class RowCyclicFactor:
             be.panel_apply(J, owner == self.rank, payload)
         return v_out
 
-    def downdate(self, v, check_diag: bool = True):
+    def downdate(self, v, check_diag: bool = True, per_panel=None):
         """In-place rank-1 downdate ``L L^T - v v^T`` of the distributed factor (reference semantics:
         ``_seeger_impl_cython.pyx:160-330``).  The forward substitution ``p = L^{-1} v`` runs panel by
         panel (the owner of each diagonal block broadcasts the panel's ``p``; every rank updates the
@@ -442,7 +446,11 @@ class RowCyclicFactor:
         the reverse sweep touches only local rows -- no further exchange.  Returns the
         scratch vector (rotg's z_k; ``p`` if the result is not positive definite).  Raises
         ``numpy.linalg.LinAlgError`` on every rank, with the factor untouched, for a zero on the
-        diagonal (``check_diag``) or when the downdated matrix is not positive definite."""
+        diagonal (``check_diag``) or when the downdated matrix is not positive definite.
+
+        ``per_panel``: None = the forward substitution runs on the wavefront kernels (one owner kernel
+        and one read-only trail kernel per panel) when their exchange needs no collective (peer memory,
+        or a single rank), else per panel with an NCCL broadcast; True = always the latter."""
         import numpy as np
         import torch
         import torch.distributed as dist
@@ -457,6 +465,32 @@ class RowCyclicFactor:
         be = self.backend
         multi = self.world > 1 and dist.is_available() and dist.is_initialized()
         v_out = torch.zeros_like(v)
+        use_p2p = (multi and per_panel is not True and getattr(be, "supports_wave_solve", False)
+                   and be.p2p_ready(self.group))
+        if getattr(be, "supports_wave_solve", False) and per_panel is not True and (use_p2p or not multi):
+            # forward substitution on the wavefront kernels (K = 1, solve only): one owner kernel and one
+            # read-only trail kernel per panel, the panel's p exchanged over peer memory -- no collective
+            pay_mine, pay_all = be.wave_begin(v.reshape(1, -1), v_out.reshape(1, -1), check_diag)
+            be.v_out = v_out
+            if check_diag:
+                st = be.status_tensor()
+                if multi:
+                    dist.all_reduce(st, op=dist.ReduceOp.MAX, group=self.group)
+                if int(st.item()) == 1:
+                    raise np.linalg.LinAlgError("The given Cholesky factor `L` contains zeros on its diagonal")
+            steps = (self.n + RC_BLOCK - 1) // RC_BLOCK
+            for d in range(steps):
+                if use_p2p:
+                    be.wave_owner_p2p(d, pay_mine, solve_only=True)
+                    be.wave_apply_p2p(d, 0, solve_only=True)
+                else:
+                    be.wave_owner(d, pay_mine, solve_only=True)
+                    be.wave_apply(d, pay_all, 0, solve_only=True)
+            if use_p2p:
+                be.wave_end_p2p(steps)
+            if be.dd_finish() == 2:
+                raise np.linalg.LinAlgError("The downdated matrix is not positive definite.")
+            return v_out
         be.prepare(v, v_out, check_diag)
         if check_diag:
             st = be.status_tensor()

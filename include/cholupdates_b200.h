@@ -179,7 +179,11 @@ int chub_rc_dd_finish_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int
  *      rows_mode of the apply calls: 0 = all local rows of every task; look-ahead split: 1 = only the
  *      two 256-row blocks J, J+1 of every task (all that the owner call of step d+1 depends on),
  *      2 = the blocks below.  Mode 2 of step d may run on a second stream concurrently with the owner
- *      and mode-1 calls of step d+1; the mode-1 call of step d+1 must wait for mode 2 of step d. */
+ *      and mode-1 calls of step d+1; the mode-1 call of step d+1 must wait for mode 2 of step d.
+ *      Forward substitution only (the distributed downdate's p = L^{-1} v, K = 1): owner calls with
+ *      solve_only = 1, apply calls with solve_ws = the chub_workspace_bytes() workspace that
+ *      chub_rc_dd_finish will read (p and the signs of the input diagonal are stored there); A_loc
+ *      is not modified.  solve_ws = NULL / solve_only = 0: the update. */
 int chub_rcw_payload_doubles(void);
 int chub_rcw_max_tasks(int64_t n, int64_t K, int G);
 size_t chub_rcw_workspace_bytes(int64_t n, int64_t K, int G);
@@ -188,15 +192,15 @@ int chub_rcw_prepare_f64(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int 
 int chub_rcw_prepare_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, const void *V,
                          int64_t K, int64_t ldv, void *workspace, int flags, int32_t *status, void *stream);
 int chub_rcw_owner_f64(void *A_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
-                       void *workspace, double *pay_mine, int32_t *status, void *stream);
+                       void *workspace, double *pay_mine, int solve_only, int32_t *status, void *stream);
 int chub_rcw_owner_f32(void *A_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
-                       void *workspace, double *pay_mine, int32_t *status, void *stream);
+                       void *workspace, double *pay_mine, int solve_only, int32_t *status, void *stream);
 int chub_rcw_apply_f64(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
                        void *workspace, const double *pay_all, void *V_out, int64_t ldv, int rows_mode,
-                       int32_t *status, void *stream);
+                       void *solve_ws, int32_t *status, void *stream);
 int chub_rcw_apply_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
                        void *workspace, const double *pay_all, void *V_out, int64_t ldv, int rows_mode,
-                       int32_t *status, void *stream);
+                       void *solve_ws, int32_t *status, void *stream);
 
 /* ---- the same wavefront with the exchange over NVLink peer memory instead of a collective
  *      (one process per GPU).  Every rank allocates a mailbox (chub_p2p_alloc of
@@ -216,16 +220,18 @@ int chub_p2p_import(const void *handle64, void **peer_ptr);
 int chub_p2p_close(void *peer_ptr);
 int chub_rcw_owner_p2p_f64(void *A_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
                            void *workspace, double *pay_mine, const void *peer_table, void *mailbox,
-                           int64_t epoch, int32_t *status, void *stream);
+                           int64_t epoch, int solve_only, int32_t *status, void *stream);
 int chub_rcw_owner_p2p_f32(void *A_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
                            void *workspace, double *pay_mine, const void *peer_table, void *mailbox,
-                           int64_t epoch, int32_t *status, void *stream);
+                           int64_t epoch, int solve_only, int32_t *status, void *stream);
 int chub_rcw_apply_p2p_f64(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K,
                            int64_t d, void *workspace, const void *peer_table, void *mailbox, void *V_out,
-                           int64_t ldv, int64_t epoch, int rows_mode, int32_t *status, void *stream);
+                           int64_t ldv, int64_t epoch, int rows_mode, void *solve_ws, int32_t *status,
+                           void *stream);
 int chub_rcw_apply_p2p_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K,
                            int64_t d, void *workspace, const void *peer_table, void *mailbox, void *V_out,
-                           int64_t ldv, int64_t epoch, int rows_mode, int32_t *status, void *stream);
+                           int64_t ldv, int64_t epoch, int rows_mode, void *solve_ws, int32_t *status,
+                           void *stream);
 
 /* ---- tuning / introspection (bench.py and tests) */
 /* Force a kernel path: 0 = automatic, 1 = single-CTA kernels only, 2 = panel

@@ -87,9 +87,12 @@ def main():
     A = torch.from_numpy(np.ascontiguousarray(L[rows])).to(dev)
     vd = downdate_vector(L, 21)
     facd = RowCyclicFactor(A, n, rank, world)
-    facd.downdate(torch.from_numpy(vd.copy()).to(dev))
+    facd.downdate(torch.from_numpy(vd.copy()).to(dev))                      # wavefront kernels if peer memory
     L_ref = np.array(L, order="F")
     oracle.downdate(L_ref, vd.copy())
+    vd2 = downdate_vector(np.tril(L_ref), 23)
+    facd.downdate(torch.from_numpy(vd2.copy()).to(dev), per_panel=True)      # per panel + broadcast
+    oracle.downdate(L_ref, vd2.copy())
     got = np.where(lower, A.cpu().numpy(), 0.0)
     want = np.tril(L_ref)[rows]
     err = float(np.linalg.norm(got - want) / np.linalg.norm(want))
@@ -142,22 +145,24 @@ def main():
                   f"{per:.3f} ms/update, {bytes_upd / per / 1e6:.0f} GB/s aggregate "
                   f"({bytes_upd / per / 1e6 / world:.0f} GB/s per GPU)", flush=True)
     # one downdate (v = 0.5 * L u / |u| is always valid)
-    u = torch.randn(n, dtype=torch.float64, device=dev, generator=gv)
-    u = 0.5 * u / u.norm()
-    vloc = torch.zeros(n, dtype=torch.float64, device=dev)
-    vloc[rt] = A @ u  # the rows of L u this rank owns
-    dist.all_reduce(vloc)
-    torch.cuda.synchronize()
-    dist.barrier()
-    e0.record()
-    fac.downdate(vloc, check_diag=False)
-    e1.record()
-    dist.barrier()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        print(f"[rowcyclic downdate timing] n={n} world={world}: {float(ms.item()):.3f} ms per downdate", flush=True)
+    for per_panel in (True, None):
+        uu = torch.randn(n, dtype=torch.float64, device=dev, generator=gv)
+        uu = 0.5 * uu / uu.norm()
+        vloc = torch.zeros(n, dtype=torch.float64, device=dev)
+        vloc[rt] = A @ uu  # the rows of L u this rank owns
+        dist.all_reduce(vloc)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        fac.downdate(vloc, check_diag=False, per_panel=per_panel)
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            how = "forward substitution per panel + broadcast" if per_panel else "forward substitution on the wavefront kernels"
+            print(f"[rowcyclic downdate timing] n={n} world={world} {how}: {float(ms.item()):.3f} ms per downdate", flush=True)
 
     # wavefront: k_wave successive updates in one call (BASELINE.json configs[4]: 64)
     gv.manual_seed(8)

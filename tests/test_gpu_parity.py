@@ -399,10 +399,12 @@ def test_rowcyclic_wavefront_single_rank_matches_oracle(n, K, dtype):
     assert torch.equal(keep, Lz)
 
 
+@pytest.mark.parametrize("per_panel", [None, True])
 @pytest.mark.parametrize("n", [300, 1000, 2048])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_rowcyclic_downdate_single_rank_matches_oracle(n, dtype):
-    """Distributed downdate driver on one rank: panel-wise forward substitution, rho^2 test, local sweep."""
+def test_rowcyclic_downdate_single_rank_matches_oracle(n, dtype, per_panel):
+    """Distributed downdate driver on one rank: panel-wise forward substitution (on the wavefront kernels,
+    or per panel), rho^2 test, local sweep."""
     from cholupdates_b200.distributed import RowCyclicFactor
 
     L = synth_factor(n, 35).astype(dtype)
@@ -410,7 +412,7 @@ def test_rowcyclic_downdate_single_rank_matches_oracle(n, dtype):
     v = downdate_vector(L, 36)
     A = torch.from_numpy(L.copy()).cuda()
     A += torch.triu(torch.full_like(A, float("nan")), 1)
-    z = RowCyclicFactor(A, n).downdate(torch.from_numpy(v.copy()).cuda())
+    z = RowCyclicFactor(A, n).downdate(torch.from_numpy(v.copy()).cuda(), per_panel=per_panel)
     L_ref, z_ref = np.array(L, order="F"), v.copy()
     oracle.downdate(L_ref, z_ref)
     got = A.cpu().numpy()
@@ -422,7 +424,7 @@ def test_rowcyclic_downdate_single_rank_matches_oracle(n, dtype):
     keep = A.clone()
     bad = downdate_vector(np.tril(L_ref).astype(dtype), 37, norm_p=1.2)
     with pytest.raises(np.linalg.LinAlgError, match="not positive definite"):
-        RowCyclicFactor(A, n).downdate(torch.from_numpy(bad).cuda())
+        RowCyclicFactor(A, n).downdate(torch.from_numpy(bad).cuda(), per_panel=per_panel)
     assert torch.equal(torch.tril(keep), torch.tril(A))
 
 
