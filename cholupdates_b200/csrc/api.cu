@@ -361,20 +361,22 @@ int rcw_prepare(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, 
   return 0;
 }
 // tasks of anti-diagonal d: panels Jlo..Jhi (update u = d - J)
-inline void rcw_span(int64_t n, int64_t K, int64_t d, int *Jlo, int *Jhi) {
+inline void rcw_span(int64_t n, int64_t K, int64_t d, int *Jlo, int *Jhi) {  // K = updates, or groups when fused
   const int64_t nJ = rcw_panels(n);
   *Jlo = (int)(d - K + 1 > 0 ? d - K + 1 : 0);
   *Jhi = (int)(d < nJ - 1 ? d : nJ - 1);
 }
 template <typename T>
 int rcw_owner(void *A, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d, void *workspace,
-              double *pay_mine, const void *peer_table, void *mailbox, int64_t epoch, int solve_only,
+              double *pay_mine, const void *peer_table, void *mailbox, int64_t epoch, int solve_only, int fuse,
               int32_t *status, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (fuse < 1 || fuse > kRcwMaxFuse || (solve_only && fuse != 1)) return (int)cudaErrorInvalidValue;
   RcWave wv = rcw_carve(workspace, n, K, G);
+  wv.F = fuse;
   RcwP2P pp{(double *const *)peer_table, (double *)mailbox, (long long)epoch, rcw_max_tasks(n, K, G)};
   int Jlo, Jhi;
-  rcw_span(n, K, d, &Jlo, &Jhi);
+  rcw_span(n, rcw_groups(K, fuse), d, &Jlo, &Jhi);
   const int Jfirst = Jlo + (((rank - Jlo) % G) + G) % G;
   const int count = Jfirst > Jhi ? 0 : (Jhi - Jfirst) / G + 1;
   if (count == 0 && !peer_table) return 0;
@@ -389,12 +391,14 @@ int rcw_owner(void *A, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_
 template <typename T>
 int rcw_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
               void *workspace, const double *pay_all, const void *peer_table, void *mailbox, void *V_out,
-              int64_t ldv, int64_t epoch, int rows_mode, void *solve_ws, int32_t *status, void *stream) {
+              int64_t ldv, int64_t epoch, int rows_mode, void *solve_ws, int fuse, int32_t *status, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (fuse < 1 || fuse > kRcwMaxFuse || (solve_ws && fuse != 1)) return (int)cudaErrorInvalidValue;
   RcWave wv = rcw_carve(workspace, n, K, G);
+  wv.F = fuse;
   RcwP2P pp{(double *const *)peer_table, (double *)mailbox, (long long)epoch, rcw_max_tasks(n, K, G)};
   int Jlo, Jhi;
-  rcw_span(n, K, d, &Jlo, &Jhi);
+  rcw_span(n, rcw_groups(K, fuse), d, &Jlo, &Jhi);
   if (Jhi < Jlo) return 0;
   int nt = kRcwTrailNT;
   if (const char *e = getenv("CHUB_RCW_NT")) nt = atoi(e);
@@ -410,18 +414,22 @@ int rcw_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, in
   // head of the look-ahead split: only the CTAs of the two 256-row blocks J and J+1 of every task
   const unsigned gx = rows_mode == 1 ? (unsigned)(2 * kRcBlock / nt) : (unsigned)((m_loc > 0 ? m_loc + nt - 1 : nt) / nt);
   dim3 grid(gx, (unsigned)(Jhi - Jlo + 1));
-#define CHUB_TRAIL_GO(NTV, UPD)                                                                                      \
-  rcw_trail_kernel<T, NTV, UPD><<<grid, NTV, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, wv, (int)d, Jlo,      \
-                                                      pp.max_tasks, pay_all, (T *)V_out, ldv, pp, rows_mode, p_out,  \
-                                                      dn_out, status)
+#define CHUB_TRAIL_GO(NTV, UPD, FV)                                                                                  \
+  rcw_trail_kernel<T, NTV, UPD, FV><<<grid, NTV, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, wv, (int)d, Jlo,  \
+                                                          pp.max_tasks, pay_all, (T *)V_out, ldv, pp, rows_mode,     \
+                                                          p_out, dn_out, status)
   if (solve_ws) {
-    if (nt == 32) CHUB_TRAIL_GO(32, false);
-    else if (nt == 64) CHUB_TRAIL_GO(64, false);
-    else CHUB_TRAIL_GO(128, false);
+    if (nt == 32) CHUB_TRAIL_GO(32, false, 1);
+    else if (nt == 64) CHUB_TRAIL_GO(64, false, 1);
+    else CHUB_TRAIL_GO(128, false, 1);
+  } else if (fuse == 2) {
+    if (nt == 32) CHUB_TRAIL_GO(32, true, 2);
+    else if (nt == 64) CHUB_TRAIL_GO(64, true, 2);
+    else CHUB_TRAIL_GO(128, true, 2);
   } else {
-    if (nt == 32) CHUB_TRAIL_GO(32, true);
-    else if (nt == 64) CHUB_TRAIL_GO(64, true);
-    else CHUB_TRAIL_GO(128, true);
+    if (nt == 32) CHUB_TRAIL_GO(32, true, 1);
+    else if (nt == 64) CHUB_TRAIL_GO(64, true, 1);
+    else CHUB_TRAIL_GO(128, true, 1);
   }
 #undef CHUB_TRAIL_GO
   LAUNCHED();
@@ -546,7 +554,8 @@ int chub_p2p_close(void *peer_ptr) {
   return 0;
 }
 
-int chub_rcw_payload_doubles(void) { return kRcwPayload; }
+int chub_rcw_payload_doubles(void) { return kRcwSlot; }
+int chub_rcw_max_fuse(void) { return kRcwMaxFuse; }
 int chub_rcw_max_tasks(int64_t n, int64_t K, int G) { return rcw_max_tasks(n, K, G > 0 ? G : 1); }
 size_t chub_rcw_workspace_bytes(int64_t n, int64_t K, int G) {
   if (n < 0) n = 0;
@@ -575,30 +584,30 @@ DEFINE_RC_DD(f32, float)
     return rcw_prepare<T>(A, m_loc, n, ld, G, rank, V, K, ldv, workspace, flags, status, stream);                  \
   }                                                                                                                \
   int chub_rcw_owner_##SUF(void *A, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d, void *workspace, \
-                           double *pay_mine, int solve_only, int32_t *status, void *stream) {                      \
-    return rcw_owner<T>(A, n, ld, G, rank, K, d, workspace, pay_mine, nullptr, nullptr, 0, solve_only, status,     \
-                        stream);                                                                                   \
+                           double *pay_mine, int solve_only, int fuse, int32_t *status, void *stream) {            \
+    return rcw_owner<T>(A, n, ld, G, rank, K, d, workspace, pay_mine, nullptr, nullptr, 0, solve_only, fuse,       \
+                        status, stream);                                                                           \
   }                                                                                                                \
   int chub_rcw_apply_##SUF(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,   \
                            void *workspace, const double *pay_all, void *V_out, int64_t ldv, int rows_mode,        \
-                           void *solve_ws, int32_t *status, void *stream) {                                        \
+                           void *solve_ws, int fuse, int32_t *status, void *stream) {                              \
     return rcw_apply<T>(A, m_loc, n, ld, G, rank, K, d, workspace, pay_all, nullptr, nullptr, V_out, ldv, 0,       \
-                        rows_mode, solve_ws, status, stream);                                                      \
+                        rows_mode, solve_ws, fuse, status, stream);                                                \
   }                                                                                                                \
   int chub_rcw_owner_p2p_##SUF(void *A, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,              \
                                void *workspace, double *pay_mine, const void *peer_table, void *mailbox,           \
-                               int64_t epoch, int solve_only, int32_t *status, void *stream) {                     \
+                               int64_t epoch, int solve_only, int fuse, int32_t *status, void *stream) {           \
     if (!peer_table || !mailbox) return (int)cudaErrorInvalidValue;                                                \
     return rcw_owner<T>(A, n, ld, G, rank, K, d, workspace, pay_mine, peer_table, mailbox, epoch, solve_only,      \
-                        status, stream);                                                                           \
+                        fuse, status, stream);                                                                     \
   }                                                                                                                \
   int chub_rcw_apply_p2p_##SUF(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K,          \
                                int64_t d, void *workspace, const void *peer_table, void *mailbox, void *V_out,     \
-                               int64_t ldv, int64_t epoch, int rows_mode, void *solve_ws, int32_t *status,         \
-                               void *stream) {                                                                     \
+                               int64_t ldv, int64_t epoch, int rows_mode, void *solve_ws, int fuse,                \
+                               int32_t *status, void *stream) {                                                    \
     if (!peer_table || !mailbox) return (int)cudaErrorInvalidValue;                                                \
     return rcw_apply<T>(A, m_loc, n, ld, G, rank, K, d, workspace, (const double *)mailbox, peer_table, mailbox,   \
-                        V_out, ldv, epoch, rows_mode, solve_ws, status, stream);                                   \
+                        V_out, ldv, epoch, rows_mode, solve_ws, fuse, status, stream);                             \
   }
 DEFINE_RCW(f64, double)
 DEFINE_RCW(f32, float)

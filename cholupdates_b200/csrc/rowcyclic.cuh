@@ -209,9 +209,14 @@ struct RcWave {
   double *W;     // [K][n_pad]  residual vector of every update (entries of the owned rows are live)
   double *scal;  // [K][8]      {t, S} of every update entering its next panel
   double *X;     // [max_tasks][8][kXBlock]  inverse diagonal blocks of this rank's tasks of the step
+  double *D;     // [max_tasks][256][256]    fused mode: working copy of a task's diagonal block
   int64_t n_pad;
   int K;
+  int F;         // updates per task (1, or kRcwMaxFuse: consecutive updates share one pass over the panel)
 };
+constexpr int kRcwMaxFuse = 2;
+// Fused mode: "update" in the task grid means a GROUP of F consecutive updates; NU groups in all.
+__host__ __device__ inline int64_t rcw_groups(int64_t K, int F) { return (K + F - 1) / F; }
 
 inline int rcw_panels(int64_t n) { return (int)((n + kBig - 1) / kBig); }
 inline int rcw_max_tasks(int64_t n, int64_t K, int G) {
@@ -220,7 +225,7 @@ inline int rcw_max_tasks(int64_t n, int64_t K, int G) {
 }
 inline size_t rcw_ws_doubles(int64_t n, int64_t K, int G) {
   const int64_t n_pad = (n + 31) & ~31LL;
-  return (size_t)(K * n_pad + K * 8 + (int64_t)rcw_max_tasks(n, K, G) * (kBig / kPanel) * kXBlock);
+  return (size_t)(K * n_pad + K * 8 + (int64_t)rcw_max_tasks(n, K, G) * ((kBig / kPanel) * kXBlock + kBig * kBig));
 }
 inline RcWave rcw_carve(void *base, int64_t n, int64_t K, int G) {
   RcWave wv;
@@ -229,8 +234,9 @@ inline RcWave rcw_carve(void *base, int64_t n, int64_t K, int G) {
   double *d = reinterpret_cast<double *>(base);
   wv.W = d; d += K * wv.n_pad;
   wv.scal = d; d += K * 8;
-  wv.X = d;
-  (void)G;
+  wv.X = d; d += (int64_t)rcw_max_tasks(n, K, G) * (kBig / kPanel) * kXBlock;
+  wv.D = d;
+  wv.F = 1;
   return wv;
 }
 
@@ -244,6 +250,7 @@ inline RcWave rcw_carve(void *base, int64_t n, int64_t K, int G) {
 // waits for all G flags: no rank can be more than one step ahead of another, which is what makes two
 // parities enough.  No NCCL call, no host synchronisation between steps: 2 launches per step.
 constexpr int kRcwSets = 4;
+constexpr int kRcwSlot = 2 * kRcwPayload;  // a task's slot holds the payloads of up to kRcwMaxFuse updates
 struct RcwP2P {
   double *const *peer_mail;  // device array [G]: mailbox base of every rank as mapped here (nullptr = NCCL mode)
   double *mail;              // this rank's own mailbox
@@ -257,10 +264,10 @@ struct RcwP2P {
 // The flags sit at a fixed place, so calls with different K (different max_tasks) can share a mailbox
 // that was sized for the largest one.
 inline size_t rcw_mailbox_doubles(int64_t n, int64_t K, int G) {
-  return (size_t)kRcwSets * G + 8 + (size_t)kRcwSets * G * rcw_max_tasks(n, K, G) * kRcwPayload;
+  return (size_t)kRcwSets * G + 8 + (size_t)kRcwSets * G * rcw_max_tasks(n, K, G) * kRcwSlot;
 }
 __host__ __device__ inline size_t rcw_mail_slot(int q, int r, int i, int G, int max_tasks) {
-  return (size_t)kRcwSets * G + 8 + ((size_t)(q * G + r) * max_tasks + i) * kRcwPayload;
+  return (size_t)kRcwSets * G + 8 + ((size_t)(q * G + r) * max_tasks + i) * kRcwSlot;
 }
 __host__ __device__ inline size_t rcw_mail_flags(int G, int max_tasks) {
   (void)G; (void)max_tasks;
@@ -323,25 +330,72 @@ __global__ void __launch_bounds__(kBig) rcw_owner_kernel(const T *A, int n, int6
                              (int)((pp.epoch + d) & (kRcwSets - 1)) * G + rank, pp.epoch + d + 1);
     return;
   }
-  const int J = Jfirst + i * G, u = d - J;
+  const int J = Jfirst + i * G, U = d - J;  // U = update (F == 1) or group of F consecutive updates
+  const int F = UPDATE ? wv.F : 1;
+  const int Fe = min(F, wv.K - U * F);       // updates in this group (the last group may be short)
   // the diagonal block of panel J is local block J / G; shift the base so that GLOBAL row indices work
   const T *Lsh = A + ((int64_t)(J / G) - (int64_t)J) * kRcBlock * ld;
   double *X = wv.X + (int64_t)i * (kBig / kPanel) * kXBlock;
   const int warp = threadIdx.x >> 5;
-  // the 8 inverse diagonal blocks at once, one warp each (staging in dynamic shared memory)
   extern __shared__ __align__(16) double rcw_stage[];  // [8][kInvStageDoubles]
-  {
-    double *stg = rcw_stage + (size_t)warp * kInvStageDoubles;
+  double *stg = rcw_stage + (size_t)warp * kInvStageDoubles;
+  double *pay = pay_mine + (int64_t)i * kRcwSlot;
+  if (F == 1) {
+    // the 8 inverse diagonal blocks at once, one warp each (staging in dynamic shared memory)
     invdiag_block_smem<T, CHUB_ROW_MAJOR>(Lsh, n, ld, X + (int64_t)warp * kXBlock, J * (kBig / kPanel) + warp,
                                           reinterpret_cast<double (*)[kPanel + 1]>(stg), stg + kPanel * (kPanel + 1));
-  }
-  __syncthreads();
-  double *pay = pay_mine + (int64_t)i * kRcwPayload;
-  chain_body<T, CHUB_ROW_MAJOR, UPDATE>(Lsh, n, ld, J, X, wv.W + (int64_t)u * wv.n_pad, pay, pay + kBig, pay + 2 * kBig,
-                                        pay + 3 * kBig, (T *)nullptr, pay + 4 * kBig, wv.scal + u * 8, pay + 5 * kBig);
-  if (!UPDATE) {
-    const int R = J * kBig + (int)threadIdx.x;
-    pay[3 * kBig + threadIdx.x] = (R < n && Lsh[(int64_t)R * ld + R] < T(0)) ? -1.0 : 1.0;
+    __syncthreads();
+    chain_body<T, CHUB_ROW_MAJOR, UPDATE>(Lsh, n, ld, J, X, wv.W + (int64_t)U * wv.n_pad, pay, pay + kBig,
+                                          pay + 2 * kBig, pay + 3 * kBig, (T *)nullptr, pay + 4 * kBig,
+                                          wv.scal + U * 8, pay + 5 * kBig);
+    if (!UPDATE) {
+      const int R = J * kBig + (int)threadIdx.x;
+      pay[3 * kBig + threadIdx.x] = (R < n && Lsh[(int64_t)R * ld + R] < T(0)) ? -1.0 : 1.0;
+    }
+  } else {
+    // Fused: the coefficients of update f+1 need the diagonal block AFTER update f.  The block is copied
+    // into a scratch (fp64, ld = 256), and between two chains update f is applied to the scratch by the
+    // thread that owns the row.  A itself is left alone: the trail kernel applies all Fe updates to the
+    // block's rows together with every other row (the same arithmetic, from the same payloads).
+    const int base = J * kBig;
+    double *Dm = wv.D + (int64_t)i * kBig * kBig;
+    const double *Dsh = Dm - ((int64_t)base * kBig + base);  // Dsh[R * 256 + C] for global R, C of the block
+    for (int r = warp; r < kBig; r += kBig / 32) {
+      const int R = base + r;
+      if (R < n)
+        for (int c = threadIdx.x & 31; c <= r; c += 32) Dm[r * kBig + c] = (double)Lsh[(int64_t)R * ld + base + c];
+    }
+    __syncthreads();
+    __shared__ double cf[4][kBig];  // p, c, sigma, dn of the update being applied to the scratch
+    for (int f = 0; f < Fe; ++f) {
+      const int u = U * F + f;
+      double *pf = pay + (int64_t)f * kRcwPayload;
+      invdiag_block_smem<double, CHUB_ROW_MAJOR>(Dsh, n, kBig, X + (int64_t)warp * kXBlock, J * (kBig / kPanel) + warp,
+                                                 reinterpret_cast<double (*)[kPanel + 1]>(stg), stg + kPanel * (kPanel + 1));
+      __syncthreads();
+      chain_body<double, CHUB_ROW_MAJOR, true>(Dsh, n, kBig, J, X, wv.W + (int64_t)u * wv.n_pad, pf, pf + kBig,
+                                               pf + 2 * kBig, pf + 3 * kBig, (double *)nullptr, pf + 4 * kBig,
+                                               wv.scal + u * 8, pf + 5 * kBig);
+      __syncthreads();
+      if (f + 1 < Fe) {
+        const int a = threadIdx.x, R = base + a;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cf[q][a] = pf[q * kBig + a];
+        __syncthreads();
+        if (R < n) {
+          double w = wv.W[(int64_t)u * wv.n_pad + R];
+          double *row = Dm + a * kBig;
+#pragma unroll 8
+          for (int c = 0; c < a; ++c) {
+            const double lo = row[c];
+            row[c] = fma(cf[1][c], lo, cf[2][c] * w);
+            w = fma(-lo, cf[0][c], w);
+          }
+          row[a] = cf[3][a];
+        }
+        __syncthreads();
+      }
+    }
   }
   if (!pp.peer_mail) return;
   // ---- push the payload into every rank's mailbox (own included), then the flags
@@ -349,7 +403,7 @@ __global__ void __launch_bounds__(kBig) rcw_owner_kernel(const T *A, int n, int6
   const int q = (int)((pp.epoch + d) & (kRcwSets - 1));
   for (int g = 0; g < G; ++g) {
     double *dst = pp.peer_mail[g] + rcw_mail_slot(q, rank, i, G, pp.max_tasks);
-    for (int e = threadIdx.x; e < kRcwPayload; e += kBig) dst[e] = pay[e];
+    for (int e = threadIdx.x; e < Fe * kRcwPayload; e += kBig) dst[e] = pay[e];
   }
   __threadfence_system();  // my stores are performed system-wide before I am counted as done
   __syncthreads();
@@ -375,18 +429,19 @@ __global__ void __launch_bounds__(kBig) rcw_owner_kernel(const T *A, int n, int6
 // UPDATE = false: the read-only pass of the downdate's forward substitution (w <- w - L p on the rows
 // below the panel's diagonal block); the unpacking CTA stores p and the diagonal signs of the panel into
 // the n-vectors p_out / dn_out (what the rho^2 test and the sweep read) instead of {t, S} and V_out.
-template <typename T, int NT, bool UPDATE = true>
+template <typename T, int NT, bool UPDATE = true, int F = 1>
 __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, int64_t ld, int G, int rank, RcWave wv,
                                                        int d, int Jlo, int max_tasks, const double *pay_all,
                                                        T *V_out, int64_t ldv, RcwP2P pp, int rows_mode,
                                                        double *p_out, double *dn_out, int32_t *status) {
-  __shared__ __align__(16) double cp[kPanel];    // p_k
-  __shared__ __align__(16) double2 ccs[kPanel];  // (c_k, sigma_k): one 16-byte load per column
+  __shared__ __align__(16) double cp[F][kPanel];    // p_k of each of the task's updates
+  __shared__ __align__(16) double2 ccs[F][kPanel];  // (c_k, sigma_k): one 16-byte load per column
   __shared__ __align__(16) T tile[NT * kPanel];
   if (*status != 0) return;
   const int tid = threadIdx.x;
-  const int J = Jlo + (int)blockIdx.y, u = d - J;
-  const double *pay = pay_all + ((int64_t)(J % G) * max_tasks + blockIdx.y / G) * kRcwPayload;
+  const int J = Jlo + (int)blockIdx.y, U = d - J;  // U = update (F == 1) or group of F consecutive updates
+  const int Fe = min(F, wv.K - U * F);
+  const double *pay = pay_all + ((int64_t)(J % G) * max_tasks + blockIdx.y / G) * kRcwSlot;
   const int base = J * kBig;
   // Which local rows does this CTA take?  rows_mode 0: all rows below the panel's top (blockIdx.x = NT
   // consecutive local rows).  Look-ahead split: 1 = HEAD, only the two 256-row blocks J and J+1 (what
@@ -409,8 +464,8 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
     // entirely above the panel (or, for the bulk, not below the head)?
     have_rows = rows > 0 && g0 + rows > (rows_mode == 2 ? base + 2 * kRcBlock : (UPDATE ? base : base + kRcBlock));
   }
-  // CTA x = 0 of every task also unpacks: {t, S} for the next panel of update u (modes 0, 1) and the
-  // scratch vector for the caller (modes 0, 2)
+  // CTA x = 0 of every task also unpacks: {t, S} for the next panel of each update (modes 0, 1) and the
+  // scratch vectors for the caller (modes 0, 2)
   const bool unpack = blockIdx.x == 0;
   if (!have_rows && !unpack) return;
   if (pp.peer_mail) {
@@ -427,10 +482,14 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
     pay = pp.mail + rcw_mail_slot(q, J % G, blockIdx.y / G, G, max_tasks);
   }
   if (unpack && UPDATE) {
-    if (rows_mode != 2 && tid < 2) wv.scal[u * 8 + tid] = __ldcg(pay + 5 * kBig + tid);
-    if (rows_mode != 1 && V_out)
-      for (int k = tid; k < kBig; k += NT)
-        if (base + k < n) V_out[(int64_t)u * ldv + base + k] = (T)__ldcg(pay + 4 * kBig + k);
+    for (int f = 0; f < Fe; ++f) {
+      const double *pf = pay + (int64_t)f * kRcwPayload;
+      const int u = U * F + f;
+      if (rows_mode != 2 && tid < 2) wv.scal[u * 8 + tid] = __ldcg(pf + 5 * kBig + tid);
+      if (rows_mode != 1 && V_out)
+        for (int k = tid; k < kBig; k += NT)
+          if (base + k < n) V_out[(int64_t)u * ldv + base + k] = (T)__ldcg(pf + 4 * kBig + k);
+    }
   }
   if (unpack && !UPDATE && rows_mode != 1)
     for (int k = tid; k < kBig; k += NT)
@@ -443,18 +502,20 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
   T *L = A + ((int64_t)l0 - g0) * ld;  // so that L[R * ld + c] addresses global row R
   const int R = r0 + tid;
   const bool valid = tid < rows && R >= (UPDATE ? base : base + kRcBlock);
-  double *wu = wv.W + (int64_t)u * wv.n_pad;
-  double w = valid ? wu[R] : 0.0;
+  double w[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) w[f] = (valid && f < Fe) ? wv.W[(int64_t)(U * F + f) * wv.n_pad + R] : 0.0;
   const int cend = min(n, base + kBig);
   for (int c0 = base; c0 < cend; c0 += kPanel) {
     const int bw = min(kPanel, n - c0);
     if (c0 > r0 + rows - 1) break;
     __syncthreads();
-    if (tid < kPanel) {
-      const int a = c0 - base + tid;
-      cp[tid] = tid < bw ? __ldcg(pay + a) : 0.0;  // (L2 loads: in P2P mode other GPUs wrote the payload)
-      if (UPDATE)
-        ccs[tid] = make_double2(tid < bw ? __ldcg(pay + kBig + a) : 1.0, tid < bw ? __ldcg(pay + 2 * kBig + a) : 0.0);
+    for (int e = tid; e < F * kPanel; e += NT) {
+      const int f = e / kPanel, k = e % kPanel;
+      const double *pf = pay + (int64_t)f * kRcwPayload + (c0 - base + k);
+      const bool ok = k < bw && f < Fe;
+      cp[f][k] = ok ? __ldcg(pf) : 0.0;  // (L2 loads: in P2P mode other GPUs wrote the payload)
+      if (UPDATE) ccs[f][k] = make_double2(ok ? __ldcg(pf + kBig) : 1.0, ok ? __ldcg(pf + 2 * kBig) : 0.0);
     }
     tile_load_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
     if (tid < rows && c0 + kPanel < cend) {  // next block column of my row -> L2 while this one is processed
@@ -469,33 +530,46 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
         T *trow = tile + tid * kPanel;
         const int sw = tid & 31;
 #pragma unroll
-        for (int k = 0; k < kPanel; k += 2) {  // 3 coefficient loads of 16 bytes per 2 columns
-          const double2 p2 = *reinterpret_cast<const double2 *>(cp + k);
-          const double l0 = (double)trow[k ^ sw];
-          const double l1 = (double)trow[(k + 1) ^ sw];
-          if (UPDATE) {
-            const double2 q0 = ccs[k], q1 = ccs[k + 1];
-            trow[k ^ sw] = (T)fma(q0.x, l0, q0.y * w);
-            w = fma(-l0, p2.x, w);
-            trow[(k + 1) ^ sw] = (T)fma(q1.x, l1, q1.y * w);
-            w = fma(-l1, p2.y, w);
-          } else {
-            w = fma(-l0, p2.x, w);
-            w = fma(-l1, p2.y, w);
+        for (int f = 0; f < F; ++f) {
+          if (f < Fe) {
+#pragma unroll
+            for (int k = 0; k < kPanel; k += 2) {  // 3 coefficient loads of 16 bytes per 2 columns
+              const double2 p2 = *reinterpret_cast<const double2 *>(&cp[f][k]);
+              const double l0v = (double)trow[k ^ sw];
+              const double l1v = (double)trow[(k + 1) ^ sw];
+              if (UPDATE) {
+                const double2 q0 = ccs[f][k], q1 = ccs[f][k + 1];
+                const double n0 = fma(q0.x, l0v, q0.y * w[f]);
+                w[f] = fma(-l0v, p2.x, w[f]);
+                const double n1 = fma(q1.x, l1v, q1.y * w[f]);
+                w[f] = fma(-l1v, p2.y, w[f]);
+                trow[k ^ sw] = (T)n0;
+                trow[(k + 1) ^ sw] = (T)n1;
+              } else {
+                w[f] = fma(-l0v, p2.x, w[f]);
+                w[f] = fma(-l1v, p2.y, w[f]);
+              }
+            }
           }
         }
       }
     } else if (valid) {
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        if (f < Fe) {
 #pragma unroll 8
-      for (int k = 0; k < kPanel; ++k) {
-        if (k < bw && c0 + k < R) {
-          const int o = tile_off(tid, k);
-          const double lo = (double)tile[o];
-          if (UPDATE) tile[o] = (T)(ccs[k].x * lo + ccs[k].y * w);
-          w -= lo * cp[k];
+          for (int k = 0; k < kPanel; ++k) {
+            if (k < bw && c0 + k < R) {
+              const int o = tile_off(tid, k);
+              const double lo = (double)tile[o];
+              if (UPDATE) tile[o] = (T)fma(ccs[f][k].x, lo, ccs[f][k].y * w[f]);
+              w[f] = fma(-lo, cp[f][k], w[f]);
+            }
+          }
+          if (UPDATE && R >= c0 && R < c0 + bw)
+            tile[tile_off(tid, R - c0)] = (T)__ldcg(pay + (int64_t)f * kRcwPayload + 3 * kBig + R - base);
         }
       }
-      if (UPDATE && R >= c0 && R < c0 + bw) tile[tile_off(tid, R - c0)] = (T)__ldcg(pay + 3 * kBig + R - base);
     }
     if (UPDATE) {
       __syncthreads();
@@ -503,7 +577,11 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
       tile_store_rm<T, NT>(tile, L, ld, r0, rows, c0, bw);
     }
   }
-  if (valid && R >= cend) wu[R] = w;
+  if (valid && R >= cend) {
+#pragma unroll
+    for (int f = 0; f < F; ++f)
+      if (f < Fe) wv.W[(int64_t)(U * F + f) * wv.n_pad + R] = w[f];
+  }
 }
 
 }  // namespace chub

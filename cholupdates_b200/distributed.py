@@ -223,11 +223,12 @@ class _CudaRowCyclicBackend:
             f = getattr(lib, f"chub_rcw_prepare_{suf}")
             f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, vp, i64, i64, vp, ci, vp, vp]
             f = getattr(lib, f"chub_rcw_owner_{suf}")
-            f.restype, f.argtypes = ci, [vp, i64, i64, ci, ci, i64, i64, vp, vp, ci, vp, vp]
+            f.restype, f.argtypes = ci, [vp, i64, i64, ci, ci, i64, i64, vp, vp, ci, ci, vp, vp]
             f = getattr(lib, f"chub_rcw_apply_{suf}")
-            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, i64, i64, vp, vp, vp, i64, ci, vp, vp, vp]
+            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, i64, i64, vp, vp, vp, i64, ci, vp, ci, vp, vp]
         K, dev = int(V.shape[0]), self.A.device
         self.K, self.V_out = K, V_out
+        self.fuse = 1
         need = int(lib.chub_rcw_workspace_bytes(self.n, K, self.world))
         if getattr(self, "wave_ws", None) is None or self.wave_ws.numel() < need:
             self.wave_ws = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -261,9 +262,9 @@ class _CudaRowCyclicBackend:
         lib.chub_p2p_import.restype, lib.chub_p2p_import.argtypes = ci, [vp, ctypes.POINTER(vp)]
         for suf in ("f64", "f32"):
             f = getattr(lib, f"chub_rcw_owner_p2p_{suf}")
-            f.restype, f.argtypes = ci, [vp, i64, i64, ci, ci, i64, i64, vp, vp, vp, vp, i64, ci, vp, vp]
+            f.restype, f.argtypes = ci, [vp, i64, i64, ci, ci, i64, i64, vp, vp, vp, vp, i64, ci, ci, vp, vp]
             f = getattr(lib, f"chub_rcw_apply_p2p_{suf}")
-            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, i64, i64, vp, vp, vp, vp, i64, i64, ci, vp, vp, vp]
+            f.restype, f.argtypes = ci, [vp, i64, i64, i64, ci, ci, i64, i64, vp, vp, vp, vp, i64, i64, ci, vp, ci, vp, vp]
         ok = os.environ.get("CHUB_RC_P2P", "1") != "0"
         ptrs = [0] * self.world
         if ok:
@@ -304,7 +305,7 @@ class _CudaRowCyclicBackend:
         rc = getattr(self.lib, f"chub_rcw_owner_p2p_{self.suf}")(
             self.A.data_ptr(), self.n, self.A.shape[1], self.world, self.rank, self.K, d,
             self.wave_ws.data_ptr(), pay_mine.data_ptr(), self.peer_table.data_ptr(), self.mailbox, self.epoch,
-            1 if solve_only else 0, self.status.data_ptr(), self._stream())
+            1 if solve_only else 0, 1 if solve_only else self.fuse, self.status.data_ptr(), self._stream())
         _lib.check(rc, "chub_rcw_owner_p2p")
 
     def wave_apply_p2p(self, d, rows_mode=0, solve_only=False):
@@ -314,7 +315,7 @@ class _CudaRowCyclicBackend:
             self.A.data_ptr(), self.A.shape[0], self.n, self.A.shape[1], self.world, self.rank, self.K, d,
             self.wave_ws.data_ptr(), self.peer_table.data_ptr(), self.mailbox, self.V_out.data_ptr(),
             self.V_out.stride(0), self.epoch, rows_mode, self.ws.data_ptr() if solve_only else None,
-            self.status.data_ptr(), self._stream())
+            1 if solve_only else self.fuse, self.status.data_ptr(), self._stream())
         _lib.check(rc, "chub_rcw_apply_p2p")
 
     def lookahead_streams(self):
@@ -336,8 +337,8 @@ class _CudaRowCyclicBackend:
 
         rc = getattr(self.lib, f"chub_rcw_owner_{self.suf}")(
             self.A.data_ptr(), self.n, self.A.shape[1], self.world, self.rank, self.K, d,
-            self.wave_ws.data_ptr(), pay_mine.data_ptr(), 1 if solve_only else 0, self.status.data_ptr(),
-            self._stream())
+            self.wave_ws.data_ptr(), pay_mine.data_ptr(), 1 if solve_only else 0, 1 if solve_only else self.fuse,
+            self.status.data_ptr(), self._stream())
         _lib.check(rc, "chub_rcw_owner")
 
     def wave_apply(self, d, pay_all, rows_mode=0, solve_only=False):
@@ -346,7 +347,8 @@ class _CudaRowCyclicBackend:
         rc = getattr(self.lib, f"chub_rcw_apply_{self.suf}")(
             self.A.data_ptr(), self.A.shape[0], self.n, self.A.shape[1], self.world, self.rank, self.K, d,
             self.wave_ws.data_ptr(), pay_all.data_ptr(), self.V_out.data_ptr(), self.V_out.stride(0),
-            rows_mode, self.ws.data_ptr() if solve_only else None, self.status.data_ptr(), self._stream())
+            rows_mode, self.ws.data_ptr() if solve_only else None, 1 if solve_only else self.fuse,
+            self.status.data_ptr(), self._stream())
         _lib.check(rc, "chub_rcw_apply")
 
     supports_wave_solve = True  # the forward substitution of the downdate can run on the wavefront kernels
@@ -511,7 +513,7 @@ class RowCyclicFactor:
             raise np.linalg.LinAlgError("The downdated matrix is not positive definite.")
         return v_out
 
-    def update_many(self, V, check_diag: bool = True, p2p=None, lookahead=None):
+    def update_many(self, V, check_diag: bool = True, p2p=None, lookahead=None, fuse=None):
         """Apply the K successive rank-1 updates ``V[0], V[1], ...`` (``V``: ``(K, n)``, identical on
         every rank) in place -- the same result as K calls of ``update``, scheduled as a wavefront.
 
@@ -526,7 +528,12 @@ class RowCyclicFactor:
         ``p2p``: None = exchange over NVLink peer memory when every rank can map every peer's mailbox
         (one node, cudaIpc), else NCCL all-gather; False = NCCL; True = peer memory or raise.
         ``lookahead``: None = split every step's trail into head and bulk on two streams when there is
-        no collective in the loop (peer-memory exchange or a single rank) and K > 1; False = one stream."""
+        no collective in the loop (peer-memory exchange or a single rank) and K > 1; False = one stream.
+        ``fuse``: 1 (default) = one update per task; 2 = consecutive updates (2u, 2u+1) share one pass
+        over every panel (half the HBM bytes per update; the owner runs the two diagonal-block chains
+        back to back on a scratch copy of its block).  Same results; measured slower for now (one GPU,
+        n = 16384, K = 32: 0.69 vs 0.54 ms per update) because the trail kernel is bound by its per-row
+        dependent FMA chain, not by HBM -- kept as the starting point for SURVEY 8(f)1."""
         import numpy as np
         import torch
         import torch.distributed as dist
@@ -550,11 +557,20 @@ class RowCyclicFactor:
                 dist.all_reduce(st, op=dist.ReduceOp.MAX, group=self.group)
             if int(st.item()) == 1:
                 raise np.linalg.LinAlgError("The given Cholesky factor `L` contains zeros on its diagonal")
-        steps = K + (self.n + RC_BLOCK - 1) // RC_BLOCK - 1
         use_p2p = multi and p2p is not False and hasattr(be, "p2p_ready") and be.p2p_ready(self.group)
         if lookahead is None:
             lookahead = K > 1
-        if (use_p2p or not multi) and lookahead and hasattr(be, "lookahead_streams"):
+        lookahead = bool(lookahead) and (use_p2p or not multi) and hasattr(be, "lookahead_streams")
+        if fuse is None:
+            fuse = 1  # (fuse = 2 is parity-tested but not faster yet: the trail kernel is latency-bound)
+        if fuse not in (1, 2):
+            raise ValueError("`fuse` must be 1 or 2.")
+        if fuse == 2 and not hasattr(be, "lookahead_streams"):
+            raise ValueError("this backend cannot fuse updates")
+        if hasattr(be, "fuse"):
+            be.fuse = fuse
+        steps = (K + fuse - 1) // fuse + (self.n + RC_BLOCK - 1) // RC_BLOCK - 1
+        if lookahead:
             # Look-ahead split (no collective on this path, so the steps need no host synchronisation):
             # the owner kernel of step d+1 depends only on the HEAD of step d's trail -- the two 256-row
             # blocks J, J+1 of every task -- so owner + head run on a high-priority stream while the

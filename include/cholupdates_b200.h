@@ -183,8 +183,14 @@ int chub_rc_dd_finish_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int
  *      Forward substitution only (the distributed downdate's p = L^{-1} v, K = 1): owner calls with
  *      solve_only = 1, apply calls with solve_ws = the chub_workspace_bytes() workspace that
  *      chub_rc_dd_finish will read (p and the signs of the input diagonal are stored there); A_loc
- *      is not modified.  solve_ws = NULL / solve_only = 0: the update. */
-int chub_rcw_payload_doubles(void);
+ *      is not modified.  solve_ws = NULL / solve_only = 0: the update.
+ *      fuse = 1: one update per task.  fuse = 2: a task is panel J of a GROUP of two consecutive
+ *      updates (2u, 2u+1) -- the panel is read and written once for both, so the trail moves half the
+ *      bytes per update; the steps then run d = 0 .. ceil(K/2) + ceil(n/256) - 2.  The owner applies
+ *      the first update of the group to a scratch copy of its diagonal block to get the second one's
+ *      coefficients; the trail applies both to every row. */
+int chub_rcw_payload_doubles(void); /* doubles per task slot (room for chub_rcw_max_fuse() updates) */
+int chub_rcw_max_fuse(void);
 int chub_rcw_max_tasks(int64_t n, int64_t K, int G);
 size_t chub_rcw_workspace_bytes(int64_t n, int64_t K, int G);
 int chub_rcw_prepare_f64(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, const void *V,
@@ -192,15 +198,17 @@ int chub_rcw_prepare_f64(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int 
 int chub_rcw_prepare_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, const void *V,
                          int64_t K, int64_t ldv, void *workspace, int flags, int32_t *status, void *stream);
 int chub_rcw_owner_f64(void *A_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
-                       void *workspace, double *pay_mine, int solve_only, int32_t *status, void *stream);
+                       void *workspace, double *pay_mine, int solve_only, int fuse, int32_t *status,
+                       void *stream);
 int chub_rcw_owner_f32(void *A_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
-                       void *workspace, double *pay_mine, int solve_only, int32_t *status, void *stream);
+                       void *workspace, double *pay_mine, int solve_only, int fuse, int32_t *status,
+                       void *stream);
 int chub_rcw_apply_f64(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
                        void *workspace, const double *pay_all, void *V_out, int64_t ldv, int rows_mode,
-                       void *solve_ws, int32_t *status, void *stream);
+                       void *solve_ws, int fuse, int32_t *status, void *stream);
 int chub_rcw_apply_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
                        void *workspace, const double *pay_all, void *V_out, int64_t ldv, int rows_mode,
-                       void *solve_ws, int32_t *status, void *stream);
+                       void *solve_ws, int fuse, int32_t *status, void *stream);
 
 /* ---- the same wavefront with the exchange over NVLink peer memory instead of a collective
  *      (one process per GPU).  Every rank allocates a mailbox (chub_p2p_alloc of
@@ -220,18 +228,18 @@ int chub_p2p_import(const void *handle64, void **peer_ptr);
 int chub_p2p_close(void *peer_ptr);
 int chub_rcw_owner_p2p_f64(void *A_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
                            void *workspace, double *pay_mine, const void *peer_table, void *mailbox,
-                           int64_t epoch, int solve_only, int32_t *status, void *stream);
+                           int64_t epoch, int solve_only, int fuse, int32_t *status, void *stream);
 int chub_rcw_owner_p2p_f32(void *A_loc, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_t d,
                            void *workspace, double *pay_mine, const void *peer_table, void *mailbox,
-                           int64_t epoch, int solve_only, int32_t *status, void *stream);
+                           int64_t epoch, int solve_only, int fuse, int32_t *status, void *stream);
 int chub_rcw_apply_p2p_f64(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K,
                            int64_t d, void *workspace, const void *peer_table, void *mailbox, void *V_out,
-                           int64_t ldv, int64_t epoch, int rows_mode, void *solve_ws, int32_t *status,
-                           void *stream);
+                           int64_t ldv, int64_t epoch, int rows_mode, void *solve_ws, int fuse,
+                           int32_t *status, void *stream);
 int chub_rcw_apply_p2p_f32(void *A_loc, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, int64_t K,
                            int64_t d, void *workspace, const void *peer_table, void *mailbox, void *V_out,
-                           int64_t ldv, int64_t epoch, int rows_mode, void *solve_ws, int32_t *status,
-                           void *stream);
+                           int64_t ldv, int64_t epoch, int rows_mode, void *solve_ws, int fuse,
+                           int32_t *status, void *stream);
 
 /* ---- tuning / introspection (bench.py and tests) */
 /* Force a kernel path: 0 = automatic, 1 = single-CTA kernels only, 2 = panel

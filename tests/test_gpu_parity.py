@@ -366,9 +366,10 @@ def test_rowcyclic_single_rank_matches_oracle(n):
     assert torch.equal(keep, Lz)
 
 
+@pytest.mark.parametrize("fuse", [None, 1, 2])
 @pytest.mark.parametrize("n,K", [(300, 1), (700, 5), (1000, 2), (2048, 11)])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_rowcyclic_wavefront_single_rank_matches_oracle(n, K, dtype):
+def test_rowcyclic_wavefront_single_rank_matches_oracle(n, K, dtype, fuse):
     """K successive updates as one wavefront (anti-diagonals of (update, panel) tasks) == K oracle calls;
     the scratch vectors are rotg's z_k, as the Cython path leaves them in v."""
     from cholupdates_b200.distributed import RowCyclicFactor
@@ -379,7 +380,8 @@ def test_rowcyclic_wavefront_single_rank_matches_oracle(n, K, dtype):
     A = torch.from_numpy(L.copy()).cuda()
     A_upper = torch.triu(torch.full_like(A, float("nan")), 1)
     A += A_upper  # the strict upper triangle must never reach the arithmetic
-    Z = RowCyclicFactor(A, n).update_many(torch.from_numpy(V.copy()).cuda())
+    # fuse = 2: consecutive updates share one pass over every panel (odd K: the last group is short)
+    Z = RowCyclicFactor(A, n).update_many(torch.from_numpy(V.copy()).cuda(), fuse=fuse)
     L_ref = np.array(L, order="F")
     z_ref = []
     for u in range(K):

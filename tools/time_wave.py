@@ -32,11 +32,11 @@ for rep in range(2):
     print(f"[wave] n={n} K={K}: {ms / K:.3f} ms/update ({ms:.1f} ms total), "
           f"{bytes_upd * K / ms / 1e6:.0f} GB/s", flush=True)
 assert bool(torch.isfinite(torch.tril(A)).all().item())
-for la in (False, True):
+for la, fuse in ((False, 1), (True, 1), (True, 2)):
     e0.record()
-    fac.update_many(V, check_diag=False, lookahead=la)
+    fac.update_many(V, check_diag=False, lookahead=la, fuse=fuse)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(f"[wave] n={n} K={K} lookahead={la}: {ms / K:.3f} ms/update ({ms:.1f} ms total), "
-          f"{bytes_upd * K / ms / 1e6:.0f} GB/s", flush=True)
+    print(f"[wave] n={n} K={K} lookahead={la} fuse={fuse}: {ms / K:.3f} ms/update ({ms:.1f} ms total), "
+          f"{bytes_upd * K / ms / 1e6:.0f} GB/s algorithmic", flush=True)
