@@ -299,6 +299,26 @@ class _CudaRowCyclicBackend:
         self._p2p_state = ok
         return ok
 
+    def p2p_close(self, group=None):
+        """Collective: unmap the peers' mailboxes and free this rank's (after every rank has stopped using them)."""
+        import ctypes
+
+        import torch.distributed as dist
+
+        if not getattr(self, "_p2p_state", False):
+            return
+        self.torch.cuda.synchronize(self.A.device)
+        dist.barrier(group=group)
+        self.lib.chub_p2p_close.restype, self.lib.chub_p2p_close.argtypes = ctypes.c_int, [ctypes.c_void_p]
+        self.lib.chub_p2p_free.restype, self.lib.chub_p2p_free.argtypes = ctypes.c_int, [ctypes.c_void_p]
+        for g, ptr in enumerate(self.peer_table.tolist()):
+            if g != self.rank:
+                self.lib.chub_p2p_close(ptr)
+        dist.barrier(group=group)
+        self.lib.chub_p2p_free(self.mailbox)
+        self._p2p_state = None
+        self.mailbox = None
+
     def wave_owner_p2p(self, d, pay_mine, solve_only=False):
         from . import _lib
 
@@ -388,6 +408,12 @@ class RowCyclicFactor:
         if not A_local.is_contiguous():
             raise ValueError("`A_local` must be row-major contiguous.")
         self.backend = backend if backend is not None else _CudaRowCyclicBackend(A_local, self.n, rank, world_size)
+
+    def close(self):
+        """Release the peer-memory mailboxes (collective over the group; the factor's rows are untouched).
+        Optional: a process that keeps one factor for its lifetime can skip it."""
+        if hasattr(self.backend, "p2p_close"):
+            self.backend.p2p_close(self.group)
 
     def update(self, v, check_diag: bool = True, per_panel=None):
         """In-place update of the distributed factor.  Returns the scratch vector (rotg's z_k; with

@@ -187,6 +187,9 @@ def main():
                   f"({bytes_upd / per / 1e6 / world:.0f} GB/s per GPU)", flush=True)
     finite = bool(torch.isfinite(A).all().item())
     assert finite
+    fac.close()  # unmap / free the peer-memory mailboxes (collective)
+    facw.close()
+    facd.close()
     dist.destroy_process_group()
 
 
