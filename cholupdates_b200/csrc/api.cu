@@ -439,7 +439,7 @@ int rcw_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, in
 
 extern "C" {
 
-int chub_version(void) { return 100; }
+int chub_version(void) { return 110; }  // 110: chub_rcw_* (wavefront), chub_rc_dd_*, chub_p2p_*
 const char *chub_last_error(void) { return g_err; }
 
 int chub_device_count(void) {
