@@ -173,3 +173,30 @@ def test_rowcyclic_argument_checks_need_no_gpu():
         fac.update_many(torch.ones((n, 2), dtype=torch.float64).t())
     assert fac.update_many(torch.ones((0, n), dtype=torch.float64)).shape == (0, n)
 
+
+def test_wavefront_sizing_entry_points_need_no_gpu():
+    """Slot / workspace / mailbox sizing of the wavefront mode is host arithmetic: consistent with the
+    Python driver's own task bookkeeping (max tasks of one rank on an anti-diagonal)."""
+    import ctypes
+
+    lib = _lib.load()
+    i64, ci = ctypes.c_int64, ctypes.c_int
+    lib.chub_rcw_max_tasks.restype, lib.chub_rcw_max_tasks.argtypes = ci, [i64, i64, ci]
+    lib.chub_rcw_workspace_bytes.restype, lib.chub_rcw_workspace_bytes.argtypes = ctypes.c_size_t, [i64, i64, ci]
+    lib.chub_rcw_mailbox_bytes.restype, lib.chub_rcw_mailbox_bytes.argtypes = ctypes.c_size_t, [i64, i64, ci]
+    pay = lib.chub_rcw_payload_doubles()
+    assert pay == lib.chub_rcw_max_fuse() * (5 * 256 + 8)
+    for n in (1, 255, 256, 257, 4096, 65536):
+        n_panels = (n + 255) // 256
+        for K in (1, 2, 7, 64, 1000):
+            for G in (1, 2, 3, 8):
+                # brute force: the most panels J = r (mod G) inside any window of min(K, panels) consecutive J
+                L = min(K, n_panels)
+                want = max(1, max(sum(1 for J in range(lo, lo + L) if J % G == r)
+                                  for lo in range(0, n_panels - L + 1) for r in range(G)))
+                got = lib.chub_rcw_max_tasks(n, K, G)
+                assert got >= want and got == max(1, -(-L // G)), (n, K, G, got, want)
+                n_pad = (n + 31) // 32 * 32
+                assert lib.chub_rcw_workspace_bytes(n, K, G) >= 8 * (K * n_pad + K * 8)
+                assert lib.chub_rcw_mailbox_bytes(n, K, G) >= 8 * 4 * G * got * pay
+
