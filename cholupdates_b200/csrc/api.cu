@@ -161,9 +161,10 @@ int run_single(void *Lv, int64_t n, int64_t ld, int layout, void *vv, int flags,
     return (int)cudaErrorInvalidValue;
   }
   LargeWs ws = large_ws_carve(workspace, n);
-  if (path == 3 && layout == CHUB_COL_MAJOR && !getenv("CHUB_COL_MAJOR_NATIVE")) {
-    // Column-major: the fast persistent kernel is row-major (tensor-map boxes along rows).  Until the
-    // column-major boxes exist, go through a row-major scratch copy of the lower triangle: two extra
+  if (path == 3 && layout == CHUB_COL_MAJOR && !dataflow_native<T>(n, ld, layout, L) &&
+      !getenv("CHUB_COL_MAJOR_NATIVE")) {
+    // Column-major shapes the native tensor-map kernel (df_kernel_cm) does not take (beyond its row cap,
+    // odd leading dimension): go through a row-major scratch copy of the lower triangle -- two extra
     // coalesced triangle passes cost less than the older column-major kernel (df_kernel_v2).
     constexpr int64_t kEpc = 16 / sizeof(T);
     const int64_t ldr = (n + kEpc - 1) / kEpc * kEpc;  // 16-byte aligned rows
@@ -275,7 +276,7 @@ int rc_panel_owner(void *A, int64_t n, int64_t ld, int G, int rank, int J, void 
   LAUNCHED();
   large_chain_kernel<T, CHUB_ROW_MAJOR, true><<<1, kBig, 0, st>>>(Lsh, (int)n, ld, (T *)v_out, ws, J, status);
   LAUNCHED();
-  rc_pack_kernel<<<1, kBig, 0, st>>>(ws, J, payload, status);
+  rc_pack_kernel<<<1, kBig, 0, st>>>(ws, J, (int)((n + 31) & ~31LL), payload, status);
   LAUNCHED();
   return 0;
 }
@@ -285,7 +286,7 @@ int rc_panel_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int ran
   cudaStream_t st = (cudaStream_t)stream;
   LargeWs ws = large_ws_carve(workspace, n);
   if (!is_owner) {
-    rc_unpack_kernel<<<1, kBig, 0, st>>>(ws, J, payload, status);
+    rc_unpack_kernel<<<1, kBig, 0, st>>>(ws, J, (int)((n + 31) & ~31LL), payload, status);
     LAUNCHED();
   }
   if (m_loc > 0) {
@@ -317,7 +318,7 @@ int rc_dd_panel_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int 
                       const double *payload, int32_t *status, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   LargeWs ws = large_ws_carve(workspace, n);
-  rc_unpack_dd_kernel<<<1, kBig, 0, st>>>(ws, J, payload, status);  // (the owner too: it sets the signs)
+  rc_unpack_dd_kernel<<<1, kBig, 0, st>>>(ws, J, (int)((n + 31) & ~31LL), payload, status);  // (the owner too: it sets the signs)
   LAUNCHED();
   if (m_loc > 0 && (int64_t)(J + 1) * kBig < n) {
     rc_trail_kernel<T, false><<<(unsigned)((m_loc + 127) / 128), 128, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank,
@@ -360,6 +361,17 @@ int rcw_prepare(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, 
   LAUNCHED();
   return 0;
 }
+// Peer-memory exchange arguments.  The slot stride is a property of the mailbox (rcw_mail_tasks), not of
+// the call; the watchdog is generous because ranks may enter a call seconds apart (CHUB_P2P_WATCHDOG_MS).
+inline RcwP2P rcw_p2p_args(const void *peer_table, void *mailbox, int64_t epoch, int64_t n, int G) {
+  static long long cycles = 0;
+  if (!cycles) {
+    long long ms = 20000;
+    if (const char *e = getenv("CHUB_P2P_WATCHDOG_MS")) ms = atoll(e) > 0 ? atoll(e) : ms;
+    cycles = ms * 2000000LL;  // ~2 GHz
+  }
+  return RcwP2P{(double *const *)peer_table, (double *)mailbox, (long long)epoch, rcw_mail_tasks(n, G), cycles};
+}
 // tasks of anti-diagonal d: panels Jlo..Jhi (update u = d - J)
 inline void rcw_span(int64_t n, int64_t K, int64_t d, int *Jlo, int *Jhi) {  // K = updates, or groups when fused
   const int64_t nJ = rcw_panels(n);
@@ -374,7 +386,7 @@ int rcw_owner(void *A, int64_t n, int64_t ld, int G, int rank, int64_t K, int64_
   if (fuse < 1 || fuse > kRcwMaxFuse || (solve_only && fuse != 1)) return (int)cudaErrorInvalidValue;
   RcWave wv = rcw_carve(workspace, n, K, G);
   wv.F = fuse;
-  RcwP2P pp{(double *const *)peer_table, (double *)mailbox, (long long)epoch, rcw_max_tasks(n, K, G)};
+  RcwP2P pp = rcw_p2p_args(peer_table, mailbox, epoch, n, G);
   int Jlo, Jhi;
   rcw_span(n, rcw_groups(K, fuse), d, &Jlo, &Jhi);
   const int Jfirst = Jlo + (((rank - Jlo) % G) + G) % G;
@@ -396,7 +408,7 @@ int rcw_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, in
   if (fuse < 1 || fuse > kRcwMaxFuse || (solve_ws && fuse != 1)) return (int)cudaErrorInvalidValue;
   RcWave wv = rcw_carve(workspace, n, K, G);
   wv.F = fuse;
-  RcwP2P pp{(double *const *)peer_table, (double *)mailbox, (long long)epoch, rcw_max_tasks(n, K, G)};
+  RcwP2P pp = rcw_p2p_args(peer_table, mailbox, epoch, n, G);
   int Jlo, Jhi;
   rcw_span(n, rcw_groups(K, fuse), d, &Jlo, &Jhi);
   if (Jhi < Jlo) return 0;
@@ -416,8 +428,8 @@ int rcw_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, in
   dim3 grid(gx, (unsigned)(Jhi - Jlo + 1));
 #define CHUB_TRAIL_GO(NTV, UPD, FV)                                                                                  \
   rcw_trail_kernel<T, NTV, UPD, FV><<<grid, NTV, 0, st>>>((T *)A, (int)m_loc, (int)n, ld, G, rank, wv, (int)d, Jlo,  \
-                                                          pp.max_tasks, pay_all, (T *)V_out, ldv, pp, rows_mode,     \
-                                                          p_out, dn_out, status)
+                                                          rcw_max_tasks(n, K, G), pay_all, (T *)V_out, ldv, pp,      \
+                                                          rows_mode, p_out, dn_out, status)
   if (solve_ws) {
     if (nt == 32) CHUB_TRAIL_GO(32, false, 1);
     else if (nt == 64) CHUB_TRAIL_GO(64, false, 1);
@@ -439,8 +451,10 @@ int rcw_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, in
 
 extern "C" {
 
-int chub_version(void) { return 110; }  // 110: chub_rcw_* (wavefront), chub_rc_dd_*, chub_p2p_*
+int chub_version(void) { return 120; }  // 120: resident factors, chub_*_many; 110: chub_rcw_* (wavefront), chub_rc_dd_*, chub_p2p_*
 const char *chub_last_error(void) { return g_err; }
+// (internal, not in the header) host.cu reports its failures through the same buffer
+void chub_internal_set_error(const char *msg) { snprintf(g_err, sizeof(g_err), "%s", msg ? msg : ""); }
 
 int chub_device_count(void) {
   int n = 0;

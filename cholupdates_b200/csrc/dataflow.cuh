@@ -185,6 +185,28 @@ __device__ __forceinline__ double df_wait_value(const double *p, int32_t *status
   }
 }
 
+// Poll the value at `cur` with the poll of `nxt` (the next block row's entry, wanted right after) in flight
+// at the same time: every round issues both loads back to back, so a consumer that takes one block row
+// per round trip keeps up with a producer twice as fast.  b_cur / b_nxt carry polls that are already back.
+__device__ __forceinline__ double df_wait_value2(const double *cur, const double *nxt, unsigned long long &b_cur,
+                                                 unsigned long long &b_nxt, int32_t *status) {
+  if (b_cur == kSentinelBits) {
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    while (true) {
+      const unsigned long long x = ld_relaxed_u64(cur);
+      const unsigned long long y = nxt ? ld_relaxed_u64(nxt) : kSentinelBits;
+      b_nxt = y;
+      if (x != kSentinelBits) { b_cur = x; break; }
+      if ((++spins & 255u) == 0u) {
+        if (ld_relaxed_s32(status) == CHUB_STATUS_INTERNAL) { b_cur = 0; break; }
+        if (clock64() - t0 > kWatchdogCycles) { atomicMax(status, CHUB_STATUS_INTERNAL); b_cur = 0; break; }
+      }
+    }
+  }
+  return __longlong_as_double((long long)b_cur);
+}
+
 __device__ __forceinline__ double df_sanitize(double x) {
   // never let user data alias the sentinel
   return (unsigned long long)__double_as_longlong(x) == kSentinelBits ? __longlong_as_double(0x7FF8000000000000LL) : x;
@@ -244,7 +266,8 @@ __global__ void df_prepare_kernel(const T *L, int n, int64_t ld, const T *v, Lar
 // are computed unconditionally (they only read L) -- the persistent kernel checks the status word.
 template <typename T, int LAYOUT>
 __global__ void __launch_bounds__(128) df_prepass_kernel(const T *L, int n, int64_t ld, const T *v, LargeWs ws,
-                                                         int flags, int32_t *status, int band_depth) {
+                                                         int flags, int32_t *status, int band_depth,
+                                                         bool with_m1) {
   const int i = blockIdx.x * 128 + threadIdx.x;
   const int n_pad = (n + 31) & ~31;
   if (i < n_pad) {
@@ -264,7 +287,7 @@ __global__ void __launch_bounds__(128) df_prepass_kernel(const T *L, int n, int6
     }
   }
   if (i == 0) { ws.scal[0] = 1.0; ws.scal[1] = 1.0; ws.scal[2] = 0.0; ws.scal[3] = 0.0; }
-  invdiag_block<T, LAYOUT>(L, n, ld, ws, blockIdx.x * 4 + (threadIdx.x >> 5));
+  invdiag_block<T, LAYOUT>(L, n, ld, ws, blockIdx.x * 4 + (threadIdx.x >> 5), with_m1);
 }
 
 // ------------------------------------------------------------------ chain CTA
@@ -744,82 +767,179 @@ template <typename T> struct RmGeom {
   static constexpr int CTILE = HALVES * 4096;              // bytes of a chain tile (32 rows)
 };
 
-// ---- chain CTA (threads 0..255 of CTA 0)
-template <typename T, bool PROF>
+// ---- chain CTA (threads 0..255 of CTA 0): eight warps with fixed roles, no CTA-wide barrier in the loop.
+//
+// With M1_r = X_r L[r, r-1] (formed by the pre-pass, off the critical path) the forward substitution reads
+//     p_r = ua_r + xw_r - M1_r p_{r-1},   ua_r = -X_r sum_{q=2..d} L[r, r-q] p_{r-q},   xw_r = X_r wt_r
+// so the step p_{r-1} -> p_r is ONE 32x32 mat-vec (warp C).  ua_r is complete one step earlier: block row r
+// belongs to band warp (r - 2) mod 4, which adds the band tiles (r, j), j = r-d .. r-2, as the p_j arrive
+// (one tile per step, accumulator in registers, lane = row) and multiplies by X_r after the last one.
+//   warp 0      C: p_r = u_r - M1_r p_{r-1}; publishes p_r (shared ring + global)
+//   warps 1..4  B: band tiles + u_r
+//   warp 5      P: polls wt_r (handed over by the workers) and forms xw_r = X_r wt_r, so that wt_r is needed
+//                  only one mat-vec before p_r is due:  p_r = ua_r + xw_r - M1_r p_{r-1}
+//   warp 6      T: issues the TMA loads of a block column as soon as its ring slot has been consumed, and
+//                  prefetches the band tiles of a later block column into L2
+// Hand-offs are counters in shared memory (st.release.cta / ld.acquire.cta); every spin has a watchdog.
+constexpr int kChTiles = kDfD - 1;  // band tiles per block column in the ring (distance 1 is folded into M1)
+constexpr int kChRing = 8;          // p / u / wt rings (block rows)
+
+template <typename T>
+struct ChGeom {
+  static constexpr int SLOT = kChTiles * RmGeom<T>::CTILE + 2 * kXBlock * 8;  // tiles, X_{j+2}, M1_{j+1}
+  static constexpr int BASE = 8192;                                            // control block + rings
+};
+
+__device__ __forceinline__ void ch_spin(const volatile int *flag, int need, int32_t *status) {
+  if (ld_acquire_cta_smem(flag) >= need) return;
+  const long long t0 = clock64();
+  while (ld_acquire_cta_smem(flag) < need) {
+    if (clock64() - t0 > kWatchdogCycles) { atomicMax(status, CHUB_STATUS_INTERNAL); return; }
+  }
+}
+
+// LAYOUT: row-major band tiles arrive as two 128-byte-swizzled boxes of [32 rows][16 columns] (lane = row
+// reads 16-byte chunks, conflict free); column-major ones as one plain box [32 columns][32 rows] (lane = row
+// reads 8 bytes per column, conflict free).
+template <typename T, int LAYOUT, bool PROF>
 __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsigned char *smem) {
   constexpr int HALVES = RmGeom<T>::HALVES, BOXC = RmGeom<T>::BOXC, EPC = RmGeom<T>::EPC;
-  constexpr int CTILE = RmGeom<T>::CTILE;
+  constexpr int CTILE = RmGeom<T>::CTILE, SLOT = ChGeom<T>::SLOT;
+  static_assert(kDfD >= 2 && kChTiles == 4, "band warps are dealt block rows modulo 4");
+  static_assert(SLOT % 1024 == 0, "ring slots keep the 1024-byte alignment of the swizzled boxes");
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
   const int T_ = P.T;
   long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
   unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);  // [kDfSlots]
-  double *acc = reinterpret_cast<double *>(smem + 64);                      // [kDfD+1][32]
-  double *pbuf = acc + (kDfD + 1) * kPanel;                                 // [2][32]
-  double *wvec = pbuf + 2 * kPanel;                                         // [32]
-  double *wtb = wvec + kPanel;                                              // [2][32]
-  double *Xs = reinterpret_cast<double *>(smem + 4096);                     // [kDfSlots][kXBlock]
-  unsigned char *tiles = smem + 4096 + ((kDfSlots * kXBlock * 8 + 1023) / 1024) * 1024;  // [kDfSlots][kDfD][CTILE]
+  volatile int *ctl = reinterpret_cast<volatile int *>(smem + 64);
+  volatile int *pdone = ctl;        // p_r is in pbuf for r < *pdone
+  volatile int *xwdone = ctl + 1;   // xw_r = X_r wt_r is in xwb for r < *xwdone
+  volatile int *xprog = ctl + 7;    // block columns whose X (in the ring slot) warp P has taken into registers
+  volatile int *bprog = ctl + 2;    // [4] block columns whose ring slot band warp k has finished reading
+  volatile int *uready = ctl + 8;   // [kChRing] r + 1 once u_r is in ubuf[r % kChRing]
+  double *pbuf = reinterpret_cast<double *>(smem + 512);   // [kChRing][32]
+  double *ubuf = pbuf + kChRing * kPanel;                   // [kChRing][32]
+  double *xwb = ubuf + kChRing * kPanel;                    // [kChRing][32]  xw_r
+  double *wtb = xwb + kChRing * kPanel;                     // [32] staging of wt_r (warp P)
+  double *wsum = wtb + kPanel;                              // [4][32] per band warp: staging of acc_r
+  unsigned char *slots = smem + ChGeom<T>::BASE;            // [kDfSlots][SLOT]
 
   if (tid == 0) {
     for (int i = 0; i < kDfSlots; ++i) mbar_init(&full[i], 1);
     fence_mbar_init();
   }
-  for (int e = tid; e < (kDfD + 1) * kPanel; e += 256) acc[e] = 0.0;
+  if (tid < 32) ctl[tid] = 0;
   named_sync(1, 256);
 
-  // one thread issues everything block column j needs: tiles (j+1..j+d, j) and X_{j+1}
-  auto issue_slot = [&](int j) {
-    if (j < 0 || j >= T_) return;
-    const int slot = j % kDfSlots;
-    void *bar = &full[slot];
-    int ntiles = min(kDfD, T_ - 1 - j);
-    if (ntiles < 0) ntiles = 0;
-    const bool do_x = j + 1 < T_;
-    const unsigned bytes = (unsigned)ntiles * CTILE + (do_x ? kXBlock * 8u : 0u);
-    if (bytes == 0) { mbar_arrive(bar); return; }
-    mbar_arrive_expect_tx(bar, bytes);
-    for (int q = 0; q < ntiles; ++q)
-      for (int h = 0; h < HALVES; ++h)
-        tma_load_2d(tiles + ((size_t)slot * kDfD + q) * CTILE + h * 4096, tmap32,
-                    j * kPanel + h * BOXC, (j + 1 + q) * kPanel, bar);
-    if (do_x) bulk_g2s(Xs + slot * kXBlock, P.ws.X + (int64_t)(j + 1) * kXBlock, kXBlock * 8u, bar);
-  };
-
-  if (warp == kDfD + 1 && elect_one())
-    for (int j = 0; j < kDfSlots - 1; ++j) issue_slot(j);
   if (warp == 0) {
-    wvec[lane] = df_wait_value(P.ws.w + lane, P.status);
-    __syncwarp();
-    const double *X0 = P.ws.X + lane * kXStride;
-    double a0 = 0.0, a1 = 0.0;
+    // ------------------------------------------------------------ C: the critical path
+    const long long t_chain0 = DF_PROF_T();
+    {
+      const double w0 = df_wait_value(P.ws.w + lane, P.status);
+      pbuf[lane] = w0;  // (staging: the mat-vec reads all 32 entries)
+      __syncwarp();
+      const double *X0 = P.ws.X + lane * kXStride;
+      double a0 = 0.0, a1 = 0.0;
 #pragma unroll 8
-    for (int k = 0; k < kPanel; k += 2) {
-      a0 += X0[k] * wvec[k];
-      a1 += X0[k + 1] * wvec[k + 1];
+      for (int k = 0; k < kPanel; k += 2) {
+        a0 = fma(X0[k], pbuf[k], a0);
+        a1 = fma(X0[k + 1], pbuf[k + 1], a1);
+      }
+      __syncwarp();
+      const double p0 = a0 + a1;
+      pbuf[lane] = p0;
+      st_relaxed_f64(P.ws.p + lane, p0);
+      __syncwarp();
+      if (lane == 0) st_release_cta_smem(pdone, 1);
     }
-    const double p0 = a0 + a1;
-    pbuf[lane] = p0;
-    st_relaxed_f64(P.ws.p + lane, p0);
-  }
-  // warp d polls wt one block row ahead without blocking: the load for wt_{j+2} is in flight
-  // while block column j is processed
-  unsigned long long wt_bits = kSentinelBits;
-  if (warp == kDfD && T_ > 1) wt_bits = ld_relaxed_u64(P.ws.w + kPanel + lane);
-  named_sync(1, 256);
-
-  const long long t_chain0 = DF_PROF_T();
-  for (int j = 0; j < T_; ++j) {
-    long long tp = DF_PROF_T();
-    const double *pj = pbuf + (j & 1) * kPanel;
-    if (warp < kDfD) {
-      const int br = j + 1 + warp;
-      if (br < T_) {
+    // u_1 = X_1 wt_1 (block row 1 has no band tile beyond distance 1)
+    double u_first = 0.0;
+    if (T_ > 1) {
+      const double w1 = df_wait_value(P.ws.w + kPanel + lane, P.status);
+      ubuf[kPanel + lane] = w1;  // staging in the slot of u_1
+      __syncwarp();
+      const double *X1 = P.ws.X + kXBlock + lane * kXStride;
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < kPanel; k += 2) {
+        a0 = fma(X1[k], ubuf[kPanel + k], a0);
+        a1 = fma(X1[k + 1], ubuf[kPanel + k + 1], a1);
+      }
+      u_first = a0 + a1;
+      __syncwarp();
+    }
+    for (int j = 0; j + 1 < T_; ++j) {
+      const int r = j + 1;
+      long long tp = DF_PROF_T();
+      mbar_wait(&full[j % kDfSlots], (unsigned)((j / kDfSlots) & 1), P.status);
+      if (lane == 0) DF_PROF_ADD(1, tp);
+      const double *M = reinterpret_cast<const double *>(slots + (size_t)(j % kDfSlots) * SLOT + kChTiles * CTILE +
+                                                         kXBlock * 8) + lane * kXStride;
+      const double *pj = pbuf + (j % kChRing) * kPanel;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int k = 0; k < kPanel; k += 4) {
+        const double2 x = *reinterpret_cast<const double2 *>(M + k);
+        const double2 y = *reinterpret_cast<const double2 *>(M + k + 2);
+        const double2 a = *reinterpret_cast<const double2 *>(pj + k);
+        const double2 b = *reinterpret_cast<const double2 *>(pj + k + 2);
+        a0 = fma(x.x, a.x, a0);
+        a1 = fma(x.y, a.y, a1);
+        a2 = fma(y.x, b.x, a2);
+        a3 = fma(y.y, b.y, a3);
+      }
+      tp = DF_PROF_T();
+      double u = u_first;
+      if (r > 1) {
+        ch_spin(uready + (r % kChRing), r + 1, P.status);
+        u = ubuf[(r % kChRing) * kPanel + lane];
+        if (lane == 0) DF_PROF_ADD(2, tp);
+        tp = DF_PROF_T();
+        ch_spin(xwdone, r + 1, P.status);
+        u += xwb[(r % kChRing) * kPanel + lane];
+        if (lane == 0) DF_PROF_ADD(6, tp);
+      }
+      const double pr = u - ((a0 + a1) + (a2 + a3));
+      pbuf[(r % kChRing) * kPanel + lane] = pr;
+      st_relaxed_f64(P.ws.p + (int64_t)r * kPanel + lane, pr);  // publish: the data is its own flag
+      __syncwarp();
+      if (lane == 0) {
+        st_release_cta_smem(pdone, r + 1);
+        DF_TRACE(2, r);
+      }
+    }
+    if (lane == 0) DF_PROF_ADD(0, t_chain0);
+  } else if (warp <= 4) {
+    // ------------------------------------------------------------ B: band tiles and u_r
+    const int k4 = warp - 1;
+    double acc = 0.0;
+    double *ws_ = wsum + k4 * kPanel;
+    for (int j = 0; j < T_; ++j) {
+      const int r = j + 2 + ((k4 - j) & 3);  // my block row among j+2 .. j+5:  r = k4 + 2 (mod 4)
+      if (r < T_) {
+        if (j == 0 || r - j == kDfD) acc = 0.0;  // first tile of this block row
+        ch_spin(pdone, j + 1, P.status);
+        long long tp = DF_PROF_T();
         mbar_wait(&full[j % kDfSlots], (unsigned)((j / kDfSlots) & 1), P.status);
-        if (tid == 0) DF_PROF_ADD(1, tp);
-        const unsigned char *tb = tiles + ((size_t)(j % kDfSlots) * kDfD + warp) * CTILE;
+        if (lane == 0 && k4 == 0) DF_PROF_ADD(3, tp);
+        const unsigned char *slot = slots + (size_t)(j % kDfSlots) * SLOT;
+        const unsigned char *tb = slot + (size_t)(r - j - 2) * CTILE;
+        const double *pj = pbuf + (j % kChRing) * kPanel;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        if (LAYOUT == CHUB_COL_MAJOR) {
+          const T *tc = reinterpret_cast<const T *>(tb) + lane;  // element (row = lane, column k) at [k][lane]
+#pragma unroll
+          for (int k = 0; k < kPanel; k += 4) {
+            const double2 pp = *reinterpret_cast<const double2 *>(pj + k);
+            const double2 pq = *reinterpret_cast<const double2 *>(pj + k + 2);
+            a0 = fma((double)tc[k * kPanel], pp.x, a0);
+            a1 = fma((double)tc[(k + 1) * kPanel], pp.y, a1);
+            a2 = fma((double)tc[(k + 2) * kPanel], pq.x, a2);
+            a3 = fma((double)tc[(k + 3) * kPanel], pq.y, a3);
+          }
+        } else {
 #pragma unroll
         for (int h = 0; h < HALVES; ++h) {
           const unsigned char *rowp = tb + h * 4096 + lane * 128;
@@ -830,74 +950,131 @@ __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsign
             const int k0 = h * BOXC + c * EPC;
             if (EPC == 2) {
               const double2 pp = *reinterpret_cast<const double2 *>(pj + k0);
-              if (c & 1) { a2 += (double)x[0] * pp.x; a3 += (double)x[1] * pp.y; }
-              else       { a0 += (double)x[0] * pp.x; a1 += (double)x[1] * pp.y; }
+              if (c & 1) { a2 = fma((double)x[0], pp.x, a2); a3 = fma((double)x[1], pp.y, a3); }
+              else       { a0 = fma((double)x[0], pp.x, a0); a1 = fma((double)x[1], pp.y, a1); }
             } else {
               const double2 pp = *reinterpret_cast<const double2 *>(pj + k0);
               const double2 pq = *reinterpret_cast<const double2 *>(pj + k0 + 2);
-              a0 += (double)x[0] * pp.x;
-              a1 += (double)x[1] * pp.y;
-              a2 += (double)x[2 % EPC] * pq.x;
-              a3 += (double)x[3 % EPC] * pq.y;
+              a0 = fma((double)x[0], pp.x, a0);
+              a1 = fma((double)x[1], pp.y, a1);
+              a2 = fma((double)x[2 % EPC], pq.x, a2);
+              a3 = fma((double)x[3 % EPC], pq.y, a3);
             }
           }
         }
-        acc[(br % (kDfD + 1)) * kPanel + lane] -= (a0 + a1) + (a2 + a3);
+        }
+        acc -= (a0 + a1) + (a2 + a3);
+        if (r - j == 2) {
+          // last band tile of block row r: ua_r = X_r acc; X_r came with this block column
+          ws_[lane] = acc;
+          __syncwarp();
+          const double *X = reinterpret_cast<const double *>(slot + kChTiles * CTILE) + lane * kXStride;
+          double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+#pragma unroll
+          for (int k = 0; k < kPanel; k += 4) {
+            const double2 x = *reinterpret_cast<const double2 *>(X + k);
+            const double2 y = *reinterpret_cast<const double2 *>(X + k + 2);
+            const double2 a = *reinterpret_cast<const double2 *>(ws_ + k);
+            const double2 b = *reinterpret_cast<const double2 *>(ws_ + k + 2);
+            b0 = fma(x.x, a.x, b0);
+            b1 = fma(x.y, a.y, b1);
+            b2 = fma(y.x, b.x, b2);
+            b3 = fma(y.y, b.y, b3);
+          }
+          ubuf[(r % kChRing) * kPanel + lane] = (b0 + b1) + (b2 + b3);
+          __syncwarp();
+          if (lane == 0) st_release_cta_smem(uready + (r % kChRing), r + 1);
+        }
       }
-      if (tid == 0) DF_PROF_ADD(2, tp);
-    } else if (warp == kDfD) {
-      if (j + 1 < T_) {
-        long long tq = DF_PROF_T();
-        const double wt = wt_bits != kSentinelBits
-                              ? __longlong_as_double((long long)wt_bits)
-                              : df_wait_value(P.ws.w + (int64_t)(j + 1) * kPanel + lane, P.status);
-        wtb[((j + 1) & 1) * kPanel + lane] = wt;
-        if (j + 2 < T_) wt_bits = ld_relaxed_u64(P.ws.w + (int64_t)(j + 2) * kPanel + lane);
-        __syncwarp();
-        if (lane == 0) { DF_PROF_ADD(4, tq); DF_TRACE(1, j + 1); }
-      }
-    } else if (warp == kDfD + 1) {
-      if (elect_one()) issue_slot(j + kDfSlots - 1);
-    } else if (kDfPf > 0) {
-      // the spare warp: the ring's lead (kDfSlots-1 block columns) is shorter than the DRAM latency
-      // while every SM streams, so the band tiles of block column j + kDfSlots-1 + kDfPf go to L2 now
-      const int jp = j + kDfSlots - 1 + kDfPf;
-      const int np = min(kDfD, T_ - 1 - jp);
-      if (lane < np * HALVES)
-        tma_prefetch_2d(tmap32, jp * kPanel + (lane % HALVES) * BOXC, (jp + 1 + lane / HALVES) * kPanel);
-    }
-    tp = DF_PROF_T();
-    named_sync(1, 256);
-    if (warp == 0 && j + 1 < T_) {
-      const int r = j + 1;
-      double *a = acc + (r % (kDfD + 1)) * kPanel;
-      wvec[lane] = wtb[(r & 1) * kPanel + lane] + a[lane];
-      a[lane] = 0.0;
       __syncwarp();
-      if (tid == 0) DF_PROF_ADD(3, tp);
-      tp = DF_PROF_T();
-      const double *X = Xs + (j % kDfSlots) * kXBlock + lane * kXStride;
+      if (lane == 0) st_release_cta_smem(bprog + k4, j + 1);  // my reads of ring slot j % kDfSlots are done
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------ P: wt_r from the workers (global), xw_r = X_r wt_r
+    unsigned long long b0 = kSentinelBits, b1 = kSentinelBits;
+    if (T_ > 2) b0 = ld_relaxed_u64(P.ws.w + 2 * kPanel + lane);
+    if (T_ > 3) b1 = ld_relaxed_u64(P.ws.w + 3 * kPanel + lane);
+    for (int r = 2; r < T_; ++r) {
+      // X_r travels with block column r - 2: my row of it goes into registers, the slot is released
+      const int jx = r - 2;
+      mbar_wait(&full[jx % kDfSlots], (unsigned)((jx / kDfSlots) & 1), P.status);
+      const double *X = reinterpret_cast<const double *>(slots + (size_t)(jx % kDfSlots) * SLOT + kChTiles * CTILE) +
+                        lane * kXStride;
+      double2 xr[kPanel / 2];
+#pragma unroll
+      for (int k = 0; k < kPanel / 2; ++k) xr[k] = *reinterpret_cast<const double2 *>(X + 2 * k);
+      __syncwarp();
+      if (lane == 0) st_release_cta_smem(xprog, jx + 1);
+      long long tq = DF_PROF_T();
+      const double *nx = r + 1 < T_ ? P.ws.w + (int64_t)(r + 1) * kPanel + lane : nullptr;
+      const double wt = df_wait_value2(P.ws.w + (int64_t)r * kPanel + lane, nx, b0, b1, P.status);
+      b0 = b1;
+      b1 = r + 2 < T_ ? ld_relaxed_u64(P.ws.w + (int64_t)(r + 2) * kPanel + lane) : kSentinelBits;
+      if (lane == 0) { DF_PROF_ADD(5, tq); DF_TRACE(1, r); }
+      wtb[lane] = wt;
+      __syncwarp();
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-      for (int k = 0; k < kPanel; k += 4) {
-        const double2 x = *reinterpret_cast<const double2 *>(X + k);
-        const double2 y = *reinterpret_cast<const double2 *>(X + k + 2);
-        const double2 u = *reinterpret_cast<const double2 *>(wvec + k);
-        const double2 z = *reinterpret_cast<const double2 *>(wvec + k + 2);
-        a0 += x.x * u.x;
-        a1 += x.y * u.y;
-        a2 += y.x * z.x;
-        a3 += y.y * z.y;
+      for (int k = 0; k < kPanel / 2; k += 2) {
+        const double2 a = *reinterpret_cast<const double2 *>(wtb + 2 * k);
+        const double2 b = *reinterpret_cast<const double2 *>(wtb + 2 * k + 2);
+        a0 = fma(xr[k].x, a.x, a0);
+        a1 = fma(xr[k].y, a.y, a1);
+        a2 = fma(xr[k + 1].x, b.x, a2);
+        a3 = fma(xr[k + 1].y, b.y, a3);
       }
-      const double pr = (a0 + a1) + (a2 + a3);
-      pbuf[(r & 1) * kPanel + lane] = pr;
-      st_relaxed_f64(P.ws.p + (int64_t)r * kPanel + lane, pr);
-      if (tid == 0) { DF_PROF_ADD(5, tp); DF_TRACE(2, r); }
+      // xwb[r % 8] was last read for p_{r-8}: C is long past it (p_{r-1} needs ua/xw of r-1 only)
+      xwb[(r % kChRing) * kPanel + lane] = (a0 + a1) + (a2 + a3);
+      __syncwarp();
+      if (lane == 0) st_release_cta_smem(xwdone, r + 1);
     }
-    named_sync(1, 256);
+  } else if (warp == 6) {
+    // ------------------------------------------------------------ T: TMA loads, block column jj -> slot jj % 4
+    for (int jj = 0; jj < T_; ++jj) {
+      if (kDfPf > 0) {  // band tiles of block column jj + kDfPf -> L2 (all lanes; nothing to wait for)
+        const int jp = jj + kDfPf;
+        const int np = min(kChTiles, T_ - 2 - jp);
+        if (LAYOUT == CHUB_COL_MAJOR) {
+          if (lane < np) tma_prefetch_2d(tmap32, (jp + 2 + lane) * kPanel, jp * kPanel);
+        } else if (lane < np * HALVES) {
+          tma_prefetch_2d(tmap32, jp * kPanel + (lane % HALVES) * BOXC, (jp + 2 + lane / HALVES) * kPanel);
+        }
+      }
+      if (elect_one()) {
+        if (jj >= kDfSlots) {
+          // the slot held block column jj - 4: read by the band warps (tiles, X) and by C (M1 -> p_{jj-3})
+          const int done = jj - kDfSlots + 1;
+          for (int k = 0; k < 4; ++k) ch_spin(bprog + k, done, P.status);
+          ch_spin(pdone, min(done + 1, T_), P.status);
+          if (done + 1 < T_) ch_spin(xprog, done, P.status);  // (X_{jj-2} travelled with block column jj - 4)
+        }
+        const int slot = jj % kDfSlots;
+        void *bar = &full[slot];
+        unsigned char *sb = slots + (size_t)slot * SLOT;
+        int ntiles = min(kChTiles, T_ - 2 - jj);
+        if (ntiles < 0) ntiles = 0;
+        const bool do_x = jj + 2 < T_, do_m = jj + 1 < T_;
+        const unsigned bytes = (unsigned)ntiles * CTILE + (do_x ? kXBlock * 8u : 0u) + (do_m ? kXBlock * 8u : 0u);
+        if (bytes == 0) {
+          mbar_arrive(bar);
+        } else {
+          mbar_arrive_expect_tx(bar, bytes);
+          if (do_m) bulk_g2s(sb + kChTiles * CTILE + kXBlock * 8, P.ws.M1 + (int64_t)(jj + 1) * kXBlock, kXBlock * 8u, bar);
+          for (int q = 0; q < ntiles; ++q) {
+            if (LAYOUT == CHUB_COL_MAJOR) {  // (coordinates: row first -- rows are the contiguous dimension)
+              tma_load_2d(sb + (size_t)q * CTILE, tmap32, (jj + 2 + q) * kPanel, jj * kPanel, bar);
+            } else {
+              for (int h = 0; h < HALVES; ++h)
+                tma_load_2d(sb + (size_t)q * CTILE + h * 4096, tmap32, jj * kPanel + h * BOXC, (jj + 2 + q) * kPanel, bar);
+            }
+          }
+          if (do_x) bulk_g2s(sb + kChTiles * CTILE, P.ws.X + (int64_t)(jj + 2) * kXBlock, kXBlock * 8u, bar);
+        }
+      }
+      __syncwarp();
+    }
   }
-  if (tid == 0) DF_PROF_ADD(0, t_chain0);
-  if (P.prof && (tid == 0 || tid == kDfD * 32)) {
+  if (P.prof && lane == 0 && (warp == 0 || warp == 1 || warp == 5)) {
     for (int i = 0; i < 8; ++i)
       if (pacc[i]) P.prof[(size_t)blockIdx.x * 16 + i] = pacc[i];
   }
@@ -905,8 +1082,87 @@ __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsign
 
 template <typename T>
 inline size_t df_chain_rm_smem() {
-  return 4096 + ((size_t)(kDfSlots * kXBlock * 8 + 1023) / 1024) * 1024 +
-         (size_t)kDfSlots * kDfD * RmGeom<T>::CTILE;
+  return (size_t)ChGeom<T>::BASE + (size_t)kDfSlots * ChGeom<T>::SLOT;
+}
+
+// ---- coefficient warp of a worker CTA (shared by the row-major and the column-major workers)
+template <typename T, bool UPDATE, bool PROF>
+__device__ __forceinline__ void df_coef_warp(T *v, const DfParams &P, double *coef, volatile int *prog,
+                                             volatile int *cprog, volatile int *pprog, int wkr, int lane) {
+  const int n = P.n, T_ = P.T, Wk = P.Wk;
+  long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // ---------------- coefficient warp (software-pipelined: the poll of block column s+1 is in
+  // flight while the coefficients of block column s are formed).  A ring slot is reused once
+  // every row warp has finished the step that last read it (prog[]); finished warps have left.
+  double t_run = 1.0, S_run = 1.0;
+  unsigned long long b0 = ld_relaxed_u64(P.ws.p + lane);
+  unsigned long long b1 = T_ > 1 ? ld_relaxed_u64(P.ws.p + kPanel + lane) : kSentinelBits;
+  double ndg = P.ws.dg[lane];
+  for (int pan = 0; pan < T_; ++pan) {
+    const int slot = pan % kDfCoefRing;
+    const int k = pan * kPanel + lane;
+    long long tq = DF_PROF_T();
+    // two polls in flight (this block column and the next): the chain may run at two block columns per
+    // round trip of a poll
+    const double pk = df_wait_value2(P.ws.p + k, pan + 1 < T_ ? P.ws.p + k + kPanel : nullptr, b0, b1, P.status);
+    b0 = b1;
+    b1 = pan + 2 < T_ ? ld_relaxed_u64(P.ws.p + k + 2 * kPanel) : kSentinelBits;
+    const double dg = ndg;
+    if (pan + 1 < T_) ndg = P.ws.dg[k + kPanel];
+    if (lane == 0) DF_PROF_ADD(6, tq);
+    if (lane == 0 && wkr == 0) DF_TRACE(3, pan);
+    if (pan >= kDfCoefRing) {
+      // slot last used by block column pan-8, read for the last time at step pan-8+d
+      const int need = pan - kDfCoefRing + kDfD + 1;
+      const long long t0 = clock64();
+      while (__reduce_min_sync(0xffffffffu, ld_acquire_cta_smem(prog + lane)) < need) {
+        if (clock64() - t0 > kWatchdogCycles) { atomicMax(P.status, CHUB_STATUS_INTERNAL); break; }
+      }
+    }
+    double *cf = coef + (size_t)slot * 4 * kPanel;
+    cf[lane] = pk;
+    // p alone is enough for the residual w (and for the hand-over to the chain, which is on the
+    // chain <-> worker latency loop): publish it before the scan / rsqrt of the coefficients
+    __syncwarp();
+    if (lane == 0) st_release_cta_smem(pprog, pan + 1);
+    if (UPDATE) {
+      double incl = pk * pk;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 0.0;
+      const double tk = t_run + excl, tk1 = t_run + incl;
+      const unsigned negmask = __ballot_sync(0xffffffffu, dg < 0.0);
+      const double sgn = dg < 0.0 ? -1.0 : 1.0;
+      const double rinv = rsqrt(tk * tk1);
+      const double ck = sgn * tk * rinv, sigk = sgn * pk * rinv;
+      cf[kPanel + lane] = ck;
+      cf[2 * kPanel + lane] = sigk;
+      cf[3 * kPanel + lane] = fabs(dg) * tk1 * rinv;
+      __syncwarp();
+      if (lane == 0) st_release_cta_smem(cprog, pan + 1);
+      if (wkr == pan % Wk && k < n) {  // one worker per panel leaves rotg's z_k in v[k]
+        const double Sk = (__popc(negmask & ((1u << lane) - 1u)) & 1) ? -S_run : S_run;
+        const double nuk = Sk * dg * pk / sqrt(tk);
+        const double sk = Sk * sgn * pk / sqrt(tk1);
+        v[k] = (T)rotg_z<double>(dg, nuk, ck, sk);
+      }
+      t_run = __shfl_sync(0xffffffffu, tk1, 31);
+      if (__popc(negmask) & 1) S_run = -S_run;
+    } else {
+      __syncwarp();
+      if (lane == 0) st_release_cta_smem(cprog, pan + 1);
+    }
+    if (lane == 0 && wkr == 0) DF_TRACE(4, pan);
+    if (lane == 0) DF_PROF_ADD(7, tq);
+  }
+  if (P.prof && lane == 0) {
+    P.prof[(size_t)blockIdx.x * 16 + 6] = pacc[6];
+    P.prof[(size_t)blockIdx.x * 16 + 7] = pacc[7];
+  }
 }
 
 // ---- worker CTAs
@@ -941,77 +1197,7 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
   if (warp > nrw) return;
 
   if (warp == nrw) {
-    // ---------------- coefficient warp (software-pipelined: the poll of block column s+1 is in
-    // flight while the coefficients of block column s are formed).  A ring slot is reused once
-    // every row warp has finished the step that last read it (prog[]); finished warps have left.
-    double t_run = 1.0, S_run = 1.0;
-    unsigned long long nbits = ld_relaxed_u64(P.ws.p + lane);
-    double ndg = P.ws.dg[lane];
-    for (int pan = 0; pan < T_; ++pan) {
-      const int slot = pan % kDfCoefRing;
-      const int k = pan * kPanel + lane;
-      long long tq = DF_PROF_T();
-      const double pk = nbits != kSentinelBits ? __longlong_as_double((long long)nbits)
-                                               : df_wait_value(P.ws.p + k, P.status);
-      const double dg = ndg;
-      if (pan + 1 < T_) {
-        nbits = ld_relaxed_u64(P.ws.p + k + kPanel);
-        ndg = P.ws.dg[k + kPanel];
-      }
-      if (lane == 0) DF_PROF_ADD(6, tq);
-      if (lane == 0 && wkr == 0) DF_TRACE(3, pan);
-      if (pan >= kDfCoefRing) {
-        // slot last used by block column pan-8, read for the last time at step pan-8+d
-        const int need = pan - kDfCoefRing + kDfD + 1;
-        const long long t0 = clock64();
-        while (__reduce_min_sync(0xffffffffu, ld_acquire_cta_smem(prog + lane)) < need) {
-          if (clock64() - t0 > kWatchdogCycles) { atomicMax(P.status, CHUB_STATUS_INTERNAL); break; }
-        }
-      }
-      double *cf = coef + (size_t)slot * 4 * kPanel;
-      cf[lane] = pk;
-      // p alone is enough for the residual w (and for the hand-over to the chain, which is on the
-      // chain <-> worker latency loop): publish it before the scan / rsqrt of the coefficients
-      __syncwarp();
-      if (lane == 0) st_release_cta_smem(pprog, pan + 1);
-      if (UPDATE) {
-        double incl = pk * pk;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const double y = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += y;
-        }
-        double excl = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) excl = 0.0;
-        const double tk = t_run + excl, tk1 = t_run + incl;
-        const unsigned negmask = __ballot_sync(0xffffffffu, dg < 0.0);
-        const double sgn = dg < 0.0 ? -1.0 : 1.0;
-        const double rinv = rsqrt(tk * tk1);
-        const double ck = sgn * tk * rinv, sigk = sgn * pk * rinv;
-        cf[kPanel + lane] = ck;
-        cf[2 * kPanel + lane] = sigk;
-        cf[3 * kPanel + lane] = fabs(dg) * tk1 * rinv;
-        __syncwarp();
-        if (lane == 0) st_release_cta_smem(cprog, pan + 1);
-        if (wkr == pan % Wk && k < n) {  // one worker per panel leaves rotg's z_k in v[k]
-          const double Sk = (__popc(negmask & ((1u << lane) - 1u)) & 1) ? -S_run : S_run;
-          const double nuk = Sk * dg * pk / sqrt(tk);
-          const double sk = Sk * sgn * pk / sqrt(tk1);
-          v[k] = (T)rotg_z<double>(dg, nuk, ck, sk);
-        }
-        t_run = __shfl_sync(0xffffffffu, tk1, 31);
-        if (__popc(negmask) & 1) S_run = -S_run;
-      } else {
-        __syncwarp();
-        if (lane == 0) st_release_cta_smem(cprog, pan + 1);
-      }
-      if (lane == 0 && wkr == 0) DF_TRACE(4, pan);
-      if (lane == 0) DF_PROF_ADD(7, tq);
-    }
-    if (P.prof && lane == 0) {
-      P.prof[(size_t)blockIdx.x * 16 + 6] = pacc[6];
-      P.prof[(size_t)blockIdx.x * 16 + 7] = pacc[7];
-    }
+    df_coef_warp<T, UPDATE, PROF>(v, P, coef, prog, cprog, pprog, wkr, lane);
     return;
   }
 
@@ -1239,11 +1425,304 @@ df_kernel_rm(T *L, T *v, DfParams P, const __grid_constant__ CUtensorMap tmap8,
   extern __shared__ __align__(1024) unsigned char df_smem[];
   if (*P.status != 0) return;  // check_diag failed: L and v stay untouched
   if (blockIdx.x == 0) {
-    if (threadIdx.x < 256) df_chain_rm<T, PROF>(P, &tmap32, df_smem);
+    if (threadIdx.x < 256) df_chain_rm<T, CHUB_ROW_MAJOR, PROF>(P, &tmap32, df_smem);
   } else {
     df_worker_rm<T, UPDATE, PROF>(L, v, P, &tmap8, df_smem);
   }
 }
+
+// =====================================================================================
+// Column-major (the reference's recommended layout, _seeger.py:65-68): native tensor-map workers
+// =====================================================================================
+// Rows are the contiguous dimension, so a warp owns a whole block row (32 rows, lane = row) and moves one
+// [32 rows x 32 columns] box per step with ONE TMA instruction (256-byte runs, no swizzle: lane = row reads
+// 8 bytes per column, conflict free).  The row's residual chain over the 32 columns is cut into four
+// independent 8-column segments (prefix sums in registers; this kernel has few threads per CTA, so each
+// thread may keep the whole row segment of the tile), combined by three subtractions -- no shuffles.  Per
+// byte this needs a quarter of the instructions of the row-major mapping.  Same dataflow otherwise: same
+// chain CTA (band tiles read through a column-major box), same coefficient warp, same delay of d steps
+// inside the band, ragged diagonal tile written with predicated global stores (coalesced: for a fixed
+// column the 32 lanes are 32 consecutive rows).
+constexpr int kCmStages = 4;
+constexpr int kCmMaxQ = 6;  // row warps (block rows) per worker: n <= 147 * 6 * 32 = 28224
+
+template <typename T>
+struct CmGeom {
+  static constexpr int TILE = kPanel * kPanel * (int)sizeof(T);  // 8 KB / 4 KB
+};
+
+template <typename T, bool UPDATE, bool PROF>
+__device__ void df_worker_cm(T *L, T *v, const DfParams &P, const CUtensorMap *tmapc, unsigned char *smem) {
+  constexpr int TILE = CmGeom<T>::TILE;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int wkr = blockIdx.x - 1;
+  const int n = P.n, T_ = P.T, Wk = P.Wk, nrw = P.nw;
+  const int64_t ld = P.ld;
+  long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);      // [nrw][kCmStages]
+  volatile int *prog = reinterpret_cast<volatile int *>(smem + 256);             // [32] steps finished per row warp
+  volatile int *cprog = prog + 32;
+  volatile int *pprog = prog + 33;
+  double *coef = reinterpret_cast<double *>(smem + 2048);                        // [kDfCoefRing][4][32]
+  unsigned char *stages = smem + 2048 + kDfCoefRing * 4 * kPanel * 8;            // [nrw][kCmStages][TILE]
+
+  if (tid == 0) {
+    for (int i = 0; i < kCmStages * nrw; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) prog[tid] = tid < nrw ? 0 : 0x7fffffff;
+  if (tid == 0) { *cprog = 0; *pprog = 0; }
+  __syncthreads();
+  if (warp > nrw) return;
+  if (warp == nrw) {
+    df_coef_warp<T, UPDATE, PROF>(v, P, coef, prog, cprog, pprog, wkr, lane);
+    return;
+  }
+
+  // ---------------- row warps: warp = block row b (32 rows), lane = row
+  const int b = wkr + warp * Wk;
+  const int64_t row0 = (int64_t)b * kPanel;
+  if (row0 >= n) {
+    if (lane == 0) prog[warp] = 0x7fffffff;
+    return;
+  }
+  const int64_t row = row0 + lane;
+  const bool valid = row < n;
+  const int last_step = min(T_ + kDfD - 1, b + kDfD);
+  double w = valid ? P.ws.v0[row] : 0.0;
+  const bool prof_me = PROF && P.prof && lane == 0 && (warp + 1 >= nrw || (int64_t)(b + Wk) * kPanel >= n);
+  unsigned long long *myfull = full + warp * kCmStages;
+  unsigned char *mytile = stages + (size_t)warp * (kCmStages * TILE);
+
+  auto issue_load = [&](int s) {  // elected lane
+    if (s > last_step) return;
+    void *bar = &myfull[s % kCmStages];
+    const int pan = df_panel_at<kDfD>(b, s);
+    if (pan < 0) { mbar_arrive(bar); return; }
+    mbar_arrive_expect_tx(bar, (unsigned)TILE);
+    tma_load_2d(mytile + (s % kCmStages) * TILE, tmapc, (int)row0, pan * kPanel, bar);
+  };
+
+  auto wait_flag = [&](volatile int *flag, int need) {
+    if (ld_acquire_cta_smem(flag) < need) {
+      const long long t0 = clock64();
+      while (ld_acquire_cta_smem(flag) < need) {
+        if (clock64() - t0 > kWatchdogCycles) { atomicMax(P.status, CHUB_STATUS_INTERNAL); break; }
+      }
+    }
+  };
+
+  if (elect_one()) {
+    issue_load(0);
+    issue_load(1);
+  }
+  __syncwarp();
+  const long long t_wk0 = DF_PROF_T();
+  for (int s = 0; s <= last_step; ++s) {
+    long long tp = DF_PROF_T();
+    if (elect_one()) {
+      bulk_wait_read<1>();  // the store of step s-2 has left its stage
+      issue_load(s + 2);
+    }
+    __syncwarp();
+    if (prof_me) DF_PROF_ADD(2, tp);
+    tp = DF_PROF_T();
+    mbar_wait(&myfull[s % kCmStages], (unsigned)((s / kCmStages) & 1), P.status);
+    if (prof_me) DF_PROF_ADD(1, tp);
+    tp = DF_PROF_T();
+    // step s is gated on p_s: p_s published implies that the chain has consumed everything step s overwrites
+    wait_flag(pprog, min(s, T_ - 1) + 1);
+    if (prof_me) DF_PROF_ADD(4, tp);
+    tp = DF_PROF_T();
+    const int pan = df_panel_at<kDfD>(b, s);
+    bool do_store = false;
+    if (pan >= 0) {
+      T *tile = reinterpret_cast<T *>(mytile + (s % kCmStages) * TILE) + lane;  // element (lane, k) at tile[k * 32]
+      const double *cf = coef + (size_t)(pan % kDfCoefRing) * 4 * kPanel;
+      const bool diag = (pan == b);  // columns c0 + k, c0 = row0: k < lane below, k == lane on the diagonal
+      double lo[kPanel], pre[kPanel], tot[4];
+#pragma unroll
+      for (int k = 0; k < kPanel; ++k) lo[k] = (double)tile[k * kPanel];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        double run = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const int k = 8 * q + j;
+          const double2 pp = *reinterpret_cast<const double2 *>(cf + k);
+          pre[k] = run;
+          if (!diag || k < lane) run = fma(lo[k], pp.x, run);
+          pre[k + 1] = run;
+          if (!diag || k + 1 < lane) run = fma(lo[k + 1], pp.y, run);
+        }
+        tot[q] = run;
+      }
+      double wq[4];
+      wq[0] = w;
+      wq[1] = wq[0] - tot[0];
+      wq[2] = wq[1] - tot[1];
+      wq[3] = wq[2] - tot[2];
+      w = wq[3] - tot[3];
+      // hand the residual over to the chain after the last far-left block column
+      if (s == b - kDfD - 1 && valid) {
+        st_relaxed_f64(P.ws.w + row, df_sanitize(w));
+        if (lane == 0) DF_TRACE(0, b);
+      }
+      if (UPDATE) {
+        wait_flag(cprog, pan + 1);
+        if (!diag) {
+#pragma unroll
+          for (int k = 0; k < kPanel; k += 2) {
+            const double2 c2 = *reinterpret_cast<const double2 *>(cf + kPanel + k);
+            const double2 s2 = *reinterpret_cast<const double2 *>(cf + 2 * kPanel + k);
+            tile[k * kPanel] = (T)fma(c2.x, lo[k], s2.x * (wq[k >> 3] - pre[k]));
+            tile[(k + 1) * kPanel] = (T)fma(c2.y, lo[k + 1], s2.y * (wq[k >> 3] - pre[k + 1]));
+          }
+          do_store = true;
+        } else if (valid) {  // ragged diagonal tile: straight to global memory, nothing above the diagonal
+          T *gp = L + row + (int64_t)row0 * ld;  // (row, row0 + k) at gp[k * ld]
+#pragma unroll
+          for (int k = 0; k < kPanel; ++k) {
+            if (k < lane) gp[(int64_t)k * ld] = (T)fma(cf[kPanel + k], lo[k], cf[2 * kPanel + k] * (wq[k >> 3] - pre[k]));
+            else if (k == lane) gp[(int64_t)k * ld] = (T)cf[3 * kPanel + k];
+          }
+        }
+      }
+    }
+    if (prof_me) DF_PROF_ADD(3, tp);
+    tp = DF_PROF_T();
+    fence_proxy_async();  // my generic-proxy writes -> visible to the TMA (async proxy) store
+    __syncwarp();
+    if (elect_one()) {
+      prog[warp] = s >= last_step ? 0x7fffffff : s + 1;
+      if (do_store) tma_store_2d(tmapc, (int)row0, pan * kPanel, mytile + (s % kCmStages) * TILE);
+      bulk_commit();
+    }
+    __syncwarp();
+    if (prof_me) DF_PROF_ADD(5, tp);
+  }
+  if (prof_me) DF_PROF_ADD(0, t_wk0);
+  if (elect_one()) bulk_wait_all<0>();
+  if (prof_me) {
+    for (int i = 0; i < 6; ++i) P.prof[(size_t)blockIdx.x * 16 + i] = pacc[i];
+  }
+}
+
+template <typename T>
+inline size_t df_worker_cm_smem(int nrw) {
+  return 2048 + (size_t)kDfCoefRing * 4 * kPanel * 8 + (size_t)kCmStages * nrw * CmGeom<T>::TILE;
+}
+
+constexpr int kCmMaxThreads = 256;  // chain: 8 warps; workers: kCmMaxQ row warps + coefficient warp
+
+template <typename T, bool UPDATE, bool PROF>
+__global__ void __launch_bounds__(kCmMaxThreads, 1)
+df_kernel_cm(T *L, T *v, DfParams P, const __grid_constant__ CUtensorMap tmapc) {
+  extern __shared__ __align__(1024) unsigned char df_smem[];
+  if (*P.status != 0) return;  // check_diag failed: L and v stay untouched
+  if (blockIdx.x == 0) df_chain_rm<T, CHUB_COL_MAJOR, PROF>(P, &tmapc, df_smem);
+  else df_worker_cm<T, UPDATE, PROF>(L, v, P, &tmapc, df_smem);
+}
+
+// ---- downdate sweep, column-major: one warp per block row (lane = row), tiles from the diagonal to
+// column 0 through a ring of TMA boxes with the block column's (c, s, sgn) riding along.  The reverse sweep
+// (_seeger_impl_cython.pyx:285-330, row-independent form of SURVEY A.3) is a 32-long dependent FMA chain per
+// tile and lane; eight warps per SM hide it.
+constexpr int kSwCmStages = 3;
+
+template <typename T>
+struct SwCmGeom {
+  static constexpr int STAGE = CmGeom<T>::TILE + 1024;  // tile + (c, s, sgn)[32] doubles (768 B, padded)
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) dd_sweep_cm_kernel(T *L, int n, int64_t ld, LargeWs ws, const int32_t *status,
+                                                          const __grid_constant__ CUtensorMap tmapc) {
+  constexpr int TILE = CmGeom<T>::TILE, STAGE = SwCmGeom<T>::STAGE;
+  extern __shared__ __align__(1024) unsigned char sw_smem[];
+  if (*status != 0) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int T_ = (n + 31) / 32;
+  const int b = T_ - 1 - ((int)blockIdx.x * 4 + warp);  // longest rows first
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(sw_smem) + warp * kSwCmStages;
+  unsigned char *mystage = sw_smem + 1024 + (size_t)warp * kSwCmStages * STAGE;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4 * kSwCmStages; ++i) mbar_init(reinterpret_cast<unsigned long long *>(sw_smem) + i, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (b < 0) return;
+  const int64_t row0 = (int64_t)b * kPanel, row = row0 + lane;
+  const bool valid = row < n;
+  const int nsteps = b + 1;  // tiles b, b-1, ..., 0
+
+  auto issue_load = [&](int s) {  // elected lane
+    if (s >= nsteps) return;
+    const int pan = b - s;
+    void *bar = &full[s % kSwCmStages];
+    unsigned char *stg = mystage + (size_t)(s % kSwCmStages) * STAGE;
+    mbar_arrive_expect_tx(bar, (unsigned)TILE + 768u);
+    tma_load_2d(stg, &tmapc, (int)row0, pan * kPanel, bar);
+    bulk_g2s(stg + TILE, ws.c + pan * kPanel, 256u, bar);
+    bulk_g2s(stg + TILE + 256, ws.sg + pan * kPanel, 256u, bar);
+    bulk_g2s(stg + TILE + 512, ws.dn + pan * kPanel, 256u, bar);
+  };
+
+  if (elect_one()) {
+    issue_load(0);
+    issue_load(1);
+  }
+  __syncwarp();
+  double x = 0.0;  // x_i carried from the tile to the right
+  for (int s = 0; s < nsteps; ++s) {
+    if (elect_one()) {
+      bulk_wait_read<0>();  // the store of step s-1 has left its stage (= the stage of step s+2)
+      issue_load(s + 2);
+    }
+    __syncwarp();
+    mbar_wait(&full[s % kSwCmStages], (unsigned)((s / kSwCmStages) & 1), const_cast<int32_t *>(status));
+    const int pan = b - s;
+    unsigned char *stg = mystage + (size_t)(s % kSwCmStages) * STAGE;
+    T *tile = reinterpret_cast<T *>(stg) + lane;  // element (lane, k) at tile[k * 32]
+    const double *cf = reinterpret_cast<const double *>(stg + TILE);
+    const bool diag = (s == 0);
+    double lnew[kPanel];
+#pragma unroll
+    for (int k = kPanel - 1; k >= 0; --k) {
+      const double lo = (double)tile[k * kPanel];
+      const double c = cf[k], sn = cf[kPanel + k];
+      const double ln = cf[2 * kPanel + k] * (c * lo - sn * x);
+      const double xn = fma(c, x, sn * lo);
+      // above the diagonal (diagonal tile, k > lane): identity, the entry's bits never reach x or L
+      const bool on = !diag || k <= lane;
+      lnew[k] = ln;
+      x = on ? xn : x;
+    }
+    if (!diag) {
+#pragma unroll
+      for (int k = 0; k < kPanel; ++k) tile[k * kPanel] = (T)lnew[k];
+    } else if (valid) {
+      T *gp = L + row + (int64_t)row0 * ld;
+#pragma unroll
+      for (int k = 0; k < kPanel; ++k)
+        if (k <= lane) gp[(int64_t)k * ld] = (T)lnew[k];
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (elect_one()) {
+      if (!diag) tma_store_2d(&tmapc, (int)row0, pan * kPanel, stg);
+      bulk_commit();
+    }
+    __syncwarp();
+  }
+  if (elect_one()) bulk_wait_all<0>();
+}
+
+template <typename T>
+inline size_t dd_sweep_cm_smem() { return 1024 + (size_t)4 * kSwCmStages * SwCmGeom<T>::STAGE; }
 
 // =====================================================================================
 // Downdate sweep (row-major): TMA-pipelined, 4 lanes per row, right-to-left affine scan
@@ -1503,9 +1982,59 @@ inline bool make_tmap(CUtensorMap *map, T *L, int64_t n, int64_t ld, int box_row
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// ---- column-major plan: block rows of 32 dealt cyclically, one warp per block row
+struct CmPlan {
+  bool ok = false;
+  int sms = 0, Wk = 0, Q = 0;
+  size_t smem = 0;
+};
+
+template <typename T>
+inline CmPlan cm_plan(int64_t n, int64_t ld, const void *L) {
+  CmPlan pl;
+  constexpr int EPC = 16 / sizeof(T);
+  if (n < 64 || n >= (1LL << 31) || (ld % EPC) != 0 || (reinterpret_cast<uintptr_t>(L) & 15) != 0) return pl;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return pl;
+  int sms = 0, coop = 0, smem_optin = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (!coop || sms < 2) return pl;
+  const int Wk = sms - 1;
+  const int64_t nRB = (n + kPanel - 1) / kPanel;
+  const int Q = (int)((nRB + Wk - 1) / Wk);
+  if (Q > kCmMaxQ) return pl;
+  const size_t smem = std::max(df_chain_rm_smem<T>(), df_worker_cm_smem<T>(Q));
+  if (smem > (size_t)smem_optin) return pl;
+  pl.ok = true; pl.sms = sms; pl.Wk = Wk; pl.Q = Q; pl.smem = smem;
+  return pl;
+}
+
+// Column-major n x n matrix with leading dimension ld: plain boxes of [32 columns][32 rows] (rows contiguous).
+template <typename T>
+inline bool make_tmap_cm(CUtensorMap *map, T *L, int64_t n, int64_t ld) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)n};  // (rows, columns): rows are the inner dimension
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(T)};
+  const cuuint32_t box[2] = {(cuuint32_t)kPanel, (cuuint32_t)kPanel};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  return enc(map, dt, 2, L, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// The tensor-map kernels (row-major df_kernel_rm, column-major df_kernel_cm) take this shape natively.
+template <typename T>
+inline bool dataflow_native(int64_t n, int64_t ld, int layout, const T *L) {
+  if (!get_encode_tiled() || getenv("CHUB_DF_V2")) return false;
+  return layout == CHUB_ROW_MAJOR ? rm_plan<T>(n, ld, L).ok : cm_plan<T>(n, ld, L).ok;
+}
+
 template <typename T>
 inline bool dataflow_supported(int64_t n, int64_t ld, int layout, const T *L) {
-  if (layout == CHUB_ROW_MAJOR && rm_plan<T>(n, ld, L).ok && get_encode_tiled()) return true;
+  if (dataflow_native<T>(n, ld, layout, L)) return true;
   return df_plan<T>(n, ld, layout, L).ok;
 }
 
@@ -1524,14 +2053,21 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
     rp = rm_plan<T>(n, ld, L);
     if (rp.ok && !(make_tmap<T>(&tmap8, L, n, ld, 8) && make_tmap<T>(&tmap32, L, n, ld, 32))) rp.ok = false;
   }
+  CmPlan cp;
+  alignas(64) CUtensorMap tmapc;
+  if (LAYOUT == CHUB_COL_MAJOR && !getenv("CHUB_DF_V2")) {
+    cp = cm_plan<T>(n, ld, L);
+    if (cp.ok && !make_tmap_cm<T>(&tmapc, L, n, ld)) cp.ok = false;
+  }
+  const bool tm = rp.ok || cp.ok;  // a tensor-map kernel (chain with M1, band depth kDfD)
   DfPlan pl;
-  if (!rp.ok) {
+  if (!tm) {
     pl = df_plan<T>(n, ld, LAYOUT, L);
     if (!pl.ok) return (int)cudaErrorNotSupported;
   }
   // one pre-pass: w-tilde / v0 / dg / sentinels (prepare) and the inverse diagonal blocks
   df_prepass_kernel<T, LAYOUT><<<(nb + 3) / 4, 128, 0, st>>>(L, ni, ld, v, ws, flags, status,
-                                                              rp.ok ? kDfD : kV2D);
+                                                              tm ? kDfD : kV2D, tm);
   ++*launches;
   DfParams P;
   P.n = ni; P.T = nb; P.ld = ld; P.ws = ws; P.status = status;
@@ -1548,6 +2084,13 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
     if (e != cudaSuccess) return (int)e;
     void *args[] = {(void *)&L, (void *)&v, (void *)&P, (void *)&tmap8, (void *)&tmap32};
     e = cudaLaunchCooperativeKernel((void *)kern, dim3(rp.sms), dim3(rp.threads), args, rp.smem, st);
+  } else if (cp.ok) {
+    P.R = 32; P.r_shift = 5; P.Wk = cp.Wk; P.rows_max = cp.Q * 32; P.nw = cp.Q;
+    auto kern = P.prof ? df_kernel_cm<T, UPDATE, true> : df_kernel_cm<T, UPDATE, false>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.smem);
+    if (e != cudaSuccess) return (int)e;
+    void *args[] = {(void *)&L, (void *)&v, (void *)&P, (void *)&tmapc};
+    e = cudaLaunchCooperativeKernel((void *)kern, dim3(cp.sms), dim3(kCmMaxThreads), args, cp.smem, st);
   } else {
     P.R = pl.R; P.r_shift = pl.r_shift; P.Wk = pl.Wk; P.rows_max = pl.rows_max; P.nw = pl.nw;
     auto kern = df_kernel_v2<T, LAYOUT, UPDATE>;
@@ -1567,6 +2110,12 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
       e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
       if (e != cudaSuccess) return (int)e;
       sk<<<nb, 128, ssm, st>>>(L, ni, ld, ws, status, tmap8);
+    } else if (cp.ok && !getenv("CHUB_DD_SWEEP_V1")) {
+      auto sk = dd_sweep_cm_kernel<T>;
+      const size_t ssm = dd_sweep_cm_smem<T>();
+      e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
+      if (e != cudaSuccess) return (int)e;
+      sk<<<(nb + 3) / 4, 128, ssm, st>>>(L, ni, ld, ws, status, tmapc);
     } else {
       large_dd_sweep_kernel<T, LAYOUT><<<(ni + 127) / 128, 128, 0, st>>>(L, ni, ld, ws, status);
     }

@@ -33,12 +33,18 @@ struct HostCache {
 std::mutex h_mu;
 HostCache h_cache[64];
 thread_local char h_err[256] = "";
+}  // namespace
+extern "C" void chub_internal_set_error(const char *msg);  // api.cu: what chub_last_error() returns
+namespace {
 
+// A failing call reports through chub_last_error() and leaves no copy into the caller's arrays in flight.
 #define HCK(call)                                                             \
   do {                                                                        \
     cudaError_t e_ = (call);                                                  \
     if (e_ != cudaSuccess) {                                                  \
       snprintf(h_err, sizeof(h_err), "%s: %s", #call, cudaGetErrorString(e_)); \
+      chub_internal_set_error(h_err);                                         \
+      cudaDeviceSynchronize();                                                \
       return (int)e_;                                                         \
     }                                                                         \
   } while (0)
@@ -197,7 +203,7 @@ int run_host(dev_fn fn, bool is_update, size_t es, void *L, int64_t n, int64_t l
   HCK(cudaMemcpyAsync(c.v, v, (size_t)n * es, cudaMemcpyHostToDevice, c.st));
   rc = fn(c.L, n, n, layout, c.v, flags, nullptr, 0, c.status, c.st);
   if (rc) {
-    snprintf(h_err, sizeof(h_err), "%s", chub_last_error());
+    cudaDeviceSynchronize();  // (the message is already in chub_last_error())
     return rc;
   }
   HCK(cudaMemcpyAsync(status, c.status, sizeof(int32_t), cudaMemcpyDeviceToHost, c.st));

@@ -34,6 +34,7 @@ constexpr int kXBlock = kPanel * kXStride;  // lane = row reads of 16 bytes are 
 
 struct LargeWs {
   double *X;      // [nb][kXBlock] inverse of each 32x32 diagonal block (rows of kXStride, identity padded)
+  double *M1;     // [nb][kXBlock] M1_r = X_r L[r, r-1] (dataflow kernel: the chain's one mat-vec per block row)
   double *w;      // [n_pad]  forward-substitution residual, initialised to v
   double *p;      // [n_pad]  p = L^{-1} v
   double *c;      // [n_pad]  c_k (sign folded)
@@ -48,7 +49,7 @@ struct LargeWs {
 inline size_t large_ws_doubles(int64_t n) {
   int64_t n_pad = (n + 31) & ~31LL;
   int64_t nb = n_pad / 32;
-  return (size_t)(nb * kXBlock + 7 * n_pad + 8);
+  return (size_t)(2 * nb * kXBlock + 7 * n_pad + 8);
 }
 
 inline LargeWs large_ws_carve(void *base, int64_t n) {
@@ -57,6 +58,7 @@ inline LargeWs large_ws_carve(void *base, int64_t n) {
   LargeWs ws;
   double *d = reinterpret_cast<double *>(base);
   ws.X = d; d += nb * kXBlock;
+  ws.M1 = d; d += nb * kXBlock;
   ws.w = d; d += n_pad;
   ws.p = d; d += n_pad;
   ws.c = d; d += n_pad;
@@ -93,20 +95,24 @@ __global__ void large_prepare_kernel(const T *L, int n, int64_t ld, const T *v, 
 // Core: one warp, staging area `Lw` = [32][33] doubles + `Rw` = [32] doubles of shared memory.
 template <typename T, int LAYOUT>
 __device__ __forceinline__ void invdiag_block_smem(const T *L, int n, int64_t ld, double *X, int blk,
-                                                   double (*Lw)[kPanel + 1], double *Rw);
+                                                   double (*Lw)[kPanel + 1], double *Rw, double *M1 = nullptr);
 constexpr int kInvStageDoubles = kPanel * (kPanel + 1) + kPanel;  // per warp
 
 template <typename T, int LAYOUT>
-__device__ __forceinline__ void invdiag_block_to(const T *L, int n, int64_t ld, double *X, int blk) {
+__device__ __forceinline__ void invdiag_block_to(const T *L, int n, int64_t ld, double *X, int blk,
+                                                 double *M1 = nullptr) {
   __shared__ double Ls[4][kPanel][kPanel + 1];
   __shared__ double Rd[4][kPanel];
   const int warp = (threadIdx.x >> 5) & 3;
-  invdiag_block_smem<T, LAYOUT>(L, n, ld, X, blk, Ls[warp], Rd[warp]);
+  invdiag_block_smem<T, LAYOUT>(L, n, ld, X, blk, Ls[warp], Rd[warp], M1);
 }
 
+// M1 != nullptr: also M1 = X L[blk, blk-1] (32 x 32, rows of kXStride; zero for blk == 0): with it the
+// chain of the persistent kernel needs ONE mat-vec per block row on its critical path,
+//     p_r = X_r (wt_r - sum_{q >= 2} L[r, r-q] p_{r-q}) - M1_r p_{r-1}.
 template <typename T, int LAYOUT>
 __device__ __forceinline__ void invdiag_block_smem(const T *L, int n, int64_t ld, double *X, int blk,
-                                                   double (*Lw)[kPanel + 1], double *Rw) {
+                                                   double (*Lw)[kPanel + 1], double *Rw, double *M1) {
   const int lane = threadIdx.x & 31;
   const int nb = (n + 31) / 32;
   if (blk >= nb) return;
@@ -136,10 +142,32 @@ __device__ __forceinline__ void invdiag_block_smem(const T *L, int n, int64_t ld
   }
 #pragma unroll
   for (int i = 0; i < kPanel; ++i) X[i * kXStride + j] = x[i];
+  if (M1 == nullptr) return;
+  // M1[i][c] = sum_{k <= i} X[i][k] Lt[k][c],  Lt = L[blk, blk-1];  lane = column c.  X goes through the
+  // staging area (its L_D copy is no longer needed), Lt[.][c] sits in registers.
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < kPanel; ++i) Lw[i][j] = x[i];
+  double lt[kPanel];
+#pragma unroll
+  for (int k = 0; k < kPanel; ++k)
+    lt[k] = (blk > 0 && c0 + k < n) ? (double)L[idx<LAYOUT>(c0 + k, c0 - kPanel + lane, ld)] : 0.0;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < kPanel; ++i) {
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < kPanel; k += 2) {
+      if (k <= i) a0 = fma(Lw[i][k], lt[k], a0);
+      if (k + 1 <= i) a1 = fma(Lw[i][k + 1], lt[k + 1], a1);
+    }
+    M1[i * kXStride + lane] = a0 + a1;
+  }
 }
 template <typename T, int LAYOUT>
-__device__ __forceinline__ void invdiag_block(const T *L, int n, int64_t ld, LargeWs ws, int blk) {
-  invdiag_block_to<T, LAYOUT>(L, n, ld, ws.X + (int64_t)blk * kXBlock, blk);
+__device__ __forceinline__ void invdiag_block(const T *L, int n, int64_t ld, LargeWs ws, int blk, bool with_m1 = false) {
+  invdiag_block_to<T, LAYOUT>(L, n, ld, ws.X + (int64_t)blk * kXBlock, blk,
+                              with_m1 ? ws.M1 + (int64_t)blk * kXBlock : nullptr);
 }
 
 template <typename T, int LAYOUT>

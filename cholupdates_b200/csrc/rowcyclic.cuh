@@ -39,24 +39,28 @@ __global__ void rc_prepare_kernel(const T *A, int m_loc, int n, int64_t ld, int 
   if (l == 0) { ws.scal[0] = 1.0; ws.scal[1] = 1.0; ws.scal[2] = 0.0; ws.scal[3] = 0.0; }
 }
 
-__global__ void rc_pack_kernel(LargeWs ws, int J, double *buf, const int32_t *status) {
+// (n_pad = length of the workspace vectors: a ragged last panel must not reach past them)
+__global__ void rc_pack_kernel(LargeWs ws, int J, int n_pad, double *buf, const int32_t *status) {
   const int t = threadIdx.x;  // kBig threads
   const int k = J * kBig + t;
-  buf[t] = ws.p[k];
-  buf[kBig + t] = ws.c[k];
-  buf[2 * kBig + t] = ws.sg[k];
-  buf[3 * kBig + t] = ws.dn[k];
+  const bool in = k < n_pad;
+  buf[t] = in ? ws.p[k] : 0.0;
+  buf[kBig + t] = in ? ws.c[k] : 1.0;
+  buf[2 * kBig + t] = in ? ws.sg[k] : 0.0;
+  buf[3 * kBig + t] = in ? ws.dn[k] : 1.0;
   if (t < 7) buf[4 * kBig + t] = ws.scal[t];
   if (t == 7) buf[4 * kBig + 7] = (double)*status;  // the owner's status travels with the panel
 }
 
-__global__ void rc_unpack_kernel(LargeWs ws, int J, const double *buf, int32_t *status) {
+__global__ void rc_unpack_kernel(LargeWs ws, int J, int n_pad, const double *buf, int32_t *status) {
   const int t = threadIdx.x;
   const int k = J * kBig + t;
-  ws.p[k] = buf[t];
-  ws.c[k] = buf[kBig + t];
-  ws.sg[k] = buf[2 * kBig + t];
-  ws.dn[k] = buf[3 * kBig + t];
+  if (k < n_pad) {
+    ws.p[k] = buf[t];
+    ws.c[k] = buf[kBig + t];
+    ws.sg[k] = buf[2 * kBig + t];
+    ws.dn[k] = buf[3 * kBig + t];
+  }
   if (t < 7) ws.scal[t] = buf[4 * kBig + t];
   if (t == 7 && buf[4 * kBig + 7] != 0.0) atomicMax(status, (int)buf[4 * kBig + 7]);
 }
@@ -131,11 +135,13 @@ __global__ void rc_pack_dd_kernel(const T *Lsh, int n, int64_t ld, LargeWs ws, i
   buf[3 * kBig + t] = (k < n && Lsh[(int64_t)k * ld + k] < T(0)) ? -1.0 : 1.0;
   if (t == 7) buf[4 * kBig + 7] = (double)*status;
 }
-__global__ void rc_unpack_dd_kernel(LargeWs ws, int J, const double *buf, int32_t *status) {
+__global__ void rc_unpack_dd_kernel(LargeWs ws, int J, int n_pad, const double *buf, int32_t *status) {
   const int t = threadIdx.x;
   const int k = J * kBig + t;
-  ws.p[k] = buf[t];
-  ws.dn[k] = buf[3 * kBig + t];
+  if (k < n_pad) {
+    ws.p[k] = buf[t];
+    ws.dn[k] = buf[3 * kBig + t];
+  }
   if (t == 7 && buf[4 * kBig + 7] != 0.0) atomicMax(status, (int)buf[4 * kBig + 7]);
 }
 
@@ -256,15 +262,20 @@ struct RcwP2P {
   double *mail;              // this rank's own mailbox
   long long epoch;           // global step of this call's step 0 (monotonic across calls): step d has
                              // parity (epoch + d) & 1 and flag value epoch + d + 1
-  int max_tasks;
+  int max_tasks;             // slot stride of the MAILBOX: rcw_mail_tasks(n, G), the same for every call on it
+                             // (a per-call stride would let calls with different K alias each other's slots)
+  long long watchdog;        // cycles a CTA may wait for a peer's flag before it gives up
 };
+// Tasks per (set, sender) the mailbox has room for: the most any call can have, ceil(panels / G).
+inline int rcw_mail_tasks(int64_t n, int G) { return rcw_max_tasks(n, rcw_panels(n), G); }
 // Mailbox layout (doubles): [ long long flag[4][G] | int counter, padding (8) | payload slots [4][G][max_tasks] ].
 // Four sets (global step & 3): with the look-ahead split the bulk of step d's trail may still be reading
 // its payloads while the payloads of step d+2 arrive (never those of step d+3, see distributed.py).
 // The flags sit at a fixed place, so calls with different K (different max_tasks) can share a mailbox
 // that was sized for the largest one.
 inline size_t rcw_mailbox_doubles(int64_t n, int64_t K, int G) {
-  return (size_t)kRcwSets * G + 8 + (size_t)kRcwSets * G * rcw_max_tasks(n, K, G) * kRcwSlot;
+  (void)K;  // sized for every K: the slot stride is fixed per mailbox
+  return (size_t)kRcwSets * G + 8 + (size_t)kRcwSets * G * rcw_mail_tasks(n, G) * kRcwSlot;
 }
 __host__ __device__ inline size_t rcw_mail_slot(int q, int r, int i, int G, int max_tasks) {
   return (size_t)kRcwSets * G + 8 + ((size_t)(q * G + r) * max_tasks + i) * kRcwSlot;
@@ -282,11 +293,14 @@ __device__ __forceinline__ long long ld_acquire_sys_s64(const long long *p) {
   return x;
 }
 // Spin until *flag >= want (thread 0 of a CTA); watchdog -> CHUB_STATUS_INTERNAL instead of a hang.
-__device__ __forceinline__ void rcw_wait_flag(const long long *flag, long long want, int32_t *status) {
+// After CHUB_STATUS_INTERNAL nobody stores to A any more (the callers bail out), the factor of this call
+// is invalid on every rank and the mailbox has to be re-created (distributed.py raises).
+__device__ __forceinline__ void rcw_wait_flag(const long long *flag, long long want, int32_t *status,
+                                              long long watchdog) {
   if (ld_acquire_sys_s64(flag) >= want) return;
   const long long t0 = clock64();
   while (ld_acquire_sys_s64(flag) < want) {
-    if (clock64() - t0 > 4000000000LL || *(volatile int32_t *)status == CHUB_STATUS_INTERNAL) {
+    if (clock64() - t0 > watchdog || *(volatile int32_t *)status == CHUB_STATUS_INTERNAL) {
       atomicMax(status, CHUB_STATUS_INTERNAL);
       return;
     }
@@ -473,13 +487,20 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
     // waits for the flags of ALL ranks -- the one-step bound on how far ranks drift apart.
     const int q = (int)((pp.epoch + d) & (kRcwSets - 1));
     const long long *flags = reinterpret_cast<const long long *>(pp.mail + rcw_mail_flags(G, max_tasks)) + q * G;
+    __shared__ int bail;
+    if (tid == 0) bail = 0;
+    __syncthreads();
     if (blockIdx.x == 0 && blockIdx.y == 0 && rows_mode != 2) {
-      if (tid < G) rcw_wait_flag(flags + tid, pp.epoch + d + 1, status);
+      if (tid < G) rcw_wait_flag(flags + tid, pp.epoch + d + 1, status, pp.watchdog);
     } else if (tid == 0) {
-      rcw_wait_flag(flags + J % G, pp.epoch + d + 1, status);
+      rcw_wait_flag(flags + J % G, pp.epoch + d + 1, status, pp.watchdog);
     }
     __syncthreads();
-    pay = pp.mail + rcw_mail_slot(q, J % G, blockIdx.y / G, G, max_tasks);
+    // a peer never delivered: do not touch A with a stale payload (uniform decision for the CTA)
+    if (tid == 0 && *(volatile int32_t *)status == CHUB_STATUS_INTERNAL) bail = 1;
+    __syncthreads();
+    if (bail) return;
+    pay = pp.mail + rcw_mail_slot(q, J % G, blockIdx.y / G, G, pp.max_tasks);
   }
   if (unpack && UPDATE) {
     for (int f = 0; f < Fe; ++f) {

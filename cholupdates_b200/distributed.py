@@ -349,8 +349,13 @@ class _CudaRowCyclicBackend:
         """Advance the epoch; one status read (a peer that never arrived trips the device watchdog)."""
         self.epoch += steps
         if int(self.status.item()) == 3:
-            raise RuntimeError("cholupdates_b200: a peer did not deliver its panel coefficients "
-                               "(device watchdog, CHUB_STATUS_INTERNAL)")
+            # Nothing was stored with a stale payload (the trail CTAs bail out), but the panels already
+            # applied stay applied: the factor is in an undefined intermediate state on every rank, and
+            # the flags no longer match the epoch -- the mailbox must be re-created (a new RowCyclicFactor).
+            self._p2p_state = False
+            raise RuntimeError("cholupdates_b200: a peer did not deliver its panel coefficients within "
+                               "CHUB_P2P_WATCHDOG_MS (device watchdog, CHUB_STATUS_INTERNAL); the factor "
+                               "is invalid and the peer-memory exchange of this object is disabled")
 
     def wave_owner(self, d, pay_mine, solve_only=False):
         from . import _lib
@@ -500,11 +505,11 @@ class RowCyclicFactor:
             # read-only trail kernel per panel, the panel's p exchanged over peer memory -- no collective
             pay_mine, pay_all = be.wave_begin(v.reshape(1, -1), v_out.reshape(1, -1), check_diag)
             be.v_out = v_out
-            if check_diag:
+            if check_diag or use_p2p:  # (peer memory: also the rendezvous of the call, see update_many)
                 st = be.status_tensor()
                 if multi:
                     dist.all_reduce(st, op=dist.ReduceOp.MAX, group=self.group)
-                if int(st.item()) == 1:
+                if check_diag and int(st.item()) == 1:
                     raise np.linalg.LinAlgError("The given Cholesky factor `L` contains zeros on its diagonal")
             steps = (self.n + RC_BLOCK - 1) // RC_BLOCK
             for d in range(steps):
@@ -576,14 +581,17 @@ class RowCyclicFactor:
             raise ValueError("The rows of `V` must be contiguous.")
         be = self.backend
         multi = self.world > 1 and dist.is_available() and dist.is_initialized()
+        use_p2p = multi and p2p is not False and hasattr(be, "p2p_ready") and be.p2p_ready(self.group)
         pay_mine, pay_all = be.wave_begin(V, V_out, check_diag)
-        if check_diag:
+        if check_diag or use_p2p:
+            # With the peer-memory exchange this all-reduce is also the RENDEZVOUS of the call: it runs
+            # on the stream, so a rank whose host arrives seconds late holds the others inside the
+            # collective (no watchdog there) instead of inside a kernel that spins on its flags.
             st = be.status_tensor()
             if multi:
                 dist.all_reduce(st, op=dist.ReduceOp.MAX, group=self.group)
-            if int(st.item()) == 1:
+            if check_diag and int(st.item()) == 1:
                 raise np.linalg.LinAlgError("The given Cholesky factor `L` contains zeros on its diagonal")
-        use_p2p = multi and p2p is not False and hasattr(be, "p2p_ready") and be.p2p_ready(self.group)
         if lookahead is None:
             lookahead = K > 1
         lookahead = bool(lookahead) and (use_p2p or not multi) and hasattr(be, "lookahead_streams")

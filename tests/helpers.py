@@ -51,6 +51,32 @@ def downdate_vector(L: np.ndarray, seed, norm_p: float = None) -> np.ndarray:
     return (np.tril(L).astype(np.float64) @ (norm_p * u)).astype(L.dtype)
 
 
+def rel_vec(x: np.ndarray, y: np.ndarray) -> float:
+    """Relative 2-norm error of a vector against the oracle's."""
+    x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    d = np.linalg.norm(y)
+    return float(np.linalg.norm(x - y) / (d if d > 0 else 1.0))
+
+
+def config1_inputs(n: int):
+    """(L, v) of BASELINE.json configs[0]: the reference's
+    ``random_spd_matrix(n, fast=True, rng=default_rng(0))`` (src/cholupdates/utils.py:78-90, restated
+    because the reference package does not travel to the GPU box; pinned against the live generator by
+    tests/test_oracle.py) + ``scipy.linalg.cholesky(lower=True)``; ``v ~ N(0, 10^2)`` from default_rng(1)."""
+    import scipy.linalg
+
+    g = np.random.default_rng(0)
+    A = g.standard_normal((n, n))
+    M = A @ A.T
+    M += np.eye(n)
+    D = np.sqrt(np.diag(M))
+    M = D[:, None] * M * D[None, :]
+    M = 0.5 * (M + M.T)
+    L = scipy.linalg.cholesky(M, lower=True)
+    v = np.random.default_rng(1).normal(scale=10.0, size=n)
+    return L, v
+
+
 def tol_for(dtype, n: int) -> float:
     """Parity tolerance (relative Frobenius error over the lower triangle): the north star's
     1e-12 * sqrt(n) for fp64; 1e-5 * sqrt(n) for fp32."""

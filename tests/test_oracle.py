@@ -175,3 +175,28 @@ def test_upper_triangle_never_touched():
             op(Lb, vv.copy())
             np.testing.assert_array_equal(np.triu(Lb, 1), junk)
             np.testing.assert_array_equal(np.tril(La), np.tril(Lb))
+
+
+# -------------------------------------------------- 4. the config-1 input generator (restated)
+@pytest.mark.skipif(not build_ref.reference_present(), reason="/root/reference is not present")
+@pytest.mark.parametrize("n", [50, 1000])
+def test_config1_inputs_match_reference_generator(n):
+    """helpers.config1_inputs / bench.config1_inputs restate the reference's
+    random_spd_matrix(fast=True) (src/cholupdates/utils.py:78-90) because the reference package does not
+    travel to the GPU box: the restatement must reproduce the live generator bit for bit."""
+    import scipy.linalg
+
+    import ref_api
+    from helpers import config1_inputs
+
+    api = ref_api.load_reference_api()
+    A = api.utils.random_spd_matrix(n, fast=True, rng=np.random.default_rng(0))
+    L_ref = scipy.linalg.cholesky(A, lower=True)
+    L, v = config1_inputs(n)
+    np.testing.assert_array_equal(L, L_ref)
+    np.testing.assert_array_equal(v, np.random.default_rng(1).normal(scale=10.0, size=n))
+    import bench
+
+    Lb, vb = bench.config1_inputs(n)
+    np.testing.assert_array_equal(Lb, L)
+    np.testing.assert_array_equal(vb, v)

@@ -36,8 +36,8 @@ lib.chub_debug_profile(None, n, out.ctypes.data, ctas)
 P = out.reshape(ctas, 16)
 T = (n + 31) // 32
 ch = P[0]
-print(f"CHAIN (cycles per block row, T={T}): total {ch[0]/T:.0f} | A: wait tiles {ch[1]/T:.0f} | A: total(w0) {ch[2]/T:.0f} | "
-      f"A: poll wt (w4) {ch[4]/T:.0f} | barrier+B prep {ch[3]/T:.0f} | B: matvec+publish {ch[5]/T:.0f}")
+print(f"CHAIN (cycles per block row, T={T}): C total {ch[0]/T:.0f} | C: wait ring slot {ch[1]/T:.0f} | C: wait ua_r {ch[2]/T:.0f} | "
+      f"C: wait xw_r {ch[6]/T:.0f} | band warp 0: wait ring slot {ch[3]/T:.0f} (per column) | P: poll wt {ch[5]/T:.0f}")
 W = P[1:]
 steps = T + 4
 names = ["total", "wait tile (mbar)", "wait_read+issue load", "compute", "wait coefs", "fence+store+release", "w7 poll p", "w7 per panel total"]
