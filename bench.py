@@ -498,7 +498,7 @@ def leg_update(ctx, args, sampler):
         step(i)
     ctx.barrier()
     lib.chub_launch_count(1)
-    total_ms, step_ms = timed_steps(ctx, lambda i: step(i), 0, args.steps, sampler)
+    total_ms, step_ms = timed_steps(ctx, lambda i: step(args.warmup + i), 0, args.steps, sampler)
     # (warm-up ran above so that the launch counter covers exactly the timed region)
     launches = int(lib.chub_launch_count(0))
     clocks = sampler.stop() if sampler else None

@@ -24,6 +24,7 @@ _vp, _i64, _int, _sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_s
 _SIG_SINGLE = [_vp, _i64, _i64, _int, _vp, _int, _vp, _sz, _vp, _vp]
 _SIG_BATCHED = [_vp, _i64, _i64, _i64, _int, _vp, _i64, _i64, _int, _vp, _vp]
 _SIG_HOST = [_vp, _i64, _i64, _int, _vp, _int, ctypes.POINTER(ctypes.c_int32)]
+_SIG_HOST_COPY = [_vp, _i64, _vp, _i64, _i64, _int, _vp, _int, ctypes.POINTER(ctypes.c_int32)]
 
 
 def load() -> ctypes.CDLL:
@@ -62,6 +63,9 @@ def load() -> ctypes.CDLL:
                 f.restype, f.argtypes = _int, _SIG_BATCHED
                 f = getattr(lib, f"chub_{op}_host_{suf}")
                 f.restype, f.argtypes = _int, _SIG_HOST
+                f = getattr(lib, f"chub_{op}_host_copy_{suf}", None)  # (absent in older A/B builds, CHUB_LIB)
+                if f is not None:
+                    f.restype, f.argtypes = _int, _SIG_HOST_COPY
         _lib = lib
         return lib
 

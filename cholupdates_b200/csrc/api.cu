@@ -149,7 +149,12 @@ int run_single(void *Lv, int64_t n, int64_t ld, int layout, void *vv, int flags,
   int path = g_path.load();
   if (path == 0) path = n <= kSmallCutoff ? 1 : 3;
   if (path == 1 && n > kSmallMaxN) path = 2;
-  if (path == 3 && !dataflow_supported<T>(n, ld, layout, L)) path = (g_path.load() == 0 && n <= kSmallFallback) ? 1 : 2;
+  // (row-major beyond the persistent kernel's capacity: blocked driver; column-major shapes the native
+  // kernel does not take: row-major scratch -- both decided below)
+  if (path == 3 && !dataflow_supported<T>(n, ld, layout, L) &&
+      !(layout == CHUB_ROW_MAJOR && blocked_supported<T>(n, ld, L)) &&
+      !(layout == CHUB_COL_MAJOR && n > kSmallFallback))
+    path = (g_path.load() == 0 && n <= kSmallFallback) ? 1 : 2;
   if (path == 1) return launch_small<T, UPDATE>(L, n, ld, 0, layout, v, 0, 1, flags, status, st);
 
   const size_t need = chub_workspace_bytes(dtype_of<T>(), n);
@@ -161,6 +166,14 @@ int run_single(void *Lv, int64_t n, int64_t ld, int layout, void *vv, int flags,
     return (int)cudaErrorInvalidValue;
   }
   LargeWs ws = large_ws_carve(workspace, n);
+  if (path == 3 && layout == CHUB_ROW_MAJOR && blocked_supported<T>(n, ld, L)) {
+    // beyond the persistent kernel's row capacity: diagonal blocks + rectangles (launch_blocked_rm)
+    int64_t nl = 0;
+    int rc = launch_blocked_rm<T, UPDATE>(L, n, ld, v, flags, ws, status, st, &nl);
+    g_launches.fetch_add(nl, std::memory_order_relaxed);
+    if (rc == 0) return 0;
+    return fail((cudaError_t)rc, "blocked dataflow launch");
+  }
   if (path == 3 && layout == CHUB_COL_MAJOR && !dataflow_native<T>(n, ld, layout, L) &&
       !getenv("CHUB_COL_MAJOR_NATIVE")) {
     // Column-major shapes the native tensor-map kernel (df_kernel_cm) does not take (beyond its row cap,
@@ -182,14 +195,17 @@ int run_single(void *Lv, int64_t n, int64_t ld, int layout, void *vv, int flags,
         pool_tuned.fetch_or(1ull << (dev & 63));
       }
     }
-    if (dataflow_supported<T>(n, ldr, CHUB_ROW_MAJOR, (const T *)nullptr) &&
+    if ((dataflow_supported<T>(n, ldr, CHUB_ROW_MAJOR, (const T *)nullptr) ||
+         blocked_supported<T>(n, ldr, (const T *)nullptr)) &&
         cudaMallocAsync((void **)&tmp, (size_t)n * ldr * sizeof(T), st) == cudaSuccess) {
       const int nt = (int)((n + 31) / 32);
       const unsigned tiles = (unsigned)((int64_t)nt * (nt + 1) / 2);
       tri_transpose_kernel<T, true><<<tiles, 256, 0, st>>>(tmp, ldr, L, ld, (int)n);
       LAUNCHED();
       int64_t nl = 0;
-      int rc = launch_dataflow<T, CHUB_ROW_MAJOR, UPDATE>(tmp, n, ldr, v, flags, ws, status, st, &nl);
+      int rc = blocked_supported<T>(n, ldr, tmp)
+                   ? launch_blocked_rm<T, UPDATE>(tmp, n, ldr, v, flags, ws, status, st, &nl)
+                   : launch_dataflow<T, CHUB_ROW_MAJOR, UPDATE>(tmp, n, ldr, v, flags, ws, status, st, &nl);
       g_launches.fetch_add(nl, std::memory_order_relaxed);
       if (rc == 0) {
         // (a failed check_diag / not-PD call leaves tmp == L, so copying back is harmless)
@@ -416,6 +432,35 @@ int rcw_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, in
   if (const char *e = getenv("CHUB_RCW_NT")) nt = atoi(e);
   if (nt != 32 && nt != 64) nt = 128;
   if (rows_mode < 0 || rows_mode > 2) return (int)cudaErrorInvalidValue;
+  // bulk of the look-ahead split on the TMA ring (rcw_bulk_tma_kernel) when the local rows are 16-byte aligned
+  if (rows_mode == 2 && !solve_ws && fuse == 1 && m_loc > 0 && !getenv("CHUB_RCW_BULK_STAGED") &&
+      (ld % (16 / sizeof(T))) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && get_encode_tiled()) {
+    alignas(64) CUtensorMap tmapA;
+    if (make_tmap<T>(&tmapA, (T *)A, n, ld, 8, m_loc)) {
+      static int sms = 0;
+      if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      }
+      auto kern = rcw_bulk_tma_kernel<T>;
+      const size_t smem = rect_apply_rm_smem<T>();
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int ntasks = Jhi - Jlo + 1;
+      const int64_t items = (int64_t)ntasks * ((m_loc + 7) / 8);  // upper bound
+      // The bulk runs next to the owner + head kernels of the NEXT step (high-priority stream).  Its CTAs are
+      // persistent and fill an SM's shared memory, so a few SMs are left free for those kernels -- otherwise
+      // they would queue behind the whole bulk and the look-ahead would be lost.
+      int free_sms = 12;
+      if (const char *e = getenv("CHUB_RCW_FREE_SMS")) free_sms = atoi(e);
+      const int cap = std::max(1, sms - std::max(0, free_sms));
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(cap, (items + kRectWarps - 1) / kRectWarps));
+      kern<<<grid, kRectWarps * 32, smem, st>>>((int)m_loc, (int)n, G, rank, wv, (int)d, Jlo, ntasks,
+                                                rcw_max_tasks(n, K, G), pay_all, (T *)V_out, ldv, pp, status, tmapA);
+      LAUNCHED();
+      return 0;
+    }
+  }
   // solve_ws != NULL: forward substitution only (downdate); p and the diagonal signs go into its p / dn
   double *p_out = nullptr, *dn_out = nullptr;
   if (solve_ws) {

@@ -127,6 +127,9 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 template <int N>
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;\n" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// all state spaces: generic-proxy accesses (e.g. an acquire of a flag a peer GPU raised) before async-proxy
+// copies that read global memory
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 // 2-D tensor-map TMA: one instruction moves a whole box (c0 = column, c1 = row of its corner)
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, void *bar) {
@@ -265,16 +268,18 @@ __global__ void df_prepare_kernel(const T *L, int n, int64_t ld, const T *v, Lar
 // blocks it inverts).  check_diag failures are only known after the whole grid ran, so the inverses
 // are computed unconditionally (they only read L) -- the persistent kernel checks the status word.
 template <typename T, int LAYOUT>
+// w_in != nullptr (blocked driver, diagonal block J > 0): the vector entering this block is the residual
+// left in ws.w by the panels to its left, and (t, S) carry over from the previous block (ws.scal[4..5]).
 __global__ void __launch_bounds__(128) df_prepass_kernel(const T *L, int n, int64_t ld, const T *v, LargeWs ws,
                                                          int flags, int32_t *status, int band_depth,
-                                                         bool with_m1) {
+                                                         bool with_m1, const double *w_in) {
   const int i = blockIdx.x * 128 + threadIdx.x;
   const int n_pad = (n + 31) & ~31;
   if (i < n_pad) {
     const double sentinel = __longlong_as_double((long long)kSentinelBits);
     ws.p[i] = sentinel;
     if (i < n) {
-      const double vi = df_sanitize((double)v[i]);
+      const double vi = df_sanitize(w_in ? w_in[i] : (double)v[i]);
       const T dgi = L[idx<LAYOUT>(i, i, ld)];
       ws.v0[i] = vi;
       ws.dg[i] = (double)dgi;
@@ -286,7 +291,11 @@ __global__ void __launch_bounds__(128) df_prepass_kernel(const T *L, int n, int6
       ws.w[i] = 0.0;
     }
   }
-  if (i == 0) { ws.scal[0] = 1.0; ws.scal[1] = 1.0; ws.scal[2] = 0.0; ws.scal[3] = 0.0; }
+  if (i == 0) {
+    ws.scal[0] = w_in ? ws.scal[4] : 1.0;
+    ws.scal[1] = w_in ? ws.scal[5] : 1.0;
+    ws.scal[2] = 0.0; ws.scal[3] = 0.0;
+  }
   invdiag_block<T, LAYOUT>(L, n, ld, ws, blockIdx.x * 4 + (threadIdx.x >> 5), with_m1);
 }
 
@@ -767,166 +776,92 @@ template <typename T> struct RmGeom {
   static constexpr int CTILE = HALVES * 4096;              // bytes of a chain tile (32 rows)
 };
 
-// ---- chain CTA (threads 0..255 of CTA 0): eight warps with fixed roles, no CTA-wide barrier in the loop.
-//
-// With M1_r = X_r L[r, r-1] (formed by the pre-pass, off the critical path) the forward substitution reads
-//     p_r = ua_r + xw_r - M1_r p_{r-1},   ua_r = -X_r sum_{q=2..d} L[r, r-q] p_{r-q},   xw_r = X_r wt_r
-// so the step p_{r-1} -> p_r is ONE 32x32 mat-vec (warp C).  ua_r is complete one step earlier: block row r
-// belongs to band warp (r - 2) mod 4, which adds the band tiles (r, j), j = r-d .. r-2, as the p_j arrive
-// (one tile per step, accumulator in registers, lane = row) and multiplies by X_r after the last one.
-//   warp 0      C: p_r = u_r - M1_r p_{r-1}; publishes p_r (shared ring + global)
-//   warps 1..4  B: band tiles + u_r
-//   warp 5      P: polls wt_r (handed over by the workers) and forms xw_r = X_r wt_r, so that wt_r is needed
-//                  only one mat-vec before p_r is due:  p_r = ua_r + xw_r - M1_r p_{r-1}
-//   warp 6      T: issues the TMA loads of a block column as soon as its ring slot has been consumed, and
-//                  prefetches the band tiles of a later block column into L2
-// Hand-offs are counters in shared memory (st.release.cta / ld.acquire.cta); every spin has a watchdog.
-constexpr int kChTiles = kDfD - 1;  // band tiles per block column in the ring (distance 1 is folded into M1)
-constexpr int kChRing = 8;          // p / u / wt rings (block rows)
-
-template <typename T>
-struct ChGeom {
-  static constexpr int SLOT = kChTiles * RmGeom<T>::CTILE + 2 * kXBlock * 8;  // tiles, X_{j+2}, M1_{j+1}
-  static constexpr int BASE = 8192;                                            // control block + rings
-};
-
-__device__ __forceinline__ void ch_spin(const volatile int *flag, int need, int32_t *status) {
-  if (ld_acquire_cta_smem(flag) >= need) return;
-  const long long t0 = clock64();
-  while (ld_acquire_cta_smem(flag) < need) {
-    if (clock64() - t0 > kWatchdogCycles) { atomicMax(status, CHUB_STATUS_INTERNAL); return; }
-  }
-}
-
+// ---- chain CTA (threads 0..255 of CTA 0)
 // LAYOUT: row-major band tiles arrive as two 128-byte-swizzled boxes of [32 rows][16 columns] (lane = row
 // reads 16-byte chunks, conflict free); column-major ones as one plain box [32 columns][32 rows] (lane = row
 // reads 8 bytes per column, conflict free).
 template <typename T, int LAYOUT, bool PROF>
 __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsigned char *smem) {
   constexpr int HALVES = RmGeom<T>::HALVES, BOXC = RmGeom<T>::BOXC, EPC = RmGeom<T>::EPC;
-  constexpr int CTILE = RmGeom<T>::CTILE, SLOT = ChGeom<T>::SLOT;
-  static_assert(kDfD >= 2 && kChTiles == 4, "band warps are dealt block rows modulo 4");
-  static_assert(SLOT % 1024 == 0, "ring slots keep the 1024-byte alignment of the swizzled boxes");
+  constexpr int CTILE = RmGeom<T>::CTILE;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
   const int T_ = P.T;
   long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
+  // (Measured and dropped, profiles/r02_chain_v4_experiments.txt: a ring of their own for the inverse diagonal
+  // blocks, loaded two block rows ahead, which would make room for d = 6 band tiles -- phase B then waits for
+  // X on the critical path: 0.53 ms per update instead of 0.47.)
   unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);  // [kDfSlots]
-  volatile int *ctl = reinterpret_cast<volatile int *>(smem + 64);
-  volatile int *pdone = ctl;        // p_r is in pbuf for r < *pdone
-  volatile int *xwdone = ctl + 1;   // xw_r = X_r wt_r is in xwb for r < *xwdone
-  volatile int *xprog = ctl + 7;    // block columns whose X (in the ring slot) warp P has taken into registers
-  volatile int *bprog = ctl + 2;    // [4] block columns whose ring slot band warp k has finished reading
-  volatile int *uready = ctl + 8;   // [kChRing] r + 1 once u_r is in ubuf[r % kChRing]
-  double *pbuf = reinterpret_cast<double *>(smem + 512);   // [kChRing][32]
-  double *ubuf = pbuf + kChRing * kPanel;                   // [kChRing][32]
-  double *xwb = ubuf + kChRing * kPanel;                    // [kChRing][32]  xw_r
-  double *wtb = xwb + kChRing * kPanel;                     // [32] staging of wt_r (warp P)
-  double *wsum = wtb + kPanel;                              // [4][32] per band warp: staging of acc_r
-  unsigned char *slots = smem + ChGeom<T>::BASE;            // [kDfSlots][SLOT]
+  double *acc = reinterpret_cast<double *>(smem + 64);                      // [kDfD+1][32]
+  double *pbuf = acc + (kDfD + 1) * kPanel;                                 // [2][32]
+  double *wvec = pbuf + 2 * kPanel;                                         // [32]
+  double *wtb = wvec + kPanel;                                              // [2][32]
+  double *Xs = reinterpret_cast<double *>(smem + 4096);                     // [kDfSlots][kXBlock]
+  unsigned char *tiles = smem + 4096 + ((kDfSlots * kXBlock * 8 + 1023) / 1024) * 1024;  // [kDfSlots][kDfD][CTILE]
 
   if (tid == 0) {
     for (int i = 0; i < kDfSlots; ++i) mbar_init(&full[i], 1);
     fence_mbar_init();
   }
-  if (tid < 32) ctl[tid] = 0;
+  for (int e = tid; e < (kDfD + 1) * kPanel; e += 256) acc[e] = 0.0;
   named_sync(1, 256);
 
+  // one thread issues everything block column j needs: tiles (j+1..j+d, j) and X_{j+1}
+  auto issue_slot = [&](int j) {
+    if (j < 0 || j >= T_) return;
+    const int slot = j % kDfSlots;
+    void *bar = &full[slot];
+    int ntiles = min(kDfD, T_ - 1 - j);
+    if (ntiles < 0) ntiles = 0;
+    const bool do_x = j + 1 < T_;
+    const unsigned bytes = (unsigned)ntiles * CTILE + (do_x ? kXBlock * 8u : 0u);
+    if (bytes == 0) { mbar_arrive(bar); return; }
+    mbar_arrive_expect_tx(bar, bytes);
+    for (int q = 0; q < ntiles; ++q) {
+      if (LAYOUT == CHUB_COL_MAJOR) {  // (coordinates: row first -- rows are the contiguous dimension)
+        tma_load_2d(tiles + ((size_t)slot * kDfD + q) * CTILE, tmap32, (j + 1 + q) * kPanel, j * kPanel, bar);
+      } else {
+        for (int h = 0; h < HALVES; ++h)
+          tma_load_2d(tiles + ((size_t)slot * kDfD + q) * CTILE + h * 4096, tmap32,
+                      j * kPanel + h * BOXC, (j + 1 + q) * kPanel, bar);
+      }
+    }
+    if (do_x) bulk_g2s(Xs + slot * kXBlock, P.ws.X + (int64_t)(j + 1) * kXBlock, kXBlock * 8u, bar);
+  };
+
+  if (warp == kDfD + 1 && elect_one())
+    for (int j = 0; j < kDfSlots - 1; ++j) issue_slot(j);
   if (warp == 0) {
-    // ------------------------------------------------------------ C: the critical path
-    const long long t_chain0 = DF_PROF_T();
-    {
-      const double w0 = df_wait_value(P.ws.w + lane, P.status);
-      pbuf[lane] = w0;  // (staging: the mat-vec reads all 32 entries)
-      __syncwarp();
-      const double *X0 = P.ws.X + lane * kXStride;
-      double a0 = 0.0, a1 = 0.0;
+    wvec[lane] = df_wait_value(P.ws.w + lane, P.status);
+    __syncwarp();
+    const double *X0 = P.ws.X + lane * kXStride;
+    double a0 = 0.0, a1 = 0.0;
 #pragma unroll 8
-      for (int k = 0; k < kPanel; k += 2) {
-        a0 = fma(X0[k], pbuf[k], a0);
-        a1 = fma(X0[k + 1], pbuf[k + 1], a1);
-      }
-      __syncwarp();
-      const double p0 = a0 + a1;
-      pbuf[lane] = p0;
-      st_relaxed_f64(P.ws.p + lane, p0);
-      __syncwarp();
-      if (lane == 0) st_release_cta_smem(pdone, 1);
+    for (int k = 0; k < kPanel; k += 2) {
+      a0 += X0[k] * wvec[k];
+      a1 += X0[k + 1] * wvec[k + 1];
     }
-    // u_1 = X_1 wt_1 (block row 1 has no band tile beyond distance 1)
-    double u_first = 0.0;
-    if (T_ > 1) {
-      const double w1 = df_wait_value(P.ws.w + kPanel + lane, P.status);
-      ubuf[kPanel + lane] = w1;  // staging in the slot of u_1
-      __syncwarp();
-      const double *X1 = P.ws.X + kXBlock + lane * kXStride;
-      double a0 = 0.0, a1 = 0.0;
-#pragma unroll 8
-      for (int k = 0; k < kPanel; k += 2) {
-        a0 = fma(X1[k], ubuf[kPanel + k], a0);
-        a1 = fma(X1[k + 1], ubuf[kPanel + k + 1], a1);
-      }
-      u_first = a0 + a1;
-      __syncwarp();
-    }
-    for (int j = 0; j + 1 < T_; ++j) {
-      const int r = j + 1;
-      long long tp = DF_PROF_T();
-      mbar_wait(&full[j % kDfSlots], (unsigned)((j / kDfSlots) & 1), P.status);
-      if (lane == 0) DF_PROF_ADD(1, tp);
-      const double *M = reinterpret_cast<const double *>(slots + (size_t)(j % kDfSlots) * SLOT + kChTiles * CTILE +
-                                                         kXBlock * 8) + lane * kXStride;
-      const double *pj = pbuf + (j % kChRing) * kPanel;
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-      for (int k = 0; k < kPanel; k += 4) {
-        const double2 x = *reinterpret_cast<const double2 *>(M + k);
-        const double2 y = *reinterpret_cast<const double2 *>(M + k + 2);
-        const double2 a = *reinterpret_cast<const double2 *>(pj + k);
-        const double2 b = *reinterpret_cast<const double2 *>(pj + k + 2);
-        a0 = fma(x.x, a.x, a0);
-        a1 = fma(x.y, a.y, a1);
-        a2 = fma(y.x, b.x, a2);
-        a3 = fma(y.y, b.y, a3);
-      }
-      tp = DF_PROF_T();
-      double u = u_first;
-      if (r > 1) {
-        ch_spin(uready + (r % kChRing), r + 1, P.status);
-        u = ubuf[(r % kChRing) * kPanel + lane];
-        if (lane == 0) DF_PROF_ADD(2, tp);
-        tp = DF_PROF_T();
-        ch_spin(xwdone, r + 1, P.status);
-        u += xwb[(r % kChRing) * kPanel + lane];
-        if (lane == 0) DF_PROF_ADD(6, tp);
-      }
-      const double pr = u - ((a0 + a1) + (a2 + a3));
-      pbuf[(r % kChRing) * kPanel + lane] = pr;
-      st_relaxed_f64(P.ws.p + (int64_t)r * kPanel + lane, pr);  // publish: the data is its own flag
-      __syncwarp();
-      if (lane == 0) {
-        st_release_cta_smem(pdone, r + 1);
-        DF_TRACE(2, r);
-      }
-    }
-    if (lane == 0) DF_PROF_ADD(0, t_chain0);
-  } else if (warp <= 4) {
-    // ------------------------------------------------------------ B: band tiles and u_r
-    const int k4 = warp - 1;
-    double acc = 0.0;
-    double *ws_ = wsum + k4 * kPanel;
-    for (int j = 0; j < T_; ++j) {
-      const int r = j + 2 + ((k4 - j) & 3);  // my block row among j+2 .. j+5:  r = k4 + 2 (mod 4)
-      if (r < T_) {
-        if (j == 0 || r - j == kDfD) acc = 0.0;  // first tile of this block row
-        ch_spin(pdone, j + 1, P.status);
-        long long tp = DF_PROF_T();
+    const double p0 = a0 + a1;
+    pbuf[lane] = p0;
+    st_relaxed_f64(P.ws.p + lane, p0);
+  }
+  // warp d polls wt one block row ahead without blocking: the load for wt_{j+2} is in flight
+  // while block column j is processed
+  unsigned long long wt_bits = kSentinelBits;
+  if (warp == kDfD && T_ > 1) wt_bits = ld_relaxed_u64(P.ws.w + kPanel + lane);
+  named_sync(1, 256);
+
+  const long long t_chain0 = DF_PROF_T();
+  for (int j = 0; j < T_; ++j) {
+    long long tp = DF_PROF_T();
+    const double *pj = pbuf + (j & 1) * kPanel;
+    if (warp < kDfD) {
+      const int br = j + 1 + warp;
+      if (br < T_) {
         mbar_wait(&full[j % kDfSlots], (unsigned)((j / kDfSlots) & 1), P.status);
-        if (lane == 0 && k4 == 0) DF_PROF_ADD(3, tp);
-        const unsigned char *slot = slots + (size_t)(j % kDfSlots) * SLOT;
-        const unsigned char *tb = slot + (size_t)(r - j - 2) * CTILE;
-        const double *pj = pbuf + (j % kChRing) * kPanel;
+        if (tid == 0) DF_PROF_ADD(1, tp);
+        const unsigned char *tb = tiles + ((size_t)(j % kDfSlots) * kDfD + warp) * CTILE;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         if (LAYOUT == CHUB_COL_MAJOR) {
           const T *tc = reinterpret_cast<const T *>(tb) + lane;  // element (row = lane, column k) at [k][lane]
@@ -934,10 +869,10 @@ __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsign
           for (int k = 0; k < kPanel; k += 4) {
             const double2 pp = *reinterpret_cast<const double2 *>(pj + k);
             const double2 pq = *reinterpret_cast<const double2 *>(pj + k + 2);
-            a0 = fma((double)tc[k * kPanel], pp.x, a0);
-            a1 = fma((double)tc[(k + 1) * kPanel], pp.y, a1);
-            a2 = fma((double)tc[(k + 2) * kPanel], pq.x, a2);
-            a3 = fma((double)tc[(k + 3) * kPanel], pq.y, a3);
+            a0 += (double)tc[k * kPanel] * pp.x;
+            a1 += (double)tc[(k + 1) * kPanel] * pp.y;
+            a2 += (double)tc[(k + 2) * kPanel] * pq.x;
+            a3 += (double)tc[(k + 3) * kPanel] * pq.y;
           }
         } else {
 #pragma unroll
@@ -950,131 +885,80 @@ __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsign
             const int k0 = h * BOXC + c * EPC;
             if (EPC == 2) {
               const double2 pp = *reinterpret_cast<const double2 *>(pj + k0);
-              if (c & 1) { a2 = fma((double)x[0], pp.x, a2); a3 = fma((double)x[1], pp.y, a3); }
-              else       { a0 = fma((double)x[0], pp.x, a0); a1 = fma((double)x[1], pp.y, a1); }
+              if (c & 1) { a2 += (double)x[0] * pp.x; a3 += (double)x[1] * pp.y; }
+              else       { a0 += (double)x[0] * pp.x; a1 += (double)x[1] * pp.y; }
             } else {
               const double2 pp = *reinterpret_cast<const double2 *>(pj + k0);
               const double2 pq = *reinterpret_cast<const double2 *>(pj + k0 + 2);
-              a0 = fma((double)x[0], pp.x, a0);
-              a1 = fma((double)x[1], pp.y, a1);
-              a2 = fma((double)x[2 % EPC], pq.x, a2);
-              a3 = fma((double)x[3 % EPC], pq.y, a3);
+              a0 += (double)x[0] * pp.x;
+              a1 += (double)x[1] * pp.y;
+              a2 += (double)x[2 % EPC] * pq.x;
+              a3 += (double)x[3 % EPC] * pq.y;
             }
           }
         }
         }
-        acc -= (a0 + a1) + (a2 + a3);
-        if (r - j == 2) {
-          // last band tile of block row r: ua_r = X_r acc; X_r came with this block column
-          ws_[lane] = acc;
-          __syncwarp();
-          const double *X = reinterpret_cast<const double *>(slot + kChTiles * CTILE) + lane * kXStride;
-          double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
-#pragma unroll
-          for (int k = 0; k < kPanel; k += 4) {
-            const double2 x = *reinterpret_cast<const double2 *>(X + k);
-            const double2 y = *reinterpret_cast<const double2 *>(X + k + 2);
-            const double2 a = *reinterpret_cast<const double2 *>(ws_ + k);
-            const double2 b = *reinterpret_cast<const double2 *>(ws_ + k + 2);
-            b0 = fma(x.x, a.x, b0);
-            b1 = fma(x.y, a.y, b1);
-            b2 = fma(y.x, b.x, b2);
-            b3 = fma(y.y, b.y, b3);
-          }
-          ubuf[(r % kChRing) * kPanel + lane] = (b0 + b1) + (b2 + b3);
-          __syncwarp();
-          if (lane == 0) st_release_cta_smem(uready + (r % kChRing), r + 1);
+        acc[(br % (kDfD + 1)) * kPanel + lane] -= (a0 + a1) + (a2 + a3);
+      }
+      if (tid == 0) DF_PROF_ADD(2, tp);
+    } else if (warp == kDfD) {
+      if (j + 1 < T_) {
+        long long tq = DF_PROF_T();
+        const double wt = wt_bits != kSentinelBits
+                              ? __longlong_as_double((long long)wt_bits)
+                              : df_wait_value(P.ws.w + (int64_t)(j + 1) * kPanel + lane, P.status);
+        wtb[((j + 1) & 1) * kPanel + lane] = wt;
+        if (j + 2 < T_) wt_bits = ld_relaxed_u64(P.ws.w + (int64_t)(j + 2) * kPanel + lane);
+        __syncwarp();
+        if (lane == 0) { DF_PROF_ADD(4, tq); DF_TRACE(1, j + 1); }
+      }
+    } else if (warp == kDfD + 1) {
+      if (elect_one()) issue_slot(j + kDfSlots - 1);
+      __syncwarp();
+      if (kDfPf > 0) {
+        // the ring's lead (kDfSlots-1 block columns) is shorter than the DRAM latency while every SM
+        // streams, so the band tiles of block column j + kDfSlots-1 + kDfPf go to L2 now
+        const int jp = j + kDfSlots - 1 + kDfPf;
+        const int np = min(kDfD, T_ - 1 - jp);
+        if (LAYOUT == CHUB_COL_MAJOR) {
+          if (lane < np) tma_prefetch_2d(tmap32, (jp + 1 + lane) * kPanel, jp * kPanel);
+        } else if (lane < np * HALVES) {
+          tma_prefetch_2d(tmap32, jp * kPanel + (lane % HALVES) * BOXC, (jp + 1 + lane / HALVES) * kPanel);
         }
       }
-      __syncwarp();
-      if (lane == 0) st_release_cta_smem(bprog + k4, j + 1);  // my reads of ring slot j % kDfSlots are done
     }
-  } else if (warp == 5) {
-    // ------------------------------------------------------------ P: wt_r from the workers (global), xw_r = X_r wt_r
-    unsigned long long b0 = kSentinelBits, b1 = kSentinelBits;
-    if (T_ > 2) b0 = ld_relaxed_u64(P.ws.w + 2 * kPanel + lane);
-    if (T_ > 3) b1 = ld_relaxed_u64(P.ws.w + 3 * kPanel + lane);
-    for (int r = 2; r < T_; ++r) {
-      // X_r travels with block column r - 2: my row of it goes into registers, the slot is released
-      const int jx = r - 2;
-      mbar_wait(&full[jx % kDfSlots], (unsigned)((jx / kDfSlots) & 1), P.status);
-      const double *X = reinterpret_cast<const double *>(slots + (size_t)(jx % kDfSlots) * SLOT + kChTiles * CTILE) +
-                        lane * kXStride;
-      double2 xr[kPanel / 2];
-#pragma unroll
-      for (int k = 0; k < kPanel / 2; ++k) xr[k] = *reinterpret_cast<const double2 *>(X + 2 * k);
+    tp = DF_PROF_T();
+    named_sync(1, 256);
+    if (warp == 0 && j + 1 < T_) {
+      const int r = j + 1;
+      double *a = acc + (r % (kDfD + 1)) * kPanel;
+      wvec[lane] = wtb[(r & 1) * kPanel + lane] + a[lane];
+      a[lane] = 0.0;
       __syncwarp();
-      if (lane == 0) st_release_cta_smem(xprog, jx + 1);
-      long long tq = DF_PROF_T();
-      const double *nx = r + 1 < T_ ? P.ws.w + (int64_t)(r + 1) * kPanel + lane : nullptr;
-      const double wt = df_wait_value2(P.ws.w + (int64_t)r * kPanel + lane, nx, b0, b1, P.status);
-      b0 = b1;
-      b1 = r + 2 < T_ ? ld_relaxed_u64(P.ws.w + (int64_t)(r + 2) * kPanel + lane) : kSentinelBits;
-      if (lane == 0) { DF_PROF_ADD(5, tq); DF_TRACE(1, r); }
-      wtb[lane] = wt;
-      __syncwarp();
+      if (tid == 0) DF_PROF_ADD(3, tp);
+      tp = DF_PROF_T();
+      const double *X = Xs + (j % kDfSlots) * kXBlock + lane * kXStride;
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-      for (int k = 0; k < kPanel / 2; k += 2) {
-        const double2 a = *reinterpret_cast<const double2 *>(wtb + 2 * k);
-        const double2 b = *reinterpret_cast<const double2 *>(wtb + 2 * k + 2);
-        a0 = fma(xr[k].x, a.x, a0);
-        a1 = fma(xr[k].y, a.y, a1);
-        a2 = fma(xr[k + 1].x, b.x, a2);
-        a3 = fma(xr[k + 1].y, b.y, a3);
+      for (int k = 0; k < kPanel; k += 4) {
+        const double2 x = *reinterpret_cast<const double2 *>(X + k);
+        const double2 y = *reinterpret_cast<const double2 *>(X + k + 2);
+        const double2 u = *reinterpret_cast<const double2 *>(wvec + k);
+        const double2 z = *reinterpret_cast<const double2 *>(wvec + k + 2);
+        a0 += x.x * u.x;
+        a1 += x.y * u.y;
+        a2 += y.x * z.x;
+        a3 += y.y * z.y;
       }
-      // xwb[r % 8] was last read for p_{r-8}: C is long past it (p_{r-1} needs ua/xw of r-1 only)
-      xwb[(r % kChRing) * kPanel + lane] = (a0 + a1) + (a2 + a3);
-      __syncwarp();
-      if (lane == 0) st_release_cta_smem(xwdone, r + 1);
+      const double pr = (a0 + a1) + (a2 + a3);
+      pbuf[(r & 1) * kPanel + lane] = pr;
+      st_relaxed_f64(P.ws.p + (int64_t)r * kPanel + lane, pr);
+      if (tid == 0) { DF_PROF_ADD(5, tp); DF_TRACE(2, r); }
     }
-  } else if (warp == 6) {
-    // ------------------------------------------------------------ T: TMA loads, block column jj -> slot jj % 4
-    for (int jj = 0; jj < T_; ++jj) {
-      if (kDfPf > 0) {  // band tiles of block column jj + kDfPf -> L2 (all lanes; nothing to wait for)
-        const int jp = jj + kDfPf;
-        const int np = min(kChTiles, T_ - 2 - jp);
-        if (LAYOUT == CHUB_COL_MAJOR) {
-          if (lane < np) tma_prefetch_2d(tmap32, (jp + 2 + lane) * kPanel, jp * kPanel);
-        } else if (lane < np * HALVES) {
-          tma_prefetch_2d(tmap32, jp * kPanel + (lane % HALVES) * BOXC, (jp + 2 + lane / HALVES) * kPanel);
-        }
-      }
-      if (elect_one()) {
-        if (jj >= kDfSlots) {
-          // the slot held block column jj - 4: read by the band warps (tiles, X) and by C (M1 -> p_{jj-3})
-          const int done = jj - kDfSlots + 1;
-          for (int k = 0; k < 4; ++k) ch_spin(bprog + k, done, P.status);
-          ch_spin(pdone, min(done + 1, T_), P.status);
-          if (done + 1 < T_) ch_spin(xprog, done, P.status);  // (X_{jj-2} travelled with block column jj - 4)
-        }
-        const int slot = jj % kDfSlots;
-        void *bar = &full[slot];
-        unsigned char *sb = slots + (size_t)slot * SLOT;
-        int ntiles = min(kChTiles, T_ - 2 - jj);
-        if (ntiles < 0) ntiles = 0;
-        const bool do_x = jj + 2 < T_, do_m = jj + 1 < T_;
-        const unsigned bytes = (unsigned)ntiles * CTILE + (do_x ? kXBlock * 8u : 0u) + (do_m ? kXBlock * 8u : 0u);
-        if (bytes == 0) {
-          mbar_arrive(bar);
-        } else {
-          mbar_arrive_expect_tx(bar, bytes);
-          if (do_m) bulk_g2s(sb + kChTiles * CTILE + kXBlock * 8, P.ws.M1 + (int64_t)(jj + 1) * kXBlock, kXBlock * 8u, bar);
-          for (int q = 0; q < ntiles; ++q) {
-            if (LAYOUT == CHUB_COL_MAJOR) {  // (coordinates: row first -- rows are the contiguous dimension)
-              tma_load_2d(sb + (size_t)q * CTILE, tmap32, (jj + 2 + q) * kPanel, jj * kPanel, bar);
-            } else {
-              for (int h = 0; h < HALVES; ++h)
-                tma_load_2d(sb + (size_t)q * CTILE + h * 4096, tmap32, jj * kPanel + h * BOXC, (jj + 2 + q) * kPanel, bar);
-            }
-          }
-          if (do_x) bulk_g2s(sb + kChTiles * CTILE, P.ws.X + (int64_t)(jj + 2) * kXBlock, kXBlock * 8u, bar);
-        }
-      }
-      __syncwarp();
-    }
+    named_sync(1, 256);
   }
-  if (P.prof && lane == 0 && (warp == 0 || warp == 1 || warp == 5)) {
+  if (tid == 0) DF_PROF_ADD(0, t_chain0);
+  if (P.prof && (tid == 0 || tid == kDfD * 32)) {
     for (int i = 0; i < 8; ++i)
       if (pacc[i]) P.prof[(size_t)blockIdx.x * 16 + i] = pacc[i];
   }
@@ -1082,7 +966,8 @@ __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsign
 
 template <typename T>
 inline size_t df_chain_rm_smem() {
-  return (size_t)ChGeom<T>::BASE + (size_t)kDfSlots * ChGeom<T>::SLOT;
+  return 4096 + ((size_t)(kDfSlots * kXBlock * 8 + 1023) / 1024) * 1024 +
+         (size_t)kDfSlots * kDfD * RmGeom<T>::CTILE;
 }
 
 // ---- coefficient warp of a worker CTA (shared by the row-major and the column-major workers)
@@ -1094,7 +979,7 @@ __device__ __forceinline__ void df_coef_warp(T *v, const DfParams &P, double *co
   // ---------------- coefficient warp (software-pipelined: the poll of block column s+1 is in
   // flight while the coefficients of block column s are formed).  A ring slot is reused once
   // every row warp has finished the step that last read it (prog[]); finished warps have left.
-  double t_run = 1.0, S_run = 1.0;
+  double t_run = P.ws.scal[0], S_run = P.ws.scal[1];  // (1, 1) unless a blocked driver carries them over
   unsigned long long b0 = ld_relaxed_u64(P.ws.p + lane);
   unsigned long long b1 = T_ > 1 ? ld_relaxed_u64(P.ws.p + kPanel + lane) : kSentinelBits;
   double ndg = P.ws.dg[lane];
@@ -1144,7 +1029,11 @@ __device__ __forceinline__ void df_coef_warp(T *v, const DfParams &P, double *co
       cf[3 * kPanel + lane] = fabs(dg) * tk1 * rinv;
       __syncwarp();
       if (lane == 0) st_release_cta_smem(cprog, pan + 1);
-      if (wkr == pan % Wk && k < n) {  // one worker per panel leaves rotg's z_k in v[k]
+      if (wkr == pan % Wk) {  // one worker per panel: coefficients for the rectangles below a diagonal block
+        P.ws.c[k] = ck;
+        P.ws.sg[k] = sigk;
+      }
+      if (wkr == pan % Wk && k < n) {  // ... and rotg's z_k in v[k]
         const double Sk = (__popc(negmask & ((1u << lane) - 1u)) & 1) ? -S_run : S_run;
         const double nuk = Sk * dg * pk / sqrt(tk);
         const double sk = Sk * sgn * pk / sqrt(tk1);
@@ -1159,6 +1048,7 @@ __device__ __forceinline__ void df_coef_warp(T *v, const DfParams &P, double *co
     if (lane == 0 && wkr == 0) DF_TRACE(4, pan);
     if (lane == 0) DF_PROF_ADD(7, tq);
   }
+  if (UPDATE && wkr == 0 && lane == 0) { P.ws.scal[4] = t_run; P.ws.scal[5] = S_run; }
   if (P.prof && lane == 0) {
     P.prof[(size_t)blockIdx.x * 16 + 6] = pacc[6];
     P.prof[(size_t)blockIdx.x * 16 + 7] = pacc[7];
@@ -1337,11 +1227,16 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
   // loads run two pairs ahead (issued after the compute phase, when the store of the pair whose
   // stages they reuse has drained).
   static_assert(kDfStages == 6, "the pair schedule assumes a ring of 6 stages");
+#ifndef CHUB_DF_AHEAD
+#define CHUB_DF_AHEAD 2  // pairs of block columns a row warp keeps in flight beyond the one it computes
+#endif
   if (elect_one()) {
     issue_load(0, 0);
     issue_load(1, 1);
-    issue_load(2, 2);
-    issue_load(3, 3);
+    if (CHUB_DF_AHEAD >= 2) {
+      issue_load(2, 2);
+      issue_load(3, 3);
+    }
   }
   __syncwarp();
   const long long t_wk0 = DF_PROF_T();
@@ -1382,9 +1277,15 @@ __device__ void df_worker_rm(T *L, T *v, const DfParams &P, const CUtensorMap *t
     // The ring holds the pair being processed and two pairs of loads in flight.  Pair S+2 reuses the
     // stages of pair S-1, whose TMA store has had this whole compute phase to drain.
     if (elect_one()) {
-      if (s >= 2) bulk_wait_read<0>();
-      issue_load(s + 4, stnn);
-      issue_load(s + 5, stnn + 1);
+      if (CHUB_DF_AHEAD >= 2) {
+        if (s >= 2) bulk_wait_read<0>();
+        issue_load(s + 4, stnn);
+        issue_load(s + 5, stnn + 1);
+      } else {  // one pair ahead: the next pair's stages held pair S-2, whose store is two commits back
+        if (s >= 2) bulk_wait_read<1>();
+        issue_load(s + 2, stn);
+        issue_load(s + 3, stn + 1);
+      }
     }
     if (prof_me) DF_PROF_ADD(2, tp);
     tp = DF_PROF_T();
@@ -1429,6 +1330,153 @@ df_kernel_rm(T *L, T *v, DfParams P, const __grid_constant__ CUtensorMap tmap8,
   } else {
     df_worker_rm<T, UPDATE, PROF>(L, v, P, &tmap8, df_smem);
   }
+}
+
+// =====================================================================================
+// Rectangle below a diagonal block (row-major): factors beyond the persistent kernel's row capacity
+// =====================================================================================
+// The persistent kernel keeps every row in flight at once, so one launch covers at most 147 x 14 x 8 =
+// 16464 rows.  Larger factors are cut into diagonal blocks of at most that order (blocked driver,
+// api.cu): the persistent kernel updates diagonal block J (its columns' (p, c, sigma) end up in global
+// memory), and this kernel applies those columns to ALL rows below the block -- the part of the
+// right-looking update that has no sequential dependency at all:
+//     L_ik <- c_k L_ik + sigma_k w_i ,   w_i <- w_i - L_ik p_k      (k over the block's columns)
+// leaving the residual w_i in ws.w for the next diagonal block.  A warp takes 8 rows and walks the block's
+// columns in 32-column tiles through a ring of TMA boxes, the block column's coefficients riding along;
+// same lane mapping and arithmetic as the persistent kernel's workers.  UPDATE = false: residual only
+// (forward substitution of the downdate).
+constexpr int kRectStages = 4;
+constexpr int kRectWarps = 14;
+
+template <typename T>
+struct RectGeom {
+  static constexpr int STAGE = RmGeom<T>::WTILE + 1024;  // tile + (p, c, sigma)[32] doubles (768 B, padded)
+};
+
+template <typename T, bool UPDATE>
+__global__ void __launch_bounds__(kRectWarps * 32, 1)
+rect_apply_rm_kernel(int n, int row_begin, int col_begin, int ncols, LargeWs ws, const int32_t *status,
+                     const __grid_constant__ CUtensorMap tmap8) {
+  constexpr int HALVES = RmGeom<T>::HALVES, BOXC = RmGeom<T>::BOXC, CPT = RmGeom<T>::CPT;
+  constexpr int WTILE = RmGeom<T>::WTILE, STAGE = RectGeom<T>::STAGE;
+  extern __shared__ __align__(1024) unsigned char rc_smem[];
+  if (*status != 0) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(rc_smem) + warp * kRectStages;
+  unsigned char *mystage = rc_smem + 1024 + (size_t)warp * kRectStages * STAGE;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRectWarps * kRectStages; ++i) mbar_init(reinterpret_cast<unsigned long long *>(rc_smem) + i, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int g = lane >> 3, r8 = lane & 7;
+  const int hh = (g * 8 * (int)sizeof(T)) / 128;
+  const int cb = ((g * 8 * (int)sizeof(T)) % 128) / 16;
+  const unsigned my_off = hh * 1024 + r8 * 128;
+  const int nsteps = ncols / kPanel;
+  const int ngroups = (n - row_begin + 7) / 8;
+  unsigned it = 0;  // tiles this warp has consumed so far (ring position / mbarrier phase)
+  for (int grp = (int)blockIdx.x * kRectWarps + warp; grp < ngroups; grp += (int)gridDim.x * kRectWarps) {
+    const int row0 = row_begin + grp * 8;
+    const int row = row0 + r8;
+    double w = row < n ? ws.w[row] : 0.0;
+
+    auto issue_load = [&](int s) {  // elected lane; stage / phase follow the warp's running tile count
+      if (s >= nsteps) return;
+      const unsigned st = (it + (unsigned)s) % kRectStages;
+      void *bar = &full[st];
+      unsigned char *stg = mystage + (size_t)st * STAGE;
+      const int c0 = col_begin + s * kPanel;
+      mbar_arrive_expect_tx(bar, (unsigned)WTILE + (UPDATE ? 768u : 256u));
+      tma_load_2d(stg, &tmap8, c0, row0, bar);
+      if (HALVES == 2) tma_load_2d(stg + 1024, &tmap8, c0 + BOXC, row0, bar);
+      bulk_g2s(stg + WTILE, ws.p + c0, 256u, bar);
+      if (UPDATE) {
+        bulk_g2s(stg + WTILE + 256, ws.c + c0, 256u, bar);
+        bulk_g2s(stg + WTILE + 512, ws.sg + c0, 256u, bar);
+      }
+    };
+
+    if (elect_one()) {
+      bulk_wait_read<0>();  // (the previous group's last stores have left their stages)
+      for (int s = 0; s < kRectStages - 1; ++s) issue_load(s);
+    }
+    __syncwarp();
+    for (int s = 0; s < nsteps; ++s) {
+      const unsigned st = (it + (unsigned)s) % kRectStages;
+      const unsigned ph = ((it + (unsigned)s) / kRectStages) & 1u;
+      mbar_wait(&full[st], ph, const_cast<int32_t *>(status));
+      unsigned char *stg = mystage + (size_t)st * STAGE;
+      unsigned char *rowp = stg + my_off;
+      const double *cf = reinterpret_cast<const double *>(stg + WTILE) + g * 8;
+      int4 raw[CPT];
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) raw[i] = *reinterpret_cast<const int4 *>(rowp + (((cb + i) ^ r8) << 4));
+      T *x = reinterpret_cast<T *>(raw);
+      double lo[8], pre[8];
+      double run = 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const double2 a = *reinterpret_cast<const double2 *>(cf + j);
+        lo[j] = (double)x[j];
+        pre[j] = run;
+        run = fma(lo[j], a.x, run);
+        lo[j + 1] = (double)x[j + 1];
+        pre[j + 1] = run;
+        run = fma(lo[j + 1], a.y, run);
+      }
+      double incl = run;
+      double y = __shfl_up_sync(0xffffffffu, incl, 8);
+      if (g >= 1) incl += y;
+      y = __shfl_up_sync(0xffffffffu, incl, 16);
+      if (g >= 2) incl += y;
+      const double total = __shfl_sync(0xffffffffu, incl, 24 + r8);
+      const double wseg = w - (incl - run);
+      w -= total;
+      if (UPDATE) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const double2 c = *reinterpret_cast<const double2 *>(cf + kPanel + j);
+          const double2 d = *reinterpret_cast<const double2 *>(cf + 2 * kPanel + j);
+          x[j] = (T)fma(c.x, lo[j], d.x * (wseg - pre[j]));
+          x[j + 1] = (T)fma(c.y, lo[j + 1], d.y * (wseg - pre[j + 1]));
+        }
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) *reinterpret_cast<int4 *>(rowp + (((cb + i) ^ r8) << 4)) = raw[i];
+        fence_proxy_async();
+      }
+      __syncwarp();
+      if (elect_one()) {
+        if (UPDATE) {
+          const int c0 = col_begin + s * kPanel;
+          tma_store_2d(&tmap8, c0, row0, stg);
+          if (HALVES == 2) tma_store_2d(&tmap8, c0 + BOXC, row0, stg + 1024);
+          bulk_commit();
+          bulk_wait_read<1>();  // the store of step s-1 has left the stage that step s+3 loads into
+        }
+        issue_load(s + kRectStages - 1);
+      }
+      __syncwarp();
+    }
+    it += (unsigned)nsteps;
+    if (g == 0 && row < n) ws.w[row] = w;
+  }
+  if (elect_one()) bulk_wait_all<0>();
+}
+
+template <typename T>
+inline size_t rect_apply_rm_smem() { return 1024 + (size_t)kRectWarps * kRectStages * RectGeom<T>::STAGE; }
+
+// The blocked driver's first kernel: w <- v for every row, check_diag over the WHOLE diagonal (the
+// persistent kernel's pre-pass only sees its own block), (t, S) <- (1, 1).
+template <typename T, int LAYOUT>
+__global__ void blocked_init_kernel(const T *L, int n, int64_t ld, const T *v, LargeWs ws, int flags, int32_t *status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_pad = (n + 31) & ~31;
+  if (i < n_pad) ws.w[i] = i < n ? df_sanitize((double)v[i]) : 0.0;
+  if (i < n && (flags & CHUB_FLAG_CHECK_DIAG) && L[idx<LAYOUT>(i, i, ld)] == T(0)) atomicMax(status, CHUB_STATUS_ZERO_DIAG);
+  if (i == 0) { ws.scal[4] = 1.0; ws.scal[5] = 1.0; }
 }
 
 // =====================================================================================
@@ -1970,10 +2018,10 @@ inline EncodeTiledFn get_encode_tiled() {
 
 // Row-major n x n matrix with leading dimension ld: boxes of [box_rows][128 bytes], SWIZZLE_128B.
 template <typename T>
-inline bool make_tmap(CUtensorMap *map, T *L, int64_t n, int64_t ld, int box_rows) {
+inline bool make_tmap(CUtensorMap *map, T *L, int64_t n, int64_t ld, int box_rows, int64_t rows = -1) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
-  const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)n};
+  const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)(rows < 0 ? n : rows)};  // (columns, rows)
   const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(T)};
   const cuuint32_t box[2] = {(cuuint32_t)RmGeom<T>::BOXC, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
@@ -2042,7 +2090,11 @@ inline bool dataflow_supported(int64_t n, int64_t ld, int layout, const T *L) {
 // sweep kernels).  Returns a cudaError_t-style code; *launches = kernels launched.
 template <typename T, int LAYOUT, bool UPDATE>
 int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs &ws,
-                    int32_t *status, cudaStream_t st, int64_t *launches) {
+                    int32_t *status, cudaStream_t st, int64_t *launches, const double *w_in = nullptr,
+                    bool chain_only = false) {
+  // w_in / chain_only: blocked driver (launch_blocked_rm) -- this call handles one diagonal block whose
+  // input vector is the residual w_in, and for a downdate only the forward substitution (the
+  // coefficient and sweep kernels run once, over the whole factor, afterwards)
   *launches = 0;
   const int ni = (int)n;
   const int n_pad = (ni + 31) & ~31;
@@ -2059,7 +2111,7 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
     cp = cm_plan<T>(n, ld, L);
     if (cp.ok && !make_tmap_cm<T>(&tmapc, L, n, ld)) cp.ok = false;
   }
-  const bool tm = rp.ok || cp.ok;  // a tensor-map kernel (chain with M1, band depth kDfD)
+  const bool tm = rp.ok || cp.ok;  // a tensor-map kernel (band depth kDfD)
   DfPlan pl;
   if (!tm) {
     pl = df_plan<T>(n, ld, LAYOUT, L);
@@ -2067,7 +2119,7 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
   }
   // one pre-pass: w-tilde / v0 / dg / sentinels (prepare) and the inverse diagonal blocks
   df_prepass_kernel<T, LAYOUT><<<(nb + 3) / 4, 128, 0, st>>>(L, ni, ld, v, ws, flags, status,
-                                                              tm ? kDfD : kV2D, tm);
+                                                              tm ? kDfD : kV2D, false, w_in);
   ++*launches;
   DfParams P;
   P.n = ni; P.T = nb; P.ld = ld; P.ws = ws; P.status = status;
@@ -2101,7 +2153,7 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
   }
   if (e != cudaSuccess) return (int)e;
   ++*launches;
-  if (!UPDATE) {
+  if (!UPDATE && !chain_only) {
     large_dd_coef_kernel<T, LAYOUT><<<1, 1024, 0, st>>>(L, ni, ld, v, ws, status);
     ++*launches;
     if (rp.ok && !getenv("CHUB_DD_SWEEP_V1")) {
@@ -2123,6 +2175,86 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
   }
   e = cudaGetLastError();
   return (int)e;
+}
+
+// ---- blocked driver (row-major): factors beyond the persistent kernel's row capacity.
+// Diagonal blocks of at most kBlockedMax rows (a multiple of 32): persistent kernel on block J (input = the
+// residual left by the panels to its left, (t, S) carried over), then rect_apply_rm_kernel applies the
+// block's columns to every row below it.  A downdate runs the same two kernels read-only (forward
+// substitution), then the coefficient and sweep kernels once over the whole factor.
+constexpr int64_t kBlockedMax = 16384;
+
+inline LargeWs ws_offset(const LargeWs &ws, int64_t off) {  // the workspace as diagonal block [off, ..) sees it
+  LargeWs w = ws;
+  w.X += (off / kPanel) * kXBlock;
+  w.M1 += (off / kPanel) * kXBlock;
+  w.w += off; w.p += off; w.c += off; w.sg += off; w.dn += off; w.v0 += off; w.dg += off;
+  return w;  // scal and flags are shared
+}
+
+template <typename T>
+inline bool blocked_supported(int64_t n, int64_t ld, const T *L) {
+  constexpr int EPC = 16 / sizeof(T);
+  if (n <= kBlockedMax || n >= (1LL << 31) || (ld % EPC) != 0 || (reinterpret_cast<uintptr_t>(L) & 15) != 0) return false;
+  return get_encode_tiled() != nullptr && rm_plan<T>(kBlockedMax, ld, L).ok;
+}
+
+template <typename T, bool UPDATE>
+int launch_blocked_rm(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs &ws, int32_t *status,
+                      cudaStream_t st, int64_t *launches) {
+  *launches = 0;
+  const int ni = (int)n;
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // block sizes: as many full blocks as fit, the remainder split evenly over the last two if it is small
+  int64_t sizes[64];
+  int nblk = 0;
+  for (int64_t left = n; left > 0;) {
+    int64_t take = left <= kBlockedMax ? left : kBlockedMax;
+    if (left > kBlockedMax && left - kBlockedMax < 2048) take = ((left / 2 + kPanel - 1) / kPanel) * kPanel;
+    if (nblk >= 64) return (int)cudaErrorNotSupported;
+    sizes[nblk++] = take;
+    left -= take;
+  }
+  blocked_init_kernel<T, CHUB_ROW_MAJOR><<<(ni + 255) / 256, 256, 0, st>>>(L, ni, ld, v, ws, flags, status);
+  ++*launches;
+  alignas(64) CUtensorMap tmap8;
+  if (!make_tmap<T>(&tmap8, L, n, ld, 8)) return (int)cudaErrorNotSupported;
+  auto rk = rect_apply_rm_kernel<T, UPDATE>;
+  const size_t rsm = rect_apply_rm_smem<T>();
+  cudaError_t e = cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
+  if (e != cudaSuccess) return (int)e;
+  int64_t off = 0;
+  for (int J = 0; J < nblk; ++J) {
+    const int64_t nb_ = sizes[J];
+    int64_t nl = 0;
+    // (check_diag was done for the whole diagonal by the init kernel; status != 0 stops every kernel)
+    int rc = launch_dataflow<T, CHUB_ROW_MAJOR, UPDATE>(L + off * ld + off, nb_, ld, v + off, 0, ws_offset(ws, off),
+                                                        status, st, &nl, ws.w + off, true);
+    *launches += nl;
+    if (rc) return rc;
+    if (off + nb_ < n) {
+      const int rows = (int)(n - off - nb_);
+      const int groups = (rows + 7) / 8;
+      const int grid = std::max(1, std::min(sms, (groups + kRectWarps - 1) / kRectWarps));
+      rk<<<grid, kRectWarps * 32, rsm, st>>>(ni, (int)(off + nb_), (int)off, (int)nb_, ws, status, tmap8);
+      ++*launches;
+    }
+    off += nb_;
+  }
+  if (!UPDATE) {
+    const int nb = (ni + 31) / 32;
+    large_dd_coef_kernel<T, CHUB_ROW_MAJOR><<<1, 1024, 0, st>>>(L, ni, ld, v, ws, status);
+    ++*launches;
+    auto sk = dd_sweep_rm_kernel<T>;
+    const size_t ssm = dd_sweep_rm_smem<T>();
+    e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
+    if (e != cudaSuccess) return (int)e;
+    sk<<<nb, 128, ssm, st>>>(L, ni, ld, ws, status, tmap8);
+    ++*launches;
+  }
+  return (int)cudaGetLastError();
 }
 
 }  // namespace chub

@@ -9,8 +9,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
-
+#include <thread>
 #include <vector>
 
 #include "large.cuh"
@@ -30,7 +31,7 @@ struct HostCache {
   cudaStream_t st_out = nullptr;  // device -> host copies
   std::vector<cudaEvent_t> ev_in, ev_done;
 };
-std::mutex h_mu;
+std::mutex h_mu[64];  // one per device: host calls on different devices of a process do not serialise
 HostCache h_cache[64];
 thread_local char h_err[256] = "";
 }  // namespace
@@ -98,7 +99,9 @@ constexpr int64_t kStreamMinN = 2048;
 constexpr int64_t kXferCols = 512;  // columns per host <-> device transfer panel (measured: 256 24.7 ms, 512 24.0, 1024 27.7 at n = 16384)
 
 template <typename T, int LAYOUT>
-int run_host_update_streamed(HostCache &c, T *Lh, int64_t n, int64_t ld, T *vh, int32_t *status) {
+int run_host_update_streamed(HostCache &c, const T *Lh, int64_t ld, T *Lo, int64_t ldo, int64_t n, T *vh,
+                             int32_t *status) {
+  // Lh / ld: the caller's factor (read); Lo / ldo: where the updated lower triangle goes (== Lh in place)
   using namespace chub;
   const size_t es = sizeof(T);
   const int ni = (int)n;
@@ -133,12 +136,12 @@ int run_host_update_streamed(HostCache &c, T *Lh, int64_t n, int64_t ld, T *vh, 
     const int64_t j0 = (int64_t)P * xfer;
     const int64_t bw = std::min<int64_t>(xfer, n - j0);
     // rectangle rows [j0, n) x columns [j0, j0 + bw)
-    size_t off_d, off_h, width, height;
+    size_t off_d, off_h, off_o, width, height;
     if (LAYOUT == CHUB_ROW_MAJOR) {
-      off_d = (size_t)(j0 * ldd + j0); off_h = (size_t)(j0 * ld + j0);
+      off_d = (size_t)(j0 * ldd + j0); off_h = (size_t)(j0 * ld + j0); off_o = (size_t)(j0 * ldo + j0);
       width = (size_t)bw * es; height = (size_t)(n - j0);
     } else {
-      off_d = (size_t)(j0 + j0 * ldd); off_h = (size_t)(j0 + j0 * ld);
+      off_d = (size_t)(j0 + j0 * ldd); off_h = (size_t)(j0 + j0 * ld); off_o = (size_t)(j0 + j0 * ldo);
       width = (size_t)(n - j0) * es; height = (size_t)bw;
     }
     HCK(cudaMemcpy2DAsync(Ld + off_d, (size_t)ldd * es, Lh + off_h, (size_t)ld * es, width, height,
@@ -156,7 +159,7 @@ int run_host_update_streamed(HostCache &c, T *Lh, int64_t n, int64_t ld, T *vh, 
     HCK(cudaGetLastError());
     HCK(cudaEventRecord(c.ev_done[P], c.st));
     HCK(cudaStreamWaitEvent(c.st_out, c.ev_done[P], 0));
-    HCK(cudaMemcpy2DAsync(Lh + off_h, (size_t)ld * es, Ld + off_d, (size_t)ldd * es, width, height,
+    HCK(cudaMemcpy2DAsync(Lo + off_o, (size_t)ldo * es, Ld + off_d, (size_t)ldd * es, width, height,
                           cudaMemcpyDeviceToHost, c.st_out));
   }
   HCK(cudaMemcpyAsync(vh, vd, (size_t)n * es, cudaMemcpyDeviceToHost, c.st_out));
@@ -168,14 +171,27 @@ int run_host_update_streamed(HostCache &c, T *Lh, int64_t n, int64_t ld, T *vh, 
 
 typedef int (*dev_fn)(void *, int64_t, int64_t, int, void *, int, void *, size_t, int32_t *, void *);
 
-int run_host(dev_fn fn, bool is_update, size_t es, void *L, int64_t n, int64_t ld, int layout, void *v,
-             int flags, int32_t *status) {
-  if (!status || n < 0 || ld < n) return (int)cudaErrorInvalidValue;
+// Strict upper triangle src -> dst on the host (copy mode: the reference returns a full copy of L,
+// _seeger.py:272-273, so whatever sits above the diagonal travels along -- on the host, never over PCIe).
+void copy_upper_host(char *dst, int64_t ldd, const char *src, int64_t lds, int64_t n, int layout, size_t es,
+                     int64_t i0, int64_t i1) {
+  for (int64_t i = i0; i < i1; ++i) {
+    if (layout == CHUB_ROW_MAJOR) {  // row i: columns i+1 .. n-1
+      if (i + 1 < n) memcpy(dst + (size_t)(i * ldd + i + 1) * es, src + (size_t)(i * lds + i + 1) * es, (size_t)(n - 1 - i) * es);
+    } else {                         // column i: rows 0 .. i-1
+      if (i > 0) memcpy(dst + (size_t)(i * ldd) * es, src + (size_t)(i * lds) * es, (size_t)i * es);
+    }
+  }
+}
+
+int run_host(dev_fn fn, bool is_update, size_t es, const void *L, int64_t ld, void *Lo, int64_t ldo, int64_t n,
+             int layout, void *v, int flags, int32_t *status) {
+  if (!status || n < 0 || ld < n || ldo < n) return (int)cudaErrorInvalidValue;
   *status = 0;
   if (n == 0) return 0;
   int dev = 0;
   HCK(cudaGetDevice(&dev));
-  std::lock_guard<std::mutex> lk(h_mu);
+  std::lock_guard<std::mutex> lk(h_mu[dev & 63]);
   HostCache &c = h_cache[dev & 63];
   int rc = ensure(c, (size_t)n * n * es, (size_t)n * es);
   if (rc) return rc;
@@ -188,14 +204,32 @@ int run_host(dev_fn fn, bool is_update, size_t es, void *L, int64_t n, int64_t l
     }
     flags &= ~CHUB_FLAG_CHECK_DIAG;
   }
+  // copy mode: the strict upper triangle goes from L to Lo on host threads while the GPU works
+  std::vector<std::thread> uppers;
+  if (Lo != L && n > 1) {
+    const int nt = n >= 4096 ? 4 : 1;
+    for (int t = 0; t < nt; ++t) {
+      // equal areas: the upper triangle's rows shrink (row-major) / columns grow (column-major)
+      auto cut = [&](int q) -> int64_t {
+        const double f = (double)q / nt;
+        return layout == CHUB_ROW_MAJOR ? (int64_t)(n * (1.0 - sqrt(1.0 - f))) : (int64_t)(n * sqrt(f));
+      };
+      const int64_t i0 = t == 0 ? 0 : cut(t), i1 = t == nt - 1 ? n : cut(t + 1);
+      uppers.emplace_back(copy_upper_host, (char *)Lo, ldo, (const char *)L, ld, n, layout, es, i0, i1);
+    }
+  }
+  struct Joiner {
+    std::vector<std::thread> &t;
+    ~Joiner() { for (auto &x : t) if (x.joinable()) x.join(); }
+  } joiner{uppers};
   if (is_update && n >= kStreamMinN && !getenv("CHUB_HOST_NO_STREAM")) {
     if (es == 8)
       return layout == CHUB_ROW_MAJOR
-                 ? run_host_update_streamed<double, CHUB_ROW_MAJOR>(c, (double *)L, n, ld, (double *)v, status)
-                 : run_host_update_streamed<double, CHUB_COL_MAJOR>(c, (double *)L, n, ld, (double *)v, status);
+                 ? run_host_update_streamed<double, CHUB_ROW_MAJOR>(c, (const double *)L, ld, (double *)Lo, ldo, n, (double *)v, status)
+                 : run_host_update_streamed<double, CHUB_COL_MAJOR>(c, (const double *)L, ld, (double *)Lo, ldo, n, (double *)v, status);
     return layout == CHUB_ROW_MAJOR
-               ? run_host_update_streamed<float, CHUB_ROW_MAJOR>(c, (float *)L, n, ld, (float *)v, status)
-               : run_host_update_streamed<float, CHUB_COL_MAJOR>(c, (float *)L, n, ld, (float *)v, status);
+               ? run_host_update_streamed<float, CHUB_ROW_MAJOR>(c, (const float *)L, ld, (float *)Lo, ldo, n, (float *)v, status)
+               : run_host_update_streamed<float, CHUB_COL_MAJOR>(c, (const float *)L, ld, (float *)Lo, ldo, n, (float *)v, status);
   }
   // device copy is dense (ld = n)
   rc = copy_tri((char *)c.L, (const char *)L, n, n, ld, layout, es, cudaMemcpyHostToDevice, c.st);
@@ -211,7 +245,7 @@ int run_host(dev_fn fn, bool is_update, size_t es, void *L, int64_t n, int64_t l
   if (*status == CHUB_STATUS_ZERO_DIAG) return 0;  // L and v untouched
   HCK(cudaMemcpyAsync(v, c.v, (size_t)n * es, cudaMemcpyDeviceToHost, c.st));
   if (*status == CHUB_STATUS_OK) {
-    rc = copy_tri((char *)L, (const char *)c.L, n, ld, n, layout, es, cudaMemcpyDeviceToHost, c.st);
+    rc = copy_tri((char *)Lo, (const char *)c.L, n, ldo, n, layout, es, cudaMemcpyDeviceToHost, c.st);
     if (rc) return rc;
   }
   HCK(cudaStreamSynchronize(c.st));
@@ -223,22 +257,39 @@ int run_host(dev_fn fn, bool is_update, size_t es, void *L, int64_t n, int64_t l
 extern "C" {
 
 int chub_update_host_f64(void *L, int64_t n, int64_t ld, int layout, void *v, int flags, int32_t *status) {
-  return run_host(chub_update_f64, true, 8, L, n, ld, layout, v, flags, status);
+  return run_host(chub_update_f64, true, 8, L, ld, L, ld, n, layout, v, flags, status);
 }
 int chub_update_host_f32(void *L, int64_t n, int64_t ld, int layout, void *v, int flags, int32_t *status) {
-  return run_host(chub_update_f32, true, 4, L, n, ld, layout, v, flags, status);
+  return run_host(chub_update_f32, true, 4, L, ld, L, ld, n, layout, v, flags, status);
 }
 int chub_downdate_host_f64(void *L, int64_t n, int64_t ld, int layout, void *v, int flags, int32_t *status) {
-  return run_host(chub_downdate_f64, false, 8, L, n, ld, layout, v, flags, status);
+  return run_host(chub_downdate_f64, false, 8, L, ld, L, ld, n, layout, v, flags, status);
 }
 int chub_downdate_host_f32(void *L, int64_t n, int64_t ld, int layout, void *v, int flags, int32_t *status) {
-  return run_host(chub_downdate_f32, false, 4, L, n, ld, layout, v, flags, status);
+  return run_host(chub_downdate_f32, false, 4, L, ld, L, ld, n, layout, v, flags, status);
+}
+// copy mode (overwrite_L=False, _seeger.py:272-273): L_in is only read, the result goes to L_out
+int chub_update_host_copy_f64(const void *L_in, int64_t ld_in, void *L_out, int64_t ld_out, int64_t n, int layout,
+                              void *v, int flags, int32_t *status) {
+  return run_host(chub_update_f64, true, 8, L_in, ld_in, L_out, ld_out, n, layout, v, flags, status);
+}
+int chub_update_host_copy_f32(const void *L_in, int64_t ld_in, void *L_out, int64_t ld_out, int64_t n, int layout,
+                              void *v, int flags, int32_t *status) {
+  return run_host(chub_update_f32, true, 4, L_in, ld_in, L_out, ld_out, n, layout, v, flags, status);
+}
+int chub_downdate_host_copy_f64(const void *L_in, int64_t ld_in, void *L_out, int64_t ld_out, int64_t n, int layout,
+                                void *v, int flags, int32_t *status) {
+  return run_host(chub_downdate_f64, false, 8, L_in, ld_in, L_out, ld_out, n, layout, v, flags, status);
+}
+int chub_downdate_host_copy_f32(const void *L_in, int64_t ld_in, void *L_out, int64_t ld_out, int64_t n, int layout,
+                                void *v, int flags, int32_t *status) {
+  return run_host(chub_downdate_f32, false, 4, L_in, ld_in, L_out, ld_out, n, layout, v, flags, status);
 }
 
 int chub_host_release(void) {
   int dev = 0;
   HCK(cudaGetDevice(&dev));
-  std::lock_guard<std::mutex> lk(h_mu);
+  std::lock_guard<std::mutex> lk(h_mu[dev & 63]);
   HostCache &c = h_cache[dev & 63];
   if (c.L) cudaFree(c.L);
   if (c.v) cudaFree(c.v);

@@ -12,6 +12,7 @@
 // pipelined exchange is the next step.
 #pragma once
 
+#include "dataflow.cuh"
 #include "large.cuh"
 
 namespace chub {
@@ -603,6 +604,164 @@ __global__ void __launch_bounds__(NT) rcw_trail_kernel(T *A, int m_loc, int n, i
     for (int f = 0; f < F; ++f)
       if (f < Fe) wv.W[(int64_t)(U * F + f) * wv.n_pad + R] = w[f];
   }
+}
+
+// ---- bulk of the trail on the TMA ring (look-ahead split, rows_mode 2: the 256-row blocks >= J+2 of every task
+// of the step).  These tiles are all full and strictly below the diagonal, and they are where nearly all of a
+// step's bytes are.  Same machinery as rect_apply_rm_kernel (dataflow.cuh): persistent warps, a warp takes
+// 8 local rows of one task and walks the task's 256 columns in 32-column TMA boxes through a ring that keeps
+// running from one (task, row group) item to the next, the block column's (p, c, sigma) riding along as bulk
+// copies out of the task's payload; lane mapping and arithmetic of the persistent kernel's workers.  The
+// staged kernel above reached 3.5 TB/s with 30 % of its stalls on shared-memory scoreboards and read tiles
+// that straddle the diagonal whole; this one reads exactly what it writes.
+// Items are dealt round-robin over all warps of the grid: flat index = (groups of earlier tasks) + group.
+template <typename T>
+__global__ void __launch_bounds__(kRectWarps * 32, 1)
+rcw_bulk_tma_kernel(int m_loc, int n, int G, int rank, RcWave wv, int d, int Jlo, int ntasks, int max_tasks,
+                    const double *pay_all, T *V_out, int64_t ldv, RcwP2P pp, int32_t *status,
+                    const __grid_constant__ CUtensorMap tmapA) {
+  constexpr int HALVES = RmGeom<T>::HALVES, BOXC = RmGeom<T>::BOXC, CPT = RmGeom<T>::CPT;
+  constexpr int WTILE = RmGeom<T>::WTILE, STAGE = RectGeom<T>::STAGE;
+  extern __shared__ __align__(1024) unsigned char rb_smem[];
+  if (*status != 0) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(rb_smem) + warp * kRectStages;
+  unsigned char *mystage = rb_smem + 1024 + (size_t)warp * kRectStages * STAGE;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRectWarps * kRectStages; ++i) mbar_init(reinterpret_cast<unsigned long long *>(rb_smem) + i, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int g = lane >> 3, r8 = lane & 7;
+  const int hh = (g * 8 * (int)sizeof(T)) / 128;
+  const int cb = ((g * 8 * (int)sizeof(T)) % 128) / 16;
+  const unsigned my_off = hh * 1024 + r8 * 128;
+  const int TW = (int)gridDim.x * kRectWarps, gw = (int)blockIdx.x * kRectWarps + warp;
+  constexpr int nsteps = kBig / kPanel;  // 8 tiles per item
+  unsigned it = 0;
+  long long base_items = 0;
+  bool bail = false;
+  for (int t = 0; t < ntasks && !bail; ++t) {
+    const int J = Jlo + t, U = d - J;
+    // local rows of the owned 256-row blocks with global index >= J + 2
+    int qb = J + 2 - rank;
+    qb = qb > 0 ? (qb + G - 1) / G : 0;
+    const int l_begin = qb * kRcBlock;
+    const int groups = l_begin < m_loc ? (m_loc - l_begin + 7) / 8 : 0;
+    int first = (int)(((long long)gw - base_items) % TW);
+    if (first < 0) first += TW;
+    base_items += groups;
+    const int c_base = J * kBig;
+    const int ncol = min(kBig, n - c_base);
+    const int steps_t = (ncol + kPanel - 1) / kPanel;  // (a ragged last panel has no rows below it anyway)
+    if (groups == 0 && !(gw == 0)) continue;
+    const double *pay = pay_all + ((int64_t)(J % G) * max_tasks + t / G) * kRcwSlot;
+    bool have_pay = false;
+    auto need_payload = [&]() {  // p2p: the task's payload has arrived in my mailbox (flag of its owner)
+      if (have_pay) return;
+      if (pp.peer_mail) {
+        const int q = (int)((pp.epoch + d) & (kRcwSets - 1));
+        const long long *flags = reinterpret_cast<const long long *>(pp.mail + rcw_mail_flags(G, pp.max_tasks)) + q * G;
+        if (lane == 0) rcw_wait_flag(flags + J % G, pp.epoch + d + 1, status, pp.watchdog);
+        __syncwarp();
+        pay = pp.mail + rcw_mail_slot(q, J % G, t / G, G, pp.max_tasks);
+        fence_proxy_async_all();  // the acquire above -> the bulk copies below
+      }
+      have_pay = true;
+    };
+    // warp 0 of the grid hands the task's scratch vector (rotg's z_k) to the caller, as the staged kernel's
+    // unpacking CTA does in this mode
+    if (gw == 0 && V_out) {
+      need_payload();
+      if (*(volatile int32_t *)status != CHUB_STATUS_INTERNAL)
+        for (int k = lane; k < kBig; k += 32)
+          if (c_base + k < n) V_out[(int64_t)U * ldv + c_base + k] = (T)__ldcg(pay + 4 * kBig + k);
+    }
+    for (int grp = first; grp < groups; grp += TW) {
+      need_payload();
+      if (*(volatile int32_t *)status == CHUB_STATUS_INTERNAL) { bail = true; break; }  // a peer never delivered: touch nothing
+      const int l0 = l_begin + grp * 8;
+      const int l = l0 + r8;
+      const int64_t R = l < m_loc ? rc_global_row(l, G, rank) : (int64_t)n;
+      double w = R < n ? wv.W[(int64_t)U * wv.n_pad + R] : 0.0;
+
+      auto issue_load = [&](int s) {  // elected lane
+        if (s >= steps_t) return;
+        const unsigned st = (it + (unsigned)s) % kRectStages;
+        void *bar = &full[st];
+        unsigned char *stg = mystage + (size_t)st * STAGE;
+        const int c0 = c_base + s * kPanel;
+        mbar_arrive_expect_tx(bar, (unsigned)WTILE + 768u);
+        tma_load_2d(stg, &tmapA, c0, l0, bar);
+        if (HALVES == 2) tma_load_2d(stg + 1024, &tmapA, c0 + BOXC, l0, bar);
+        bulk_g2s(stg + WTILE, pay + s * kPanel, 256u, bar);
+        bulk_g2s(stg + WTILE + 256, pay + kBig + s * kPanel, 256u, bar);
+        bulk_g2s(stg + WTILE + 512, pay + 2 * kBig + s * kPanel, 256u, bar);
+      };
+
+      if (elect_one()) {
+        bulk_wait_read<0>();
+        for (int s = 0; s < kRectStages - 1; ++s) issue_load(s);
+      }
+      __syncwarp();
+      for (int s = 0; s < steps_t; ++s) {
+        const unsigned st = (it + (unsigned)s) % kRectStages;
+        const unsigned ph = ((it + (unsigned)s) / kRectStages) & 1u;
+        mbar_wait(&full[st], ph, status);
+        unsigned char *stg = mystage + (size_t)st * STAGE;
+        unsigned char *rowp = stg + my_off;
+        const double *cf = reinterpret_cast<const double *>(stg + WTILE) + g * 8;
+        int4 raw[CPT];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) raw[i] = *reinterpret_cast<const int4 *>(rowp + (((cb + i) ^ r8) << 4));
+        T *x = reinterpret_cast<T *>(raw);
+        double lo[8], pre[8];
+        double run = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const double2 a = *reinterpret_cast<const double2 *>(cf + j);
+          lo[j] = (double)x[j];
+          pre[j] = run;
+          run = fma(lo[j], a.x, run);
+          lo[j + 1] = (double)x[j + 1];
+          pre[j + 1] = run;
+          run = fma(lo[j + 1], a.y, run);
+        }
+        double incl = run;
+        double y = __shfl_up_sync(0xffffffffu, incl, 8);
+        if (g >= 1) incl += y;
+        y = __shfl_up_sync(0xffffffffu, incl, 16);
+        if (g >= 2) incl += y;
+        const double total = __shfl_sync(0xffffffffu, incl, 24 + r8);
+        const double wseg = w - (incl - run);
+        w -= total;
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const double2 c = *reinterpret_cast<const double2 *>(cf + kPanel + j);
+          const double2 sg = *reinterpret_cast<const double2 *>(cf + 2 * kPanel + j);
+          x[j] = (T)fma(c.x, lo[j], sg.x * (wseg - pre[j]));
+          x[j + 1] = (T)fma(c.y, lo[j + 1], sg.y * (wseg - pre[j + 1]));
+        }
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) *reinterpret_cast<int4 *>(rowp + (((cb + i) ^ r8) << 4)) = raw[i];
+        fence_proxy_async();
+        __syncwarp();
+        if (elect_one()) {
+          const int c0 = c_base + s * kPanel;
+          tma_store_2d(&tmapA, c0, l0, stg);
+          if (HALVES == 2) tma_store_2d(&tmapA, c0 + BOXC, l0, stg + 1024);
+          bulk_commit();
+          bulk_wait_read<1>();
+          issue_load(s + kRectStages - 1);
+        }
+        __syncwarp();
+      }
+      it += (unsigned)steps_t;
+      if (g == 0 && R < n) wv.W[(int64_t)U * wv.n_pad + R] = w;
+    }
+  }
+  if (elect_one()) bulk_wait_all<0>();
 }
 
 }  // namespace chub

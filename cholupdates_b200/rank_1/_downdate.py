@@ -39,7 +39,9 @@ def downdate(
         #  [0.40711529 2.8424243  0.        ]
         #  [0.13725652 0.20389013 3.6022848 ]]
     """
-    if method in ("seeger", "b200"):
+    if method == "cho_factor":
+        L_upd = _cho_factor_method(L, v, check_diag, **method_kwargs)
+    elif method in ("seeger", "b200"):
         L_upd = downdate_seeger(
             L,
             v,
@@ -54,7 +56,36 @@ def downdate(
     return L_upd
 
 
-downdate.available_methods = ["seeger", "b200"]
+def _cho_factor_method(L, v, check_diag, **method_kwargs):
+    """``method="cho_factor"`` (reference ``_downdate.py``: ``tril(L) tril(L)^T - v v^T`` re-factorised, strict
+    upper triangle of ``L`` restored): the O(N^3) cross-check, on the GPU (cuSOLVER through torch -- a
+    library call is what this convenience path is in the reference, too).  Ignores ``overwrite_*`` like
+    the reference.  NumPy in -> NumPy out, CUDA tensor in -> CUDA tensor out."""
+    import numpy as np
+    import torch
+
+    from .. import _lib
+    from ._arg_validation import _validate_update_args, is_torch_tensor
+
+    _validate_update_args(L, v, check_diag)
+    if method_kwargs:
+        raise TypeError(f"unexpected keyword arguments for method 'cho_factor': {sorted(method_kwargs)}")
+    _lib.require_device()
+    as_numpy = not is_torch_tensor(L)
+    Lt = torch.as_tensor(np.ascontiguousarray(L)).cuda() if as_numpy else L
+    vt = torch.as_tensor(np.ascontiguousarray(v)).cuda() if not is_torch_tensor(v) else v
+    Ltri = torch.tril(Lt)
+    A = Ltri @ Ltri.T - torch.outer(vt, vt)
+    Lc, info = torch.linalg.cholesky_ex(A)
+    if int(info.item()) != 0:
+        raise np.linalg.LinAlgError(f"{int(info.item())}-th leading minor of the array is not positive definite")
+    out = torch.tril(Lc) + torch.triu(Lt, 1)
+    if as_numpy:
+        return np.array(out.cpu().numpy(), order="F" if (L.flags.f_contiguous and not L.flags.c_contiguous) else "C")
+    return out
+
+
+downdate.available_methods = ["cho_factor", "seeger", "b200"]
 
 
 def downdate_in_place(L, v, check_diag: bool = True, method: str = "seeger", **method_kwargs):

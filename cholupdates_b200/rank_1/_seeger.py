@@ -59,13 +59,60 @@ def _layout_of(L) -> Optional[int]:
     return None
 
 
+def _layout_and_ld(L, strided: bool):
+    """(layout, leading dimension in elements), or None.  Dense C / F arrays always; with ``strided``
+    also row- or column-major VIEWS whose inner stride is 1 and whose leading dimension exceeds N (a
+    corner of a wider buffer): a superset of what the reference accepts (``_seeger.py:260-264``), which
+    the C ABI has taken from the start (``ld`` argument)."""
+    n = int(L.shape[0])
+    lay = _layout_of(L)
+    if lay is not None:
+        return lay, max(n, 1)
+    if not strided or n == 0:
+        return None
+    if is_torch_tensor(L):
+        s0, s1 = int(L.stride(0)), int(L.stride(1))
+    else:
+        if L.strides[0] % L.itemsize or L.strides[1] % L.itemsize:
+            return None
+        s0, s1 = L.strides[0] // L.itemsize, L.strides[1] // L.itemsize
+    if s1 == 1 and s0 >= n:
+        return _lib.ROW_MAJOR, s0
+    if s0 == 1 and s1 >= n:
+        return _lib.COL_MAJOR, s1
+    return None
+
+
+def _from_dlpack(x):
+    """Objects that are neither numpy arrays nor torch tensors but speak DLPack (CuPy arrays, JAX / numba
+    device arrays ...) are viewed as torch CUDA tensors without a copy."""
+    if isinstance(x, np.ndarray) or is_torch_tensor(x) or not hasattr(x, "__dlpack__"):
+        return x
+    import torch
+
+    return torch.from_dlpack(x)
+
+
+def _to_caller_type(result, like):
+    """A freshly allocated result goes back in the caller's array type when that type can import DLPack."""
+    if like is None or isinstance(like, np.ndarray) or is_torch_tensor(like):
+        return result
+    try:
+        import importlib
+
+        xp = importlib.import_module(type(like).__module__.partition(".")[0])
+        return xp.from_dlpack(result)
+    except Exception:  # noqa: BLE001
+        return result
+
+
 def _is_contiguous_vector(v) -> bool:
     if is_torch_tensor(v):
         return v.is_contiguous()
     return bool(v.flags.c_contiguous)
 
 
-def _checks_after_diag(L, v) -> Optional[Exception]:
+def _checks_after_diag(L, v, strided: bool = False) -> Optional[Exception]:
     """The reference's checks that come after the diagonal scan, first failure only
     (``_arg_validation.py:25-30`` then ``_seeger.py:243-269`` / ``:679-705``)."""
     if v.ndim != 1 or v.shape[0] != L.shape[0]:
@@ -88,7 +135,7 @@ def _checks_after_diag(L, v) -> Optional[Exception]:
         return TypeError(
             f"`L` and `v` don't have the same dtype ({_dtype_name(L)} != {_dtype_name(v)})."
         )
-    if _layout_of(L) is None:
+    if _layout_and_ld(L, strided) is None:
         return ValueError(
             "`L` is neither Fortran- nor C-contiguous, i.e. the memory layout of the "
             "matrix is neither column- nor row-major."
@@ -98,7 +145,7 @@ def _checks_after_diag(L, v) -> Optional[Exception]:
     return None
 
 
-def _validate(L, v, check_diag: bool) -> bool:
+def _validate(L, v, check_diag: bool, strided: bool = False) -> bool:
     """Run the reference's checks in the reference's order.  Returns True if the diagonal scan
     is left to the kernel (CUDA tensors with nothing else wrong)."""
     if is_torch_tensor(L) != is_torch_tensor(v):
@@ -111,7 +158,7 @@ def _validate(L, v, check_diag: bool) -> bool:
             )
         if L.ndim != 2 or L.shape[0] != L.shape[1]:
             _validate_update_args(L, v, check_diag=False)  # raises the reference's ValueError
-        later = _checks_after_diag(L, v)
+        later = _checks_after_diag(L, v, strided)
         if later is not None:
             if check_diag and _has_zero_on_diagonal(L):
                 raise np.linalg.LinAlgError(_ZERO_DIAG_MSG)
@@ -119,7 +166,7 @@ def _validate(L, v, check_diag: bool) -> bool:
         return bool(check_diag)
     # NumPy: literally the reference's sequence.
     _validate_update_args(L, v, check_diag)
-    later = _checks_after_diag(L, v)
+    later = _checks_after_diag(L, v, strided)
     if later is not None:
         raise later
     return False
@@ -149,12 +196,12 @@ def _raise_for_status(status: int, op: str) -> None:
     raise RuntimeError(f"cholupdates_b200: {op} kernel reported internal status {status}")
 
 
-def _run(op: str, L, v, diag_on_device: bool) -> None:
+def _run(op: str, L, v, diag_on_device: bool, strided: bool = False, L_out=None) -> None:
     """In-place kernel call: the replacement for ``_update_impl_default(L, v)``
     (``_seeger.py:279-294``) / ``_downdate_impl_default(L, v)`` (``:715-730``)."""
     lib = _lib.require_device()
     n = int(L.shape[0])
-    layout = _layout_of(L)
+    layout, ld = _layout_and_ld(L, strided)
     flags = _lib.FLAG_CHECK_DIAG if diag_on_device else 0
     if is_torch_tensor(L):
         import torch
@@ -166,7 +213,7 @@ def _run(op: str, L, v, diag_on_device: bool) -> None:
             ws = _torch_workspace(L.device, stream.cuda_stream, nbytes)
             status = torch.empty(1, dtype=torch.int32, device=L.device)
             rc = getattr(lib, f"chub_{op}_{suf}")(
-                L.data_ptr(), n, n, layout, v.data_ptr(), flags, ws.data_ptr(), ws.numel(),
+                L.data_ptr(), n, ld, layout, v.data_ptr(), flags, ws.data_ptr(), ws.numel(),
                 status.data_ptr(), stream.cuda_stream,
             )
             _lib.check(rc, f"chub_{op}_{suf}")
@@ -174,9 +221,15 @@ def _run(op: str, L, v, diag_on_device: bool) -> None:
     else:
         suf = "f64" if L.dtype == np.double else "f32"
         st = ctypes.c_int32(0)
-        rc = getattr(lib, f"chub_{op}_host_{suf}")(
-            L.ctypes.data, n, n, layout, v.ctypes.data, flags, ctypes.byref(st)
-        )
+        if L_out is None:
+            rc = getattr(lib, f"chub_{op}_host_{suf}")(
+                L.ctypes.data, n, ld, layout, v.ctypes.data, flags, ctypes.byref(st)
+            )
+        else:  # copy mode: read L, write L_out (dense, same order)
+            rc = getattr(lib, f"chub_{op}_host_copy_{suf}")(
+                L.ctypes.data, ld, L_out.ctypes.data, max(n, 1), n, layout, v.ctypes.data, flags,
+                ctypes.byref(st)
+            )
         _lib.check(rc, f"chub_{op}_host_{suf}")
         code = int(st.value)
     _raise_for_status(code, op)
@@ -194,17 +247,28 @@ def _copy_v(v):
     return v.clone() if is_torch_tensor(v) else v.copy()
 
 
-def _dispatch(op: str, L, v, check_diag, overwrite_L, overwrite_v, impl, available):
-    diag_on_device = _validate(L, v, check_diag)
+def _dispatch(op: str, L, v, check_diag, overwrite_L, overwrite_v, impl, available, strided=False):
+    L_given = L
+    L, v = _from_dlpack(L), _from_dlpack(v)  # CuPy & co: zero-copy views as torch CUDA tensors
+    diag_on_device = _validate(L, v, check_diag, strided)
 
-    # Copy on demand  (_seeger.py:272-276 / :708-712)
+    # Copy on demand  (_seeger.py:272-276 / :708-712).  NumPy factors are not copied on the host first: the
+    # host entry point reads L and delivers the result into a fresh array of the same memory order
+    # (chub_*_host_copy_*; only the strict upper triangle is copied host-side, overlapped with the transfers).
+    L_out = None
     if not overwrite_L:
-        L = _copy_L(L)
+        if isinstance(L, np.ndarray) and (impl is None or impl == "b200") and L.shape[0] > 0:
+            layout, _ = _layout_and_ld(L, strided)
+            L_out = np.empty(L.shape, dtype=L.dtype, order="F" if layout == _lib.COL_MAJOR else "C")
+        else:
+            L = _copy_L(L)
     if not overwrite_v:
         v = _copy_v(v)
 
     if impl is None or impl == "b200":
-        _run(op, L, v, diag_on_device)
+        _run(op, L, v, diag_on_device, strided, L_out)
+        if L_out is not None:
+            L = L_out
     elif impl in ("cython", "python"):
         raise NotImplementedError(
             f"The {impl.capitalize()} implementation is not available in cholupdates_b200 "
@@ -215,6 +279,8 @@ def _dispatch(op: str, L, v, check_diag, overwrite_L, overwrite_v, impl, availab
             f"Unknown implementation '{impl}'. Available implementations: "
             f"{', '.join(available)}"
         )
+    if L_given is not L and not isinstance(L_given, np.ndarray) and not is_torch_tensor(L_given):
+        return L_given if overwrite_L else _to_caller_type(L, L_given)  # DLPack callers get their own type back
     return L
 
 
@@ -226,6 +292,7 @@ def update_seeger(
     overwrite_L: bool = False,
     overwrite_v: bool = False,
     impl: Optional[str] = None,
+    strided: bool = False,
 ):
     r"""Rank-1 update :math:`L^+ (L^+)^T = L L^T + v v^T` in :math:`O(N^2)` by the algorithm of
     section 2 of [Seeger, 2008], on the B200.
@@ -239,12 +306,17 @@ def update_seeger(
     * returns the updated factor: ``L`` itself if ``overwrite_L`` else a copy that keeps
       ``L``'s memory order.
     * ``impl``: ``None`` or ``"b200"``.
+    * ``strided`` (new, default off so that the reference's ``ValueError`` for non-contiguous input is
+      kept): also accept a row- or column-major VIEW with unit inner stride and a leading dimension
+      larger than ``N`` (e.g. ``big[:N, :N]``); nothing outside the ``N x N`` lower triangle is touched.
+    * Besides ``numpy.ndarray`` and ``torch.Tensor``, any CUDA array that speaks DLPack (CuPy ...) is
+      accepted zero-copy; a non-overwriting call returns the result in the caller's array type.
 
     Raises ``ValueError`` / ``TypeError`` / ``numpy.linalg.LinAlgError`` /
     ``NotImplementedError`` exactly where the reference does (``_seeger.py:241-294``).
     """
     return _dispatch(
-        "update", L, v, check_diag, overwrite_L, overwrite_v, impl, _update_available_impls
+        "update", L, v, check_diag, overwrite_L, overwrite_v, impl, _update_available_impls, strided
     )
 
 
@@ -258,6 +330,7 @@ def downdate_seeger(
     overwrite_L: bool = False,
     overwrite_v: bool = False,
     impl: Optional[str] = None,
+    strided: bool = False,
 ):
     r"""Rank-1 downdate :math:`L^- (L^-)^T = L L^T - v v^T` in :math:`O(N^2)` by the algorithm of
     section 3 of [Seeger, 2008], on the B200.
@@ -268,7 +341,7 @@ def downdate_seeger(
     ``L`` has not been modified.
     """
     return _dispatch(
-        "downdate", L, v, check_diag, overwrite_L, overwrite_v, impl, _downdate_available_impls
+        "downdate", L, v, check_diag, overwrite_L, overwrite_v, impl, _downdate_available_impls, strided
     )
 
 

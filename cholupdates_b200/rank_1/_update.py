@@ -34,8 +34,8 @@ def update(
     method :
         ``"seeger"`` -- the algorithm of section 2 of [Seeger, 2008] (the reference's default);
         here it runs on the B200.  ``"b200"`` is the explicit name of the same GPU method.
-        The reference's ``"cho_factor"`` convenience method (an :math:`O(N^3)` re-factorisation,
-        ``_update.py:157-169``) is outside the hot path and not provided.
+        ``"cho_factor"`` -- the reference's :math:`O(N^3)` cross-check (``_update.py:157-169``):
+        ``tril(L) tril(L)^T + v v^T`` re-factorised, here on the GPU (cuSOLVER through torch).
     method_kwargs : forwarded to ``update_seeger`` (``impl=None | "b200"``).
 
     Examples
@@ -49,7 +49,9 @@ def update(
         #  [17.32064554 18.08577447  0.        ]
         #  [ 6.96966215  7.15374133  1.82969791]]
     """
-    if method in ("seeger", "b200"):
+    if method == "cho_factor":
+        L_upd = _cho_factor_method(L, v, check_diag, **method_kwargs)
+    elif method in ("seeger", "b200"):
         L_upd = update_seeger(
             L,
             v,
@@ -64,7 +66,36 @@ def update(
     return L_upd
 
 
-update.available_methods = ["seeger", "b200"]
+def _cho_factor_method(L, v, check_diag, **method_kwargs):
+    """``method="cho_factor"`` (reference ``_update.py``: ``tril(L) tril(L)^T + v v^T`` re-factorised, strict
+    upper triangle of ``L`` restored): the O(N^3) cross-check, on the GPU (cuSOLVER through torch -- a
+    library call is what this convenience path is in the reference, too).  Ignores ``overwrite_*`` like
+    the reference.  NumPy in -> NumPy out, CUDA tensor in -> CUDA tensor out."""
+    import numpy as np
+    import torch
+
+    from .. import _lib
+    from ._arg_validation import _validate_update_args, is_torch_tensor
+
+    _validate_update_args(L, v, check_diag)
+    if method_kwargs:
+        raise TypeError(f"unexpected keyword arguments for method 'cho_factor': {sorted(method_kwargs)}")
+    _lib.require_device()
+    as_numpy = not is_torch_tensor(L)
+    Lt = torch.as_tensor(np.ascontiguousarray(L)).cuda() if as_numpy else L
+    vt = torch.as_tensor(np.ascontiguousarray(v)).cuda() if not is_torch_tensor(v) else v
+    Ltri = torch.tril(Lt)
+    A = Ltri @ Ltri.T + torch.outer(vt, vt)
+    Lc, info = torch.linalg.cholesky_ex(A)
+    if int(info.item()) != 0:
+        raise np.linalg.LinAlgError(f"{int(info.item())}-th leading minor of the array is not positive definite")
+    out = torch.tril(Lc) + torch.triu(Lt, 1)
+    if as_numpy:
+        return np.array(out.cpu().numpy(), order="F" if (L.flags.f_contiguous and not L.flags.c_contiguous) else "C")
+    return out
+
+
+update.available_methods = ["cho_factor", "seeger", "b200"]
 
 
 def update_in_place(L, v, check_diag: bool = True, method: str = "seeger", **method_kwargs):

@@ -119,6 +119,19 @@ int chub_downdate_host_f64(void *L, int64_t n, int64_t ld, int layout, void *v, 
                            int32_t *status);
 int chub_downdate_host_f32(void *L, int64_t n, int64_t ld, int layout, void *v, int flags,
                            int32_t *status);
+/* Copy mode of the host entry points (reference: overwrite_L=False copies L first, _seeger.py:272-273 /
+ * :708-709): L_in is only read; the updated lower triangle goes to L_out (same layout, own leading
+ * dimension), and the strict upper triangle of L_in is copied to L_out on the host, overlapped with the
+ * transfers -- no host-side copy of the lower triangle, nothing above the diagonal crosses PCIe.
+ * L_out's contents are unspecified when *status != CHUB_STATUS_OK. */
+int chub_update_host_copy_f64(const void *L_in, int64_t ld_in, void *L_out, int64_t ld_out, int64_t n, int layout,
+                              void *v, int flags, int32_t *status);
+int chub_update_host_copy_f32(const void *L_in, int64_t ld_in, void *L_out, int64_t ld_out, int64_t n, int layout,
+                              void *v, int flags, int32_t *status);
+int chub_downdate_host_copy_f64(const void *L_in, int64_t ld_in, void *L_out, int64_t ld_out, int64_t n, int layout,
+                                void *v, int flags, int32_t *status);
+int chub_downdate_host_copy_f32(const void *L_in, int64_t ld_in, void *L_out, int64_t ld_out, int64_t n, int layout,
+                                void *v, int flags, int32_t *status);
 /* Release the staging buffers the host entry points cache on the current device. */
 int chub_host_release(void);
 

@@ -600,3 +600,111 @@ def test_resident_factor_successive_updates(order, n):
         fresh = fac.download()
     np.testing.assert_array_equal(fresh, np.array(np.tril(L), order=order))
     assert fresh.flags.f_contiguous == (order == "F") or n == 1
+
+
+# ------------------------------------------------------------------- strided views (ld > n) through the front-end
+@pytest.mark.parametrize("op", ["update", "downdate"])
+@pytest.mark.parametrize("order", ["C", "F"])
+@pytest.mark.parametrize("kind", ["numpy", "torch"])
+@pytest.mark.parametrize("n,ld", [(100, 128), (1000, 1024), (700, 702)])
+def test_strided_view_through_front_end(op, order, kind, n, ld):
+    """`strided=True`: an n x n factor living in the corner of a wider buffer (ld > n), both orders, NumPy
+    and CUDA tensors; everything outside the n x n lower triangle comes back bit-identical.  Without the
+    flag the reference's ValueError is kept (_seeger.py:260-264)."""
+    L = synth_factor(n, 71)
+    v = np.random.default_rng(72).standard_normal(n) if op == "update" else downdate_vector(L, 72)
+    # a wider buffer whose memory order is `order` and whose leading dimension is `ld`
+    shape = (n + 3, ld) if order == "C" else (ld, n + 3)
+    big = np.array(np.random.default_rng(73).standard_normal(shape), order=order)
+    big[:n, :n] = np.tril(L) + np.triu(big[:n, :n], 1)
+    fn = getattr(rank_1, op)
+    L_ref, _ = _oracle(op, L, v)
+    if kind == "numpy":
+        buf = big.copy(order="K")
+        view = buf[:n, :n]
+        mk_v = lambda: v.copy()  # noqa: E731
+    else:
+        store = torch.from_numpy(np.ascontiguousarray(big if order == "C" else big.T)).cuda()
+        buf = store if order == "C" else store.t()
+        view = buf[:n, :n]
+        mk_v = lambda: torch.from_numpy(v.copy()).cuda()  # noqa: E731
+    with pytest.raises(ValueError):
+        fn(view, mk_v(), overwrite_L=True)
+    out = fn(view, mk_v(), overwrite_L=True, overwrite_v=True, strided=True)
+    assert out is view
+    got = buf if kind == "numpy" else buf.cpu().numpy()
+    assert rel_fro(got[:n, :n], L_ref) <= tol_for(np.float64, n)
+    mask = np.ones(big.shape, dtype=bool)
+    mask[:n, :n] = np.triu(np.ones((n, n), dtype=bool), 1)
+    np.testing.assert_array_equal(got[mask], big[mask])
+    # copy mode keeps the input and returns a dense result
+    before = np.array(got, copy=True)
+    v2 = 0.3 * v  # (a second downdate with the full v could leave the positive-definite cone)
+    res = fn(view, v2.copy() if kind == "numpy" else torch.from_numpy(v2.copy()).cuda(), strided=True)
+    res = res if kind == "numpy" else res.cpu().numpy()
+    np.testing.assert_array_equal(buf if kind == "numpy" else buf.cpu().numpy(), before)
+    assert rel_fro(res, _oracle(op, np.tril(before[:n, :n]), v2)[0]) <= tol_for(np.float64, n) * 2
+
+
+def test_dlpack_input_is_viewed_zero_copy():
+    """An array type that is neither numpy nor torch but speaks DLPack (CuPy ...) is updated in place
+    through a zero-copy torch view; a stand-in class exercises the protocol without CuPy."""
+
+    class Foreign:
+        def __init__(self, t):
+            self.t = t
+            self.ndim, self.shape, self.dtype = t.ndim, tuple(t.shape), t.dtype
+
+        def __dlpack__(self, stream=None):
+            return self.t.__dlpack__()
+
+        def __dlpack_device__(self):
+            return self.t.__dlpack_device__()
+
+    n = 300
+    L = synth_factor(n, 81)
+    v = np.random.default_rng(82).standard_normal(n)
+    Lt, vt = torch.from_numpy(L.copy()).cuda(), torch.from_numpy(v.copy()).cuda()
+    fl, fv = Foreign(Lt), Foreign(vt)
+    out = rank_1.update(fl, fv, overwrite_L=True, overwrite_v=True)
+    assert out is fl
+    assert rel_fro(Lt.cpu().numpy(), _oracle("update", L, v)[0]) <= tol_for(np.float64, n)
+
+
+# ------------------------------------------------------------------- method="cho_factor" and the device generators
+@pytest.mark.parametrize("n", [5, 100, 600])
+@pytest.mark.parametrize("kind", ["numpy", "torch"])
+def test_cho_factor_method_cross_check(n, kind):
+    """The reference's own cross-check (update/conftest.py:27-41 enrols every method): the O(N^3)
+    re-factorisation and the Seeger path give the same factor; the strict upper triangle is restored."""
+    A, L = spd_factor(n, 91)
+    junk = np.triu(np.random.default_rng(92).standard_normal((n, n)), 1)
+    v = np.random.default_rng(93).normal(scale=10, size=n)
+    vd = downdate_vector(L, 94)
+    for op, vec in (("update", v), ("downdate", vd)):
+        a = _run(op, L + junk, vec, kind, method="cho_factor")
+        b = _run(op, L + junk, vec, kind, method="seeger")
+        assert rel_fro(a, b) <= 1e-10
+        np.testing.assert_array_equal(np.triu(a, 1), junk)
+    with pytest.raises(np.linalg.LinAlgError):
+        rank_1.downdate(L, downdate_vector(L, 95, norm_p=1.2), method="cho_factor")
+
+
+def test_device_generators():
+    from cholupdates_b200 import utils
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    for fast in (True, False):
+        M = utils.random_spd_matrix(200, fast=fast, generator=g)
+        assert torch.equal(M, M.T)
+        assert float(torch.linalg.eigvalsh(M).min()) > 0  # (tests/cholupdates/test_utils.py:24-33)
+    spec, Q = utils.random_spd_eigendecomposition(50, generator=g)
+    assert float(spec.min()) >= 1.0 and bool((spec[1:] >= spec[:-1]).all())
+    assert float((Q.T @ Q - torch.eye(50, dtype=Q.dtype, device=Q.device)).abs().max()) < 1e-12
+    L = torch.linalg.cholesky(utils.random_spd_matrix(300, generator=g))
+    v = utils.random_rank_1_downdate(L, generator=g)
+    p = torch.linalg.solve_triangular(L, v[:, None], upper=False)[:, 0]
+    assert 0.2 <= float(p @ p) <= 0.9
+    L_dd = rank_1.downdate(L, v)
+    assert bool((torch.diagonal(L_dd) > 0).all())

@@ -200,3 +200,20 @@ def test_wavefront_sizing_entry_points_need_no_gpu():
                 assert lib.chub_rcw_workspace_bytes(n, K, G) >= 8 * (K * n_pad + K * 8)
                 assert lib.chub_rcw_mailbox_bytes(n, K, G) >= 8 * 4 * G * got * pay
 
+
+
+def test_strided_views_layout_and_leading_dimension():
+    """`strided=True` (superset of the reference's contiguity check, _seeger.py:260-264): views with a unit
+    inner stride map onto the C ABI's (layout, ld); everything else keeps raising ValueError."""
+    from cholupdates_b200.rank_1 import _seeger
+
+    big = np.zeros((12, 16))
+    assert _seeger._layout_and_ld(big[:8, :8], False) is None
+    assert _seeger._layout_and_ld(big[:8, :8], True) == (0, 16)
+    assert _seeger._layout_and_ld(big.T[:8, :8], True) == (1, 16)
+    assert _seeger._layout_and_ld(big[:8:2, :4], True) == (0, 32)
+    assert _seeger._layout_and_ld(big[:8, :16:2], True) is None  # inner stride 2: not addressable
+    assert _seeger._layout_and_ld(np.zeros((5, 5), order="F"), False) == (1, 5)
+    err = _seeger._checks_after_diag(big[:8, :8], np.zeros(8), strided=False)
+    assert isinstance(err, ValueError) and "neither Fortran- nor C-contiguous" in str(err)
+    assert _seeger._checks_after_diag(big[:8, :8], np.zeros(8), strided=True) is None
