@@ -433,7 +433,9 @@ int rcw_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, in
   if (nt != 32 && nt != 64) nt = 128;
   if (rows_mode < 0 || rows_mode > 2) return (int)cudaErrorInvalidValue;
   // bulk of the look-ahead split on the TMA ring (rcw_bulk_tma_kernel) when the local rows are 16-byte aligned
-  if (rows_mode == 2 && !solve_ws && fuse == 1 && m_loc > 0 && !getenv("CHUB_RCW_BULK_STAGED") &&
+  // (opt-in, CHUB_RCW_BULK_TMA=1: measured slower than the staged kernel so far -- 0.63 vs 0.54 ms per update at
+  // n = 16384, K = 32 -- because an item is only 8 tiles long and the ring does not yet prefetch across items)
+  if (rows_mode == 2 && !solve_ws && fuse == 1 && m_loc > 0 && getenv("CHUB_RCW_BULK_TMA") &&
       (ld % (16 / sizeof(T))) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && get_encode_tiled()) {
     alignas(64) CUtensorMap tmapA;
     if (make_tmap<T>(&tmapA, (T *)A, n, ld, 8, m_loc)) {

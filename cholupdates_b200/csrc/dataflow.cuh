@@ -914,17 +914,16 @@ __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsign
       }
     } else if (warp == kDfD + 1) {
       if (elect_one()) issue_slot(j + kDfSlots - 1);
-      __syncwarp();
-      if (kDfPf > 0) {
-        // the ring's lead (kDfSlots-1 block columns) is shorter than the DRAM latency while every SM
-        // streams, so the band tiles of block column j + kDfSlots-1 + kDfPf go to L2 now
-        const int jp = j + kDfSlots - 1 + kDfPf;
-        const int np = min(kDfD, T_ - 1 - jp);
-        if (LAYOUT == CHUB_COL_MAJOR) {
-          if (lane < np) tma_prefetch_2d(tmap32, (jp + 1 + lane) * kPanel, jp * kPanel);
-        } else if (lane < np * HALVES) {
-          tma_prefetch_2d(tmap32, jp * kPanel + (lane % HALVES) * BOXC, (jp + 1 + lane / HALVES) * kPanel);
-        }
+    } else if (kDfPf > 0) {
+      // the spare warp: the ring's lead (kDfSlots-1 block columns) is shorter than the DRAM latency
+      // while every SM streams, so the band tiles of block column j + kDfSlots-1 + kDfPf go to L2 now
+      // (issued by the TMA-issuing warp itself it costs 12-50 us per update: measured twice)
+      const int jp = j + kDfSlots - 1 + kDfPf;
+      const int np = min(kDfD, T_ - 1 - jp);
+      if (LAYOUT == CHUB_COL_MAJOR) {
+        if (lane < np) tma_prefetch_2d(tmap32, (jp + 1 + lane) * kPanel, jp * kPanel);
+      } else if (lane < np * HALVES) {
+        tma_prefetch_2d(tmap32, jp * kPanel + (lane % HALVES) * BOXC, (jp + 1 + lane / HALVES) * kPanel);
       }
     }
     tp = DF_PROF_T();
@@ -980,8 +979,11 @@ __device__ __forceinline__ void df_coef_warp(T *v, const DfParams &P, double *co
   // flight while the coefficients of block column s are formed).  A ring slot is reused once
   // every row warp has finished the step that last read it (prog[]); finished warps have left.
   double t_run = P.ws.scal[0], S_run = P.ws.scal[1];  // (1, 1) unless a blocked driver carries them over
+#ifndef CHUB_DF_POLL2
+#define CHUB_DF_POLL2 0  // two polls in flight in the coefficient warp: measured 4 % SLOWER (147 SMs hammer one L2 line)
+#endif
   unsigned long long b0 = ld_relaxed_u64(P.ws.p + lane);
-  unsigned long long b1 = T_ > 1 ? ld_relaxed_u64(P.ws.p + kPanel + lane) : kSentinelBits;
+  unsigned long long b1 = (CHUB_DF_POLL2 && T_ > 1) ? ld_relaxed_u64(P.ws.p + kPanel + lane) : kSentinelBits;
   double ndg = P.ws.dg[lane];
   for (int pan = 0; pan < T_; ++pan) {
     const int slot = pan % kDfCoefRing;
@@ -989,9 +991,15 @@ __device__ __forceinline__ void df_coef_warp(T *v, const DfParams &P, double *co
     long long tq = DF_PROF_T();
     // two polls in flight (this block column and the next): the chain may run at two block columns per
     // round trip of a poll
-    const double pk = df_wait_value2(P.ws.p + k, pan + 1 < T_ ? P.ws.p + k + kPanel : nullptr, b0, b1, P.status);
-    b0 = b1;
-    b1 = pan + 2 < T_ ? ld_relaxed_u64(P.ws.p + k + 2 * kPanel) : kSentinelBits;
+    double pk;
+    if (CHUB_DF_POLL2) {
+      pk = df_wait_value2(P.ws.p + k, pan + 1 < T_ ? P.ws.p + k + kPanel : nullptr, b0, b1, P.status);
+      b0 = b1;
+      b1 = pan + 2 < T_ ? ld_relaxed_u64(P.ws.p + k + 2 * kPanel) : kSentinelBits;
+    } else {  // one poll in flight: the next block column's, issued while this one is turned into coefficients
+      pk = b0 != kSentinelBits ? __longlong_as_double((long long)b0) : df_wait_value(P.ws.p + k, P.status);
+      b0 = pan + 1 < T_ ? ld_relaxed_u64(P.ws.p + k + kPanel) : kSentinelBits;
+    }
     const double dg = ndg;
     if (pan + 1 < T_) ndg = P.ws.dg[k + kPanel];
     if (lane == 0) DF_PROF_ADD(6, tq);
@@ -2187,7 +2195,7 @@ constexpr int64_t kBlockedMax = 16384;
 inline LargeWs ws_offset(const LargeWs &ws, int64_t off) {  // the workspace as diagonal block [off, ..) sees it
   LargeWs w = ws;
   w.X += (off / kPanel) * kXBlock;
-  w.M1 += (off / kPanel) * kXBlock;
+  if (w.M1) w.M1 += (off / kPanel) * kXBlock;
   w.w += off; w.p += off; w.c += off; w.sg += off; w.dn += off; w.v0 += off; w.dg += off;
   return w;  // scal and flags are shared
 }

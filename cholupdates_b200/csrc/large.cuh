@@ -24,6 +24,8 @@
 // both layouts.  The persistent dataflow kernel (dataflow.cuh) reuses its pieces.
 #pragma once
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace chub {
@@ -46,10 +48,30 @@ struct LargeWs {
   int32_t *flags; // [..]     spare
 };
 
+constexpr int64_t kWsPadMax = 8192;  // doubles
+
+// Where the polled vectors sit relative to each other matters: the persistent kernel's chain CTA polls w
+// (handed over by the workers) while 147 coefficient warps poll p, and a layout that puts those lines on
+// the same L2 slice costs 3.5 % of the n = 16384 update (measured by accident: inserting a 4.4 MB array
+// before w took 0.466 -> 0.482 ms with a byte-identical kernel).  CHUB_WS_PAD_W / CHUB_WS_PAD_P (doubles,
+// multiples of 32) shift w and p for such experiments; the defaults are the measured best.
+inline int64_t ws_pad(const char *name, int64_t dflt) {
+  const char *e = getenv(name);
+  int64_t x = e ? atoll(e) : dflt;
+  if (x < 0) x = 0;
+  if (x > kWsPadMax) x = kWsPadMax;
+  return x & ~31LL;
+}
+
 inline size_t large_ws_doubles(int64_t n) {
   int64_t n_pad = (n + 31) & ~31LL;
   int64_t nb = n_pad / 32;
-  return (size_t)(2 * nb * kXBlock + 7 * n_pad + 8);
+  // (+ 2 * kWsPadMax: room for the two tuning pads of large_ws_carve)
+  return (size_t)(nb * kXBlock + 7 * n_pad + 8 + 2 * kWsPadMax
+#ifdef CHUB_CHAIN_V4
+                  + nb * kXBlock
+#endif
+  );
 }
 
 inline LargeWs large_ws_carve(void *base, int64_t n) {
@@ -57,9 +79,11 @@ inline LargeWs large_ws_carve(void *base, int64_t n) {
   int64_t nb = n_pad / 32;
   LargeWs ws;
   double *d = reinterpret_cast<double *>(base);
+  static const int64_t pad_w = ws_pad("CHUB_WS_PAD_W", 0), pad_p = ws_pad("CHUB_WS_PAD_P", 0);
   ws.X = d; d += nb * kXBlock;
-  ws.M1 = d; d += nb * kXBlock;
+  d += pad_w;
   ws.w = d; d += n_pad;
+  d += pad_p;
   ws.p = d; d += n_pad;
   ws.c = d; d += n_pad;
   ws.sg = d; d += n_pad;
@@ -67,6 +91,12 @@ inline LargeWs large_ws_carve(void *base, int64_t n) {
   ws.v0 = d; d += n_pad;
   ws.dg = d; d += n_pad;
   ws.scal = d; d += 8;
+  d += 2 * kWsPadMax - pad_w - pad_p;  // (the flags keep their place whatever the pads)
+#ifdef CHUB_CHAIN_V4
+  ws.M1 = d; d += nb * kXBlock;
+#else
+  ws.M1 = nullptr;
+#endif
   ws.flags = reinterpret_cast<int32_t *>(d);
   return ws;
 }
@@ -142,6 +172,8 @@ __device__ __forceinline__ void invdiag_block_smem(const T *L, int n, int64_t ld
   }
 #pragma unroll
   for (int i = 0; i < kPanel; ++i) X[i * kXStride + j] = x[i];
+#ifdef CHUB_CHAIN_V4  // (only the experimental chain of dataflow_chain_v4.cuh uses M1; compiled out of the library:
+                      //  the dead code alone made the pre-pass measurably slower)
   if (M1 == nullptr) return;
   // M1[i][c] = sum_{k <= i} X[i][k] Lt[k][c],  Lt = L[blk, blk-1];  lane = column c.  X goes through the
   // staging area (its L_D copy is no longer needed), Lt[.][c] sits in registers.
@@ -163,6 +195,9 @@ __device__ __forceinline__ void invdiag_block_smem(const T *L, int n, int64_t ld
     }
     M1[i * kXStride + lane] = a0 + a1;
   }
+#else
+  (void)M1;
+#endif
 }
 template <typename T, int LAYOUT>
 __device__ __forceinline__ void invdiag_block(const T *L, int n, int64_t ld, LargeWs ws, int blk, bool with_m1 = false) {
@@ -421,24 +456,44 @@ __global__ void __launch_bounds__(256) tri_transpose_kernel(T *dst, int64_t ldd,
 // ------------------------------------------------------- downdate coefficients
 // One CTA of 1024 threads: rho^2 = 1 - p.p (.pyx:253-259), suffix sums, (c_k, s_k), sign of the
 // input diagonal, v <- rotg's z_k (or v <- p when the result is not positive definite).
+// Thread t owns the contiguous chunk [b0, b1) of columns; the chunk sums are combined by a block-wide
+// suffix scan (warp shuffles + one shared-memory hop) instead of every thread summing all 1024 partials.
 template <typename T, int LAYOUT>
 __global__ void __launch_bounds__(1024) large_dd_coef_kernel(const T *L, int n, int64_t ld, T *v,
                                                              LargeWs ws, int32_t *status) {
   constexpr int NT = 1024;
-  __shared__ double red[NT];
+  __shared__ double wsum[NT / 32];   // per-warp totals
+  __shared__ double wabove[NT / 32]; // sum of the totals of the warps above
+  __shared__ double total_s;
   if (*status != 0) return;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ch = (n + NT - 1) / NT;
   const int b0 = min(n, tid * ch), b1 = min(n, b0 + ch);
   double acc = 0.0;
   for (int i = b0; i < b1; ++i) acc += ws.p[i] * ws.p[i];
-  red[tid] = acc;
-  __syncthreads();
-  double p_dot_p = 0.0, above = 0.0;
-  for (int t = 0; t < NT; ++t) {
-    p_dot_p += red[t];
-    if (t > tid) above += red[t];
+  // inclusive suffix sum over the lanes of a warp: suf = sum of acc over lanes >= lane
+  double suf = acc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double y = __shfl_down_sync(0xffffffffu, suf, o);
+    if (lane + o < 32) suf += y;
   }
+  if (lane == 0) wsum[warp] = suf;
+  __syncthreads();
+  if (warp == 0) {
+    double t = wsum[lane];  // NT / 32 == 32 warps
+    double s2 = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double y = __shfl_down_sync(0xffffffffu, s2, o);
+      if (lane + o < 32) s2 += y;
+    }
+    wabove[lane] = s2 - t;  // warps strictly above
+    if (lane == 0) total_s = s2;
+  }
+  __syncthreads();
+  const double p_dot_p = total_s;
+  const double above = wabove[warp] + (suf - acc);  // sum over all threads > tid
   const T rho_sq_t = T(1) - T(p_dot_p);
   if (tid == 0) { ws.scal[2] = p_dot_p; ws.scal[3] = (double)rho_sq_t; }
   if (rho_sq_t <= T(0)) {

@@ -560,11 +560,10 @@ class RowCyclicFactor:
         (one node, cudaIpc), else NCCL all-gather; False = NCCL; True = peer memory or raise.
         ``lookahead``: None = split every step's trail into head and bulk on two streams when there is
         no collective in the loop (peer-memory exchange or a single rank) and K > 1; False = one stream.
-        ``fuse``: 1 (default) = one update per task; 2 = consecutive updates (2u, 2u+1) share one pass
-        over every panel (half the HBM bytes per update; the owner runs the two diagonal-block chains
-        back to back on a scratch copy of its block).  Same results; measured slower for now (one GPU,
-        n = 16384, K = 32: 0.69 vs 0.54 ms per update) because the trail kernel is bound by its per-row
-        dependent FMA chain, not by HBM -- kept as the starting point for SURVEY 8(f)1."""
+        ``fuse``: 1 = one update per task; 2 = consecutive updates (2u, 2u+1) share one pass over every
+        panel (half the HBM bytes per update; the owner runs the two diagonal-block chains back to back
+        on a scratch copy of its block).  Same results.  None (default) = 2 when this rank holds at least
+        24576 rows (the trail then dominates the step and halving its bytes pays), else 1."""
         import numpy as np
         import torch
         import torch.distributed as dist
@@ -596,7 +595,12 @@ class RowCyclicFactor:
             lookahead = K > 1
         lookahead = bool(lookahead) and (use_p2p or not multi) and hasattr(be, "lookahead_streams")
         if fuse is None:
-            fuse = 1  # (fuse = 2 is parity-tested but not faster yet: the trail kernel is latency-bound)
+            # Two updates per pass halve the bytes the trail moves but double the owner kernel's serial
+            # work per step.  Measured (B200): with >= 32768 local rows the trail dominates and fuse = 2 wins
+            # (n = 32768 on one GPU: 1.19 vs 1.75 ms per update; n = 65536 on two: 2.27 vs 3.53); with
+            # 16384 local rows the owner's latency dominates and it loses (0.69 vs 0.54).
+            fuse = 2 if (K >= 2 and int(self.A.shape[0]) >= 24576 and hasattr(be, "lookahead_streams")) else 1
+        self.last_fuse = fuse
         if fuse not in (1, 2):
             raise ValueError("`fuse` must be 1 or 2.")
         if fuse == 2 and not hasattr(be, "lookahead_streams"):
