@@ -40,22 +40,38 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the library if it is missing or older than its sources.  Returns its path."""
+    """Compile the library if it is missing or older than its sources.  Returns its path.
+
+    Safe under ``torchrun``: the ranks of a job serialise on a lock file, the first one builds (into a
+    file of its own, renamed into place), the others find the library fresh when they get the lock."""
     if not force and not _stale():
         return LIB
-    nvcc = _nvcc()
-    if nvcc is None:
-        if os.path.exists(LIB):
-            return LIB  # cannot rebuild here; use what travelled with the snapshot
-        raise RuntimeError("nvcc not found and libcholupdates_b200.so is not built")
     os.makedirs(LIB_DIR, exist_ok=True)
-    tmp = LIB + ".tmp"
-    cmd = [nvcc, *NVCC_FLAGS, "-o", tmp, *[os.path.join(CSRC, s) for s in SOURCES]]
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
-    os.replace(tmp, LIB)
-    return LIB
+    import fcntl
+
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB  # another process built it while this one waited
+            nvcc = _nvcc()
+            if nvcc is None:
+                if os.path.exists(LIB):
+                    return LIB  # cannot rebuild here; use what travelled with the snapshot
+                raise RuntimeError("nvcc not found and libcholupdates_b200.so is not built")
+            tmp = f"{LIB}.tmp{os.getpid()}"
+            cmd = [nvcc, *NVCC_FLAGS, "-o", tmp, *[os.path.join(CSRC, s) for s in SOURCES]]
+            if verbose:
+                print(" ".join(cmd))
+            try:
+                subprocess.check_call(cmd)
+                os.replace(tmp, LIB)
+            finally:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+            return LIB
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 if __name__ == "__main__":

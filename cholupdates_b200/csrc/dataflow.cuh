@@ -1499,8 +1499,11 @@ __global__ void blocked_init_kernel(const T *L, int n, int64_t ld, const T *v, L
 // chain CTA (band tiles read through a column-major box), same coefficient warp, same delay of d steps
 // inside the band, ragged diagonal tile written with predicated global stores (coalesced: for a fixed
 // column the 32 lanes are 32 consecutive rows).
-constexpr int kCmStages = 4;
-constexpr int kCmMaxQ = 6;  // row warps (block rows) per worker: n <= 147 * 6 * 32 = 28224
+#ifndef CHUB_CM_STAGES
+#define CHUB_CM_STAGES 4
+#endif
+constexpr int kCmStages = CHUB_CM_STAGES;  // tile ring per row warp; loads run kCmStages - 2 steps ahead
+constexpr int kCmMaxQ = 6;  // row warps (block rows) per worker: n <= 147 * 6 * 32 = 28224 (shared memory permitting)
 
 template <typename T>
 struct CmGeom {
@@ -1571,16 +1574,15 @@ __device__ void df_worker_cm(T *L, T *v, const DfParams &P, const CUtensorMap *t
   };
 
   if (elect_one()) {
-    issue_load(0);
-    issue_load(1);
+    for (int s = 0; s < kCmStages - 2; ++s) issue_load(s);
   }
   __syncwarp();
   const long long t_wk0 = DF_PROF_T();
   for (int s = 0; s <= last_step; ++s) {
     long long tp = DF_PROF_T();
     if (elect_one()) {
-      bulk_wait_read<1>();  // the store of step s-2 has left its stage
-      issue_load(s + 2);
+      bulk_wait_read<1>();  // the store of step s-2 has left its stage (= the stage of step s + kCmStages - 2)
+      issue_load(s + kCmStages - 2);
     }
     __syncwarp();
     if (prof_me) DF_PROF_ADD(2, tp);

@@ -638,7 +638,6 @@ rcw_bulk_tma_kernel(int m_loc, int n, int G, int rank, RcWave wv, int d, int Jlo
   const int cb = ((g * 8 * (int)sizeof(T)) % 128) / 16;
   const unsigned my_off = hh * 1024 + r8 * 128;
   const int TW = (int)gridDim.x * kRectWarps, gw = (int)blockIdx.x * kRectWarps + warp;
-  constexpr int nsteps = kBig / kPanel;  // 8 tiles per item
   unsigned it = 0;
   long long base_items = 0;
   bool bail = false;
