@@ -30,13 +30,30 @@ def _nvcc() -> str | None:
     return None
 
 
+def _source_hash() -> str:
+    """Content hash of everything the library is compiled from (file times do not survive the snapshot
+    that carries the repository to the GPU box, contents do)."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC))
+    deps.append(os.path.join(os.path.dirname(PKG), "include", "cholupdates_b200.h"))
+    for d in deps:
+        if os.path.isfile(d):
+            h.update(os.path.basename(d).encode())
+            with open(d, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    deps.append(os.path.join(os.path.dirname(PKG), "include", "cholupdates_b200.h"))
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    try:
+        with open(LIB + ".hash") as f:
+            return f.read().strip() != _source_hash()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -66,6 +83,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             try:
                 subprocess.check_call(cmd)
                 os.replace(tmp, LIB)
+                with open(LIB + ".hash", "w") as f:
+                    f.write(_source_hash())
             finally:
                 if os.path.exists(tmp):
                     os.remove(tmp)

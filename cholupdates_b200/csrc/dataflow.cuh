@@ -904,9 +904,13 @@ __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsign
     } else if (warp == kDfD) {
       if (j + 1 < T_) {
         long long tq = DF_PROF_T();
+#ifdef CHUB_EXP_CHAIN_FREE  // timing experiment (results are garbage): the chain never waits for the workers
+        const double wt = wt_bits != kSentinelBits ? __longlong_as_double((long long)wt_bits) : 0.0;
+#else
         const double wt = wt_bits != kSentinelBits
                               ? __longlong_as_double((long long)wt_bits)
                               : df_wait_value(P.ws.w + (int64_t)(j + 1) * kPanel + lane, P.status);
+#endif
         wtb[((j + 1) & 1) * kPanel + lane] = wt;
         if (j + 2 < T_) wt_bits = ld_relaxed_u64(P.ws.w + (int64_t)(j + 2) * kPanel + lane);
         __syncwarp();
@@ -997,7 +1001,11 @@ __device__ __forceinline__ void df_coef_warp(T *v, const DfParams &P, double *co
       b0 = b1;
       b1 = pan + 2 < T_ ? ld_relaxed_u64(P.ws.p + k + 2 * kPanel) : kSentinelBits;
     } else {  // one poll in flight: the next block column's, issued while this one is turned into coefficients
+#ifdef CHUB_EXP_WORKER_FREE  // timing experiment (results are garbage): the workers never wait for the chain
+      pk = b0 != kSentinelBits ? __longlong_as_double((long long)b0) : 0.0;
+#else
       pk = b0 != kSentinelBits ? __longlong_as_double((long long)b0) : df_wait_value(P.ws.p + k, P.status);
+#endif
       b0 = pan + 1 < T_ ? ld_relaxed_u64(P.ws.p + k + kPanel) : kSentinelBits;
     }
     const double dg = ndg;

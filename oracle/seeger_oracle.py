@@ -25,19 +25,49 @@ _LIB = os.path.join(HERE, "libseeger_oracle.so")
 _lib = None
 
 
+def _src_hash() -> str:
+    import hashlib
+
+    with open(_SRC, "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()
+
+
+def _stale() -> bool:
+    # contents, not file times: times do not survive the snapshot that carries the repo to the GPU box
+    try:
+        with open(_LIB + ".hash") as f:
+            return not os.path.exists(_LIB) or f.read().strip() != _src_hash()
+    except OSError:
+        return True
+
+
 def build(force: bool = False) -> str:
-    """Compile the C restatement with gcc (seconds).  Returns the library path."""
-    if (
-        force
-        or not os.path.exists(_LIB)
-        or os.path.getmtime(_LIB) < os.path.getmtime(_SRC)
-    ):
-        cc = os.environ.get("CC", "gcc")
-        # -ffp-contract=off: keep the restated BLAS loops un-fused, like the
-        # reference-BLAS definitions they follow.
-        subprocess.check_call(
-            [cc, "-O2", "-fPIC", "-shared", "-ffp-contract=off", _SRC, "-o", _LIB, "-lm"]
-        )
+    """Compile the C restatement with gcc (seconds).  Returns the library path.  Safe when several
+    processes (torchrun ranks) call it at once: lock file, build into a private file, rename."""
+    if not force and not _stale():
+        return _LIB
+    import fcntl
+
+    with open(os.path.join(HERE, ".oracle_build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or _stale():
+                cc = os.environ.get("CC", "gcc")
+                tmp = f"{_LIB}.tmp{os.getpid()}"
+                # -ffp-contract=off: keep the restated BLAS loops un-fused, like the
+                # reference-BLAS definitions they follow.
+                try:
+                    subprocess.check_call(
+                        [cc, "-O2", "-fPIC", "-shared", "-ffp-contract=off", _SRC, "-o", tmp, "-lm"]
+                    )
+                    os.replace(tmp, _LIB)
+                    with open(_LIB + ".hash", "w") as f:
+                        f.write(_src_hash())
+                finally:
+                    if os.path.exists(tmp):
+                        os.remove(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return _LIB
 
 
