@@ -70,10 +70,12 @@ constexpr long long kWatchdogCycles = 4000000000LL;  // ~2 s
 
 struct DfParams {
   int n, T, R, r_shift, Wk, rows_max, nw;  // nw = row warps in use
+  int use3d = 0;                           // rm5 workers: the 3-D tensor map (64-column tiles in one TMA op) is valid
   int64_t ld;
   LargeWs ws;
   int32_t *status;
   long long *prof;  // optional [gridDim.x][16] cycle counters (nullptr = off)
+  int prof_late = 0;  // CHUB_PROFILE=2: the chain's counters cover the last 3/8 of the block rows only
 };
 
 // ------------------------------------------------------------------ primitives
@@ -143,6 +145,17 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int
 // tensor-map TMA prefetch of a box into L2 (no shared-memory destination, nothing to wait for)
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, void *bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+               ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, int c0, int c1, int c2, const void *smem_src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n"
+               ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];\n" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 // exactly one lane of a converged warp (the compiler then keeps TMA operands on the uniform path)
 __device__ __forceinline__ bool elect_one() {
@@ -807,27 +820,23 @@ __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsign
   for (int e = tid; e < (kDfD + 1) * kPanel; e += 256) acc[e] = 0.0;
   named_sync(1, 256);
 
-  // one thread issues everything block column j needs: tiles (j+1..j+d, j) and X_{j+1}
+  // one thread issues everything block column j needs: the band tiles (j+1..j+d, j) as ONE box of 32 d rows
+  // (ten 2-D boxes issued one after the other by one lane cost ~1000 cycles per block row: the barrier of
+  // every block row waited for them) and X_{j+1}.  Rows past the end of the matrix are zero-filled.
+  // Shared-memory layout of a slot: row-major [half h][tile q][32 rows][128 B swizzled];
+  // column-major [32 columns][32 d rows].
   auto issue_slot = [&](int j) {
     if (j < 0 || j >= T_) return;
     const int slot = j % kDfSlots;
     void *bar = &full[slot];
-    int ntiles = min(kDfD, T_ - 1 - j);
-    if (ntiles < 0) ntiles = 0;
-    const bool do_x = j + 1 < T_;
-    const unsigned bytes = (unsigned)ntiles * CTILE + (do_x ? kXBlock * 8u : 0u);
-    if (bytes == 0) { mbar_arrive(bar); return; }
-    mbar_arrive_expect_tx(bar, bytes);
-    for (int q = 0; q < ntiles; ++q) {
-      if (LAYOUT == CHUB_COL_MAJOR) {  // (coordinates: row first -- rows are the contiguous dimension)
-        tma_load_2d(tiles + ((size_t)slot * kDfD + q) * CTILE, tmap32, (j + 1 + q) * kPanel, j * kPanel, bar);
-      } else {
-        for (int h = 0; h < HALVES; ++h)
-          tma_load_2d(tiles + ((size_t)slot * kDfD + q) * CTILE + h * 4096, tmap32,
-                      j * kPanel + h * BOXC, (j + 1 + q) * kPanel, bar);
-      }
-    }
-    if (do_x) bulk_g2s(Xs + slot * kXBlock, P.ws.X + (int64_t)(j + 1) * kXBlock, kXBlock * 8u, bar);
+    const bool do_t = j + 1 < T_;
+    if (!do_t) { mbar_arrive(bar); return; }
+    mbar_arrive_expect_tx(bar, (unsigned)kDfD * CTILE + kXBlock * 8u);
+    if (LAYOUT == CHUB_COL_MAJOR)  // (coordinates: row first -- rows are the contiguous dimension)
+      tma_load_2d(tiles + (size_t)slot * kDfD * CTILE, tmap32, (j + 1) * kPanel, j * kPanel, bar);
+    else
+      tma_load_3d(tiles + (size_t)slot * kDfD * CTILE, tmap32, 0, (j + 1) * kPanel, j * HALVES, bar);
+    bulk_g2s(Xs + slot * kXBlock, P.ws.X + (int64_t)(j + 1) * kXBlock, kXBlock * 8u, bar);
   };
 
   if (warp == kDfD + 1 && elect_one())
@@ -852,8 +861,12 @@ __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsign
   if (warp == kDfD && T_ > 1) wt_bits = ld_relaxed_u64(P.ws.w + kPanel + lane);
   named_sync(1, 256);
 
-  const long long t_chain0 = DF_PROF_T();
+  long long t_chain0 = DF_PROF_T();
   for (int j = 0; j < T_; ++j) {
+    if (PROF && P.prof && P.prof_late && j == T_ * 5 / 8) {
+      for (int i = 0; i < 8; ++i) pacc[i] = 0;
+      t_chain0 = clock64();
+    }
     long long tp = DF_PROF_T();
     const double *pj = pbuf + (j & 1) * kPanel;
     if (warp < kDfD) {
@@ -861,23 +874,25 @@ __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsign
       if (br < T_) {
         mbar_wait(&full[j % kDfSlots], (unsigned)((j / kDfSlots) & 1), P.status);
         if (tid == 0) DF_PROF_ADD(1, tp);
-        const unsigned char *tb = tiles + ((size_t)(j % kDfSlots) * kDfD + warp) * CTILE;
+        const unsigned char *sb = tiles + (size_t)(j % kDfSlots) * kDfD * CTILE;  // this block column's slot
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         if (LAYOUT == CHUB_COL_MAJOR) {
-          const T *tc = reinterpret_cast<const T *>(tb) + lane;  // element (row = lane, column k) at [k][lane]
+          // element (tile q = warp, row = lane, column k) at [k][32 q + lane]
+          const T *tc = reinterpret_cast<const T *>(sb) + warp * kPanel + lane;
+          constexpr int CS = kDfD * kPanel;  // column stride (elements)
 #pragma unroll
           for (int k = 0; k < kPanel; k += 4) {
             const double2 pp = *reinterpret_cast<const double2 *>(pj + k);
             const double2 pq = *reinterpret_cast<const double2 *>(pj + k + 2);
-            a0 += (double)tc[k * kPanel] * pp.x;
-            a1 += (double)tc[(k + 1) * kPanel] * pp.y;
-            a2 += (double)tc[(k + 2) * kPanel] * pq.x;
-            a3 += (double)tc[(k + 3) * kPanel] * pq.y;
+            a0 += (double)tc[k * CS] * pp.x;
+            a1 += (double)tc[(k + 1) * CS] * pp.y;
+            a2 += (double)tc[(k + 2) * CS] * pq.x;
+            a3 += (double)tc[(k + 3) * CS] * pq.y;
           }
         } else {
 #pragma unroll
         for (int h = 0; h < HALVES; ++h) {
-          const unsigned char *rowp = tb + h * 4096 + lane * 128;
+          const unsigned char *rowp = sb + h * (kDfD * 4096) + warp * 4096 + lane * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const int4 raw = *reinterpret_cast<const int4 *>(rowp + ((c ^ (lane & 7)) << 4));
@@ -923,11 +938,9 @@ __device__ void df_chain_rm(const DfParams &P, const CUtensorMap *tmap32, unsign
       // while every SM streams, so the band tiles of block column j + kDfSlots-1 + kDfPf go to L2 now
       // (issued by the TMA-issuing warp itself it costs 12-50 us per update: measured twice)
       const int jp = j + kDfSlots - 1 + kDfPf;
-      const int np = min(kDfD, T_ - 1 - jp);
-      if (LAYOUT == CHUB_COL_MAJOR) {
-        if (lane < np) tma_prefetch_2d(tmap32, (jp + 1 + lane) * kPanel, jp * kPanel);
-      } else if (lane < np * HALVES) {
-        tma_prefetch_2d(tmap32, jp * kPanel + (lane % HALVES) * BOXC, (jp + 1 + lane / HALVES) * kPanel);
+      if (jp + 1 < T_ && elect_one()) {
+        if (LAYOUT == CHUB_COL_MAJOR) tma_prefetch_2d(tmap32, (jp + 1) * kPanel, jp * kPanel);
+        else tma_prefetch_3d(tmap32, 0, (jp + 1) * kPanel, jp * HALVES);
       }
     }
     tp = DF_PROF_T();
@@ -976,7 +989,8 @@ inline size_t df_chain_rm_smem() {
 // ---- coefficient warp of a worker CTA (shared by the row-major and the column-major workers)
 template <typename T, bool UPDATE, bool PROF>
 __device__ __forceinline__ void df_coef_warp(T *v, const DfParams &P, double *coef, volatile int *prog,
-                                             volatile int *cprog, volatile int *pprog, int wkr, int lane) {
+                                             volatile int *cprog, volatile int *pprog, int wkr, int lane,
+                                             int reuse_lag = kDfD + 1) {
   const int n = P.n, T_ = P.T, Wk = P.Wk;
   long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // ---------------- coefficient warp (software-pipelined: the poll of block column s+1 is in
@@ -1013,8 +1027,10 @@ __device__ __forceinline__ void df_coef_warp(T *v, const DfParams &P, double *co
     if (lane == 0) DF_PROF_ADD(6, tq);
     if (lane == 0 && wkr == 0) DF_TRACE(3, pan);
     if (pan >= kDfCoefRing) {
-      // slot last used by block column pan-8, read for the last time at step pan-8+d
-      const int need = pan - kDfCoefRing + kDfD + 1;
+      // slot last used by block column pan-ring.  prog[] counts finished steps (first-generation workers:
+      // that block column is read for the last time at step pan-ring+d, reuse_lag = d+1) or the next block
+      // column a warp still needs (rm5 workers, reuse_lag = 1)
+      const int need = pan - kDfCoefRing + reuse_lag;
       const long long t0 = clock64();
       while (__reduce_min_sync(0xffffffffu, ld_acquire_cta_smem(prog + lane)) < need) {
         if (clock64() - t0 > kWatchdogCycles) { atomicMax(P.status, CHUB_STATUS_INTERNAL); break; }
@@ -1335,16 +1351,39 @@ inline size_t df_worker_rm_smem(int nrw) {
   return 2048 + (size_t)kDfCoefRing * 4 * kPanel * 8 + (size_t)kDfStages * nrw * RmGeom<T>::WTILE;
 }
 
-template <typename T, bool UPDATE, bool PROF>
+} // namespace chub
+#include "dataflow_rm5.cuh"
+#ifdef CHUB_CHAIN_V4
+#include "dataflow_chain_v4.cuh"
+#endif
+#ifndef CHUB_CHAIN_V6
+#define CHUB_CHAIN_V6 1  // 1: barrier-free chain CTA (dataflow_chain_v6.cuh); 0: the barrier chain df_chain_rm (A/B)
+#endif
+#include "dataflow_chain_v6.cuh"
+namespace chub {
+
+// V5: second-generation row warps (dataflow_rm5.cuh); false = the first generation above (CHUB_RM5=0, A/B only)
+template <typename T, bool UPDATE, bool PROF, bool V5>
 __global__ void __launch_bounds__(kRmMaxThreads, 1)
 df_kernel_rm(T *L, T *v, DfParams P, const __grid_constant__ CUtensorMap tmap8,
-             const __grid_constant__ CUtensorMap tmap32) {
+             const __grid_constant__ CUtensorMap tmap32, const __grid_constant__ CUtensorMap tmap3) {
   extern __shared__ __align__(1024) unsigned char df_smem[];
   if (*P.status != 0) return;  // check_diag failed: L and v stay untouched
   if (blockIdx.x == 0) {
+#ifndef CHUB_EXP_NO_CHAIN
+#ifdef CHUB_CHAIN_V4
+    if (threadIdx.x < 256) df_chain_v4<T, CHUB_ROW_MAJOR, PROF>(P, &tmap32, df_smem);
+#elif CHUB_CHAIN_V6
+    if (threadIdx.x < kC6Threads) df_chain_v6<T, CHUB_ROW_MAJOR, PROF>(P, &tmap32, df_smem);
+#else
     if (threadIdx.x < 256) df_chain_rm<T, CHUB_ROW_MAJOR, PROF>(P, &tmap32, df_smem);
+#endif
+#endif
   } else {
-    df_worker_rm<T, UPDATE, PROF>(L, v, P, &tmap8, df_smem);
+#ifndef CHUB_EXP_NO_WORKERS
+    if (V5) df_worker_rm5<T, UPDATE, PROF>(L, v, P, &tmap8, &tmap3, df_smem);
+    else df_worker_rm<T, UPDATE, PROF>(L, v, P, &tmap8, df_smem);
+#endif
   }
 }
 
@@ -1685,10 +1724,11 @@ constexpr int kCmMaxThreads = 256;  // chain: 8 warps; workers: kCmMaxQ row warp
 
 template <typename T, bool UPDATE, bool PROF>
 __global__ void __launch_bounds__(kCmMaxThreads, 1)
-df_kernel_cm(T *L, T *v, DfParams P, const __grid_constant__ CUtensorMap tmapc) {
+df_kernel_cm(T *L, T *v, DfParams P, const __grid_constant__ CUtensorMap tmapc,
+             const __grid_constant__ CUtensorMap tmapcb) {
   extern __shared__ __align__(1024) unsigned char df_smem[];
   if (*P.status != 0) return;  // check_diag failed: L and v stay untouched
-  if (blockIdx.x == 0) df_chain_rm<T, CHUB_COL_MAJOR, PROF>(P, &tmapc, df_smem);
+  if (blockIdx.x == 0) df_chain_rm<T, CHUB_COL_MAJOR, PROF>(P, &tmapcb, df_smem);
   else df_worker_cm<T, UPDATE, PROF>(L, v, P, &tmapc, df_smem);
 }
 
@@ -2005,10 +2045,14 @@ inline RmPlan rm_plan(int64_t n, int64_t ld, const void *L) {
   const int Q = (int)((nRB + Wk - 1) / Wk);
   if (Q > kRmMaxQ) return pl;
   const int nrw = 2 * Q;
-  const size_t smem = std::max(df_chain_rm_smem<T>(), df_worker_rm_smem<T>(nrw));
+  size_t smem = std::max(df_chain_rm_smem<T>(), df_worker_rm_smem<T>(nrw));
+#ifdef CHUB_CHAIN_V4
+  smem = std::max(smem, df_chain_v4_smem<T>());
+#endif
+  smem = std::max(smem, df_chain_v6_smem<T>());
   if (smem > (size_t)smem_optin) return pl;
   pl.ok = true; pl.sms = sms; pl.Wk = Wk; pl.Q = Q; pl.nrw = nrw;
-  pl.threads = std::max(256, 32 * (nrw + 1));
+  pl.threads = std::max(std::max(256, kC6Threads), 32 * (nrw + 2));  // row warps + coefficient warp + relay warp
   pl.smem = smem;
   return pl;
 }
@@ -2048,6 +2092,24 @@ inline bool make_tmap(CUtensorMap *map, T *L, int64_t n, int64_t ld, int box_row
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// The same matrix as [column block of BOXC][row][BOXC columns]: a box of 2*HALVES column blocks x 8 rows is a
+// [8 rows][64 columns] tile in ONE TMA operation, landing as the 128-byte-swizzled 1 KB boxes make_tmap gives.
+// (Only whole column blocks are visible: the ragged right edge of an n that is no multiple of BOXC goes
+// through the 2-D map.)
+template <typename T>
+inline bool make_tmap3(CUtensorMap *map, T *L, int64_t n, int64_t ld, int box_rows, int box_cblocks) {
+  EncodeTiledFn enc = get_encode_tiled();
+  constexpr int BOXC = RmGeom<T>::BOXC;
+  if (!enc || n / BOXC < box_cblocks) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)BOXC, (cuuint64_t)n, (cuuint64_t)(n / BOXC)};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(T), (cuuint64_t)BOXC * sizeof(T)};
+  const cuuint32_t box[3] = {(cuuint32_t)BOXC, (cuuint32_t)box_rows, (cuuint32_t)box_cblocks};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  return enc(map, dt, 3, L, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // ---- column-major plan: block rows of 32 dealt cyclically, one warp per block row
 struct CmPlan {
   bool ok = false;
@@ -2079,12 +2141,12 @@ inline CmPlan cm_plan(int64_t n, int64_t ld, const void *L) {
 
 // Column-major n x n matrix with leading dimension ld: plain boxes of [32 columns][32 rows] (rows contiguous).
 template <typename T>
-inline bool make_tmap_cm(CUtensorMap *map, T *L, int64_t n, int64_t ld) {
+inline bool make_tmap_cm(CUtensorMap *map, T *L, int64_t n, int64_t ld, int box_rows = kPanel) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)n};  // (rows, columns): rows are the inner dimension
   const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(T)};
-  const cuuint32_t box[2] = {(cuuint32_t)kPanel, (cuuint32_t)kPanel};
+  const cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)kPanel};
   const cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   return enc(map, dt, 2, L, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -2118,16 +2180,32 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
   const int n_pad = (ni + 31) & ~31;
   const int nb = n_pad / 32;
   RmPlan rp;
-  alignas(64) CUtensorMap tmap8, tmap32;
+  alignas(64) CUtensorMap tmap8, tmap32, tmap3;
+  bool use3d = false;
   if (LAYOUT == CHUB_ROW_MAJOR && !getenv("CHUB_DF_V2")) {
     rp = rm_plan<T>(n, ld, L);
-    if (rp.ok && !(make_tmap<T>(&tmap8, L, n, ld, 8) && make_tmap<T>(&tmap32, L, n, ld, 32))) rp.ok = false;
+    // tmap32: the chain's box (all d band tiles of a block column); tmap8 / tmap3: the row warps' boxes
+#ifdef CHUB_CHAIN_V4
+    if (rp.ok && !(make_tmap<T>(&tmap8, L, n, ld, 8) &&
+                   make_tmap3<T>(&tmap32, L, n, ld, kPanel * (kDfD - 1), RmGeom<T>::HALVES)))
+      rp.ok = false;
+#else
+    if (rp.ok && !(make_tmap<T>(&tmap8, L, n, ld, 8) &&
+                   make_tmap3<T>(&tmap32, L, n, ld, kPanel * kDfD, RmGeom<T>::HALVES)))
+      rp.ok = false;
+#endif
+    if (rp.ok) {
+      const char *e3 = getenv("CHUB_RM5_3D");
+      use3d = !(e3 && e3[0] == '0') && make_tmap3<T>(&tmap3, L, n, ld, 8, 2 * RmGeom<T>::HALVES);
+      if (!use3d) tmap3 = tmap8;
+    }
   }
   CmPlan cp;
-  alignas(64) CUtensorMap tmapc;
+  alignas(64) CUtensorMap tmapc, tmapcb;  // tmapcb: the chain's box (32 d rows x 32 columns)
   if (LAYOUT == CHUB_COL_MAJOR && !getenv("CHUB_DF_V2")) {
     cp = cm_plan<T>(n, ld, L);
-    if (cp.ok && !make_tmap_cm<T>(&tmapc, L, n, ld)) cp.ok = false;
+    if (cp.ok && !(make_tmap_cm<T>(&tmapc, L, n, ld) && make_tmap_cm<T>(&tmapcb, L, n, ld, kPanel * kDfD)))
+      cp.ok = false;
   }
   const bool tm = rp.ok || cp.ok;  // a tensor-map kernel (band depth kDfD)
   DfPlan pl;
@@ -2137,29 +2215,38 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
   }
   // one pre-pass: w-tilde / v0 / dg / sentinels (prepare) and the inverse diagonal blocks
   df_prepass_kernel<T, LAYOUT><<<(nb + 3) / 4, 128, 0, st>>>(L, ni, ld, v, ws, flags, status,
+#ifdef CHUB_CHAIN_V4
+                                                              tm ? kDfD : kV2D, rp.ok, w_in);
+#else
                                                               tm ? kDfD : kV2D, false, w_in);
+#endif
   ++*launches;
   DfParams P;
   P.n = ni; P.T = nb; P.ld = ld; P.ws = ws; P.status = status;
   P.prof = nullptr;
-  if (getenv("CHUB_PROFILE")) {
+  if (const char *pe = getenv("CHUB_PROFILE")) {
+    P.prof_late = pe[0] == '2';
     P.prof = reinterpret_cast<long long *>(reinterpret_cast<char *>(ws.flags) + 256);
     cudaMemsetAsync(P.prof, 0, (256 * 16 + 8 * ((size_t)n / 32 + 2)) * sizeof(long long), st);
   }
   cudaError_t e;
   if (rp.ok) {
     P.R = 16; P.r_shift = 4; P.Wk = rp.Wk; P.rows_max = rp.Q * 16; P.nw = rp.nrw;
-    auto kern = P.prof ? df_kernel_rm<T, UPDATE, true> : df_kernel_rm<T, UPDATE, false>;
+    P.use3d = use3d ? 1 : 0;
+    const char *e5 = getenv("CHUB_RM5");
+    const bool v5 = !(e5 && e5[0] == '0');
+    auto kern = v5 ? (P.prof ? df_kernel_rm<T, UPDATE, true, true> : df_kernel_rm<T, UPDATE, false, true>)
+                   : (P.prof ? df_kernel_rm<T, UPDATE, true, false> : df_kernel_rm<T, UPDATE, false, false>);
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rp.smem);
     if (e != cudaSuccess) return (int)e;
-    void *args[] = {(void *)&L, (void *)&v, (void *)&P, (void *)&tmap8, (void *)&tmap32};
+    void *args[] = {(void *)&L, (void *)&v, (void *)&P, (void *)&tmap8, (void *)&tmap32, (void *)&tmap3};
     e = cudaLaunchCooperativeKernel((void *)kern, dim3(rp.sms), dim3(rp.threads), args, rp.smem, st);
   } else if (cp.ok) {
     P.R = 32; P.r_shift = 5; P.Wk = cp.Wk; P.rows_max = cp.Q * 32; P.nw = cp.Q;
     auto kern = P.prof ? df_kernel_cm<T, UPDATE, true> : df_kernel_cm<T, UPDATE, false>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.smem);
     if (e != cudaSuccess) return (int)e;
-    void *args[] = {(void *)&L, (void *)&v, (void *)&P, (void *)&tmapc};
+    void *args[] = {(void *)&L, (void *)&v, (void *)&P, (void *)&tmapc, (void *)&tmapcb};
     e = cudaLaunchCooperativeKernel((void *)kern, dim3(cp.sms), dim3(kCmMaxThreads), args, cp.smem, st);
   } else {
     P.R = pl.R; P.r_shift = pl.r_shift; P.Wk = pl.Wk; P.rows_max = pl.rows_max; P.nw = pl.nw;

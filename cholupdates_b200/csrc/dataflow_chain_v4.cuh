@@ -82,7 +82,7 @@ __device__ void df_chain_v4(const DfParams &P, const CUtensorMap *tmap32, unsign
 
   if (warp == 0) {
     // ------------------------------------------------------------ C: the critical path
-    const long long t_chain0 = DF_PROF_T();
+    long long t_chain0 = DF_PROF_T();
     {
       const double w0 = df_wait_value(P.ws.w + lane, P.status);
       pbuf[lane] = w0;  // (staging: the mat-vec reads all 32 entries)
@@ -119,9 +119,14 @@ __device__ void df_chain_v4(const DfParams &P, const CUtensorMap *tmap32, unsign
     }
     for (int j = 0; j + 1 < T_; ++j) {
       const int r = j + 1;
+      if (PROF && P.prof && P.prof_late && j == T_ * 5 / 8) {
+        for (int i = 0; i < 8; ++i) pacc[i] = 0;
+        t_chain0 = clock64();
+      }
       long long tp = DF_PROF_T();
       mbar_wait(&full[j % kDfSlots], (unsigned)((j / kDfSlots) & 1), P.status);
       if (lane == 0) DF_PROF_ADD(1, tp);
+      tp = DF_PROF_T();
       const double *M = reinterpret_cast<const double *>(slots + (size_t)(j % kDfSlots) * SLOT + kChTiles * CTILE +
                                                          kXBlock * 8) + lane * kXStride;
       const double *pj = pbuf + (j % kChRing) * kPanel;
@@ -137,6 +142,7 @@ __device__ void df_chain_v4(const DfParams &P, const CUtensorMap *tmap32, unsign
         a2 = fma(y.x, b.x, a2);
         a3 = fma(y.y, b.y, a3);
       }
+      if (lane == 0) DF_PROF_ADD(4, tp);
       tp = DF_PROF_T();
       double u = u_first;
       if (r > 1) {
@@ -164,6 +170,7 @@ __device__ void df_chain_v4(const DfParams &P, const CUtensorMap *tmap32, unsign
     double acc = 0.0;
     double *ws_ = wsum + k4 * kPanel;
     for (int j = 0; j < T_; ++j) {
+      if (PROF && P.prof && P.prof_late && j == T_ * 5 / 8) pacc[3] = 0;
       const int r = j + 2 + ((k4 - j) & 3);  // my block row among j+2 .. j+5:  r = k4 + 2 (mod 4)
       if (r < T_) {
         if (j == 0 || r - j == kDfD) acc = 0.0;  // first tile of this block row
@@ -172,24 +179,26 @@ __device__ void df_chain_v4(const DfParams &P, const CUtensorMap *tmap32, unsign
         mbar_wait(&full[j % kDfSlots], (unsigned)((j / kDfSlots) & 1), P.status);
         if (lane == 0 && k4 == 0) DF_PROF_ADD(3, tp);
         const unsigned char *slot = slots + (size_t)(j % kDfSlots) * SLOT;
-        const unsigned char *tb = slot + (size_t)(r - j - 2) * CTILE;
+        const unsigned char *tb = slot + (size_t)(r - j - 2) * 4096;  // [half][tile q][32 rows][128 B]
         const double *pj = pbuf + (j % kChRing) * kPanel;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         if (LAYOUT == CHUB_COL_MAJOR) {
-          const T *tc = reinterpret_cast<const T *>(tb) + lane;  // element (row = lane, column k) at [k][lane]
+          // element (tile q, row = lane, column k) at [k][32 q + lane]
+          const T *tc = reinterpret_cast<const T *>(slot) + (r - j - 2) * kPanel + lane;
+          constexpr int CS = kChTiles * kPanel;
 #pragma unroll
           for (int k = 0; k < kPanel; k += 4) {
             const double2 pp = *reinterpret_cast<const double2 *>(pj + k);
             const double2 pq = *reinterpret_cast<const double2 *>(pj + k + 2);
-            a0 = fma((double)tc[k * kPanel], pp.x, a0);
-            a1 = fma((double)tc[(k + 1) * kPanel], pp.y, a1);
-            a2 = fma((double)tc[(k + 2) * kPanel], pq.x, a2);
-            a3 = fma((double)tc[(k + 3) * kPanel], pq.y, a3);
+            a0 = fma((double)tc[k * CS], pp.x, a0);
+            a1 = fma((double)tc[(k + 1) * CS], pp.y, a1);
+            a2 = fma((double)tc[(k + 2) * CS], pq.x, a2);
+            a3 = fma((double)tc[(k + 3) * CS], pq.y, a3);
           }
         } else {
 #pragma unroll
         for (int h = 0; h < HALVES; ++h) {
-          const unsigned char *rowp = tb + h * 4096 + lane * 128;
+          const unsigned char *rowp = tb + h * (kChTiles * 4096) + lane * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const int4 raw = *reinterpret_cast<const int4 *>(rowp + ((c ^ (lane & 7)) << 4));
@@ -242,6 +251,7 @@ __device__ void df_chain_v4(const DfParams &P, const CUtensorMap *tmap32, unsign
     if (T_ > 2) b0 = ld_relaxed_u64(P.ws.w + 2 * kPanel + lane);
     if (T_ > 3) b1 = ld_relaxed_u64(P.ws.w + 3 * kPanel + lane);
     for (int r = 2; r < T_; ++r) {
+      if (PROF && P.prof && P.prof_late && r == T_ * 5 / 8) pacc[5] = 0;
       // X_r travels with block column r - 2: my row of it goes into registers, the slot is released
       const int jx = r - 2;
       mbar_wait(&full[jx % kDfSlots], (unsigned)((jx / kDfSlots) & 1), P.status);
@@ -278,13 +288,11 @@ __device__ void df_chain_v4(const DfParams &P, const CUtensorMap *tmap32, unsign
   } else if (warp == 6) {
     // ------------------------------------------------------------ T: TMA loads, block column jj -> slot jj % 4
     for (int jj = 0; jj < T_; ++jj) {
-      if (kDfPf > 0) {  // band tiles of block column jj + kDfPf -> L2 (all lanes; nothing to wait for)
+      if (kDfPf > 0) {  // band tiles of block column jj + kDfPf -> L2 (nothing to wait for)
         const int jp = jj + kDfPf;
-        const int np = min(kChTiles, T_ - 2 - jp);
-        if (LAYOUT == CHUB_COL_MAJOR) {
-          if (lane < np) tma_prefetch_2d(tmap32, (jp + 2 + lane) * kPanel, jp * kPanel);
-        } else if (lane < np * HALVES) {
-          tma_prefetch_2d(tmap32, jp * kPanel + (lane % HALVES) * BOXC, (jp + 2 + lane / HALVES) * kPanel);
+        if (jp + 2 < T_ && elect_one()) {
+          if (LAYOUT == CHUB_COL_MAJOR) tma_prefetch_2d(tmap32, (jp + 2) * kPanel, jp * kPanel);
+          else tma_prefetch_3d(tmap32, 0, (jp + 2) * kPanel, jp * HALVES);
         }
       }
       if (elect_one()) {
@@ -298,24 +306,18 @@ __device__ void df_chain_v4(const DfParams &P, const CUtensorMap *tmap32, unsign
         const int slot = jj % kDfSlots;
         void *bar = &full[slot];
         unsigned char *sb = slots + (size_t)slot * SLOT;
-        int ntiles = min(kChTiles, T_ - 2 - jj);
-        if (ntiles < 0) ntiles = 0;
-        const bool do_x = jj + 2 < T_, do_m = jj + 1 < T_;
-        const unsigned bytes = (unsigned)ntiles * CTILE + (do_x ? kXBlock * 8u : 0u) + (do_m ? kXBlock * 8u : 0u);
+        const bool do_t = jj + 2 < T_, do_m = jj + 1 < T_;  // (do_t: tiles and X_{jj+2})
+        const unsigned bytes = (do_t ? (unsigned)kChTiles * CTILE + kXBlock * 8u : 0u) + (do_m ? kXBlock * 8u : 0u);
         if (bytes == 0) {
           mbar_arrive(bar);
         } else {
           mbar_arrive_expect_tx(bar, bytes);
           if (do_m) bulk_g2s(sb + kChTiles * CTILE + kXBlock * 8, P.ws.M1 + (int64_t)(jj + 1) * kXBlock, kXBlock * 8u, bar);
-          for (int q = 0; q < ntiles; ++q) {
-            if (LAYOUT == CHUB_COL_MAJOR) {  // (coordinates: row first -- rows are the contiguous dimension)
-              tma_load_2d(sb + (size_t)q * CTILE, tmap32, (jj + 2 + q) * kPanel, jj * kPanel, bar);
-            } else {
-              for (int h = 0; h < HALVES; ++h)
-                tma_load_2d(sb + (size_t)q * CTILE + h * 4096, tmap32, jj * kPanel + h * BOXC, (jj + 2 + q) * kPanel, bar);
-            }
+          if (do_t) {  // ONE box: the four band tiles (block rows jj+2 .. jj+5); rows past the end are zero-filled
+            if (LAYOUT == CHUB_COL_MAJOR) tma_load_2d(sb, tmap32, (jj + 2) * kPanel, jj * kPanel, bar);
+            else tma_load_3d(sb, tmap32, 0, (jj + 2) * kPanel, jj * HALVES, bar);
+            bulk_g2s(sb + kChTiles * CTILE, P.ws.X + (int64_t)(jj + 2) * kXBlock, kXBlock * 8u, bar);
           }
-          if (do_x) bulk_g2s(sb + kChTiles * CTILE, P.ws.X + (int64_t)(jj + 2) * kXBlock, kXBlock * 8u, bar);
         }
       }
       __syncwarp();

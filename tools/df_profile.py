@@ -36,8 +36,15 @@ lib.chub_debug_profile(None, n, out.ctypes.data, ctas)
 P = out.reshape(ctas, 16)
 T = (n + 31) // 32
 ch = P[0]
-print(f"CHAIN (cycles per block row, T={T}): C total {ch[0]/T:.0f} | C: wait ring slot {ch[1]/T:.0f} | C: wait ua_r {ch[2]/T:.0f} | "
-      f"C: wait xw_r {ch[6]/T:.0f} | band warp 0: wait ring slot {ch[3]/T:.0f} (per column) | P: poll wt {ch[5]/T:.0f}")
+Tc = T - T * 5 // 8 if os.environ.get("CHUB_PROFILE") == "2" else T
+if not os.environ.get("CHUB_V4") and not os.environ.get("CHUB_BARRIER_CHAIN"):
+    print(f"CHAIN v6 (cycles per block row over the last {Tc} of {T}): Cb total {ch[0]/Tc:.0f} | Cb: wait ring slot {ch[1]/Tc:.0f} | Cb: wait w_r {ch[3]/Tc:.0f} | "
+          f"Ca: wait ring slot {ch[9]/Tc:.0f} | Ca: wait wt_r {ch[11]/Tc:.0f} | Ca: wait p_(r-1) {ch[10]/Tc:.0f} | Ca: dot + hand-over {ch[12]/Tc:.0f} | Cb: dot + publish {ch[5]/Tc:.0f} | P: poll wt {ch[4]/Tc:.0f}")
+if os.environ.get("CHUB_V4"):
+    print(f"CHAIN v4 (cycles per block row over the last {Tc} of {T}): C total {ch[0]/Tc:.0f} | C: wait ring slot {ch[1]/Tc:.0f} | C: M1 mat-vec {ch[4]/Tc:.0f} | "
+          f"C: wait ua_r {ch[2]/Tc:.0f} | C: wait xw_r {ch[6]/Tc:.0f} | band warp 0: wait ring slot {ch[3]/Tc:.0f} | P: poll wt {ch[5]/Tc:.0f}")
+print(f"CHAIN (cycles per block row over the last {Tc} of {T}): total {ch[0]/Tc:.0f} | phase A: wait for the tiles {ch[1]/Tc:.0f}, "
+      f"whole phase {ch[2]/Tc:.0f} | barrier + w {ch[3]/Tc:.0f} | phase B mat-vec {ch[5]/Tc:.0f} | poll warp: wt {ch[4]/Tc:.0f}")
 W = P[1:]
 steps = T + 4
 names = ["total", "wait tile (mbar)", "wait_read+issue load", "compute", "wait coefs", "fence+store+release", "w7 poll p", "w7 per panel total"]
@@ -55,6 +62,22 @@ t0 = tr[2][tr[2] > 0].min()
 for r in (40, 41, 42, 43, 200, 201, 202, 203, 400, 401, 402):
     if r >= T: continue
     print(f"r={r:4d}: " + "  ".join(f"{names[e][:12]}={(tr[e, r] - t0) / 1e3:8.2f}us" if tr[e, r] > 0 else f"{names[e][:12]}=   --   " for e in range(7)))
+# pace through the run: time per block column in windows of 32 block columns, from the chain's
+# publications (event 2) and from the bottom row warp of worker 0 (event 5: iteration starts)
+for ev, lab in ((2, "chain publishes p"), (3, "relay has p"), (5, "bottom row warp of worker 0 starts pan")):
+    idx = np.nonzero(tr[ev] > 0)[0]
+    if idx.size < 8:
+        continue
+    win = []
+    for a in range(0, T, 32):
+        sel = idx[(idx >= a) & (idx < a + 32)]
+        if sel.size >= 2:
+            win.append((tr[ev][sel[-1]] - tr[ev][sel[0]]) / (sel[-1] - sel[0]))
+        else:
+            win.append(float("nan"))
+    print(f"pace [{lab}] ns per block column, windows of 32: " + " ".join(f"{w:.0f}" for w in win))
+if (tr[2] > 0).sum() < 100:
+    sys.exit(0)
 d = np.diff(tr[2][50:T - 8])
 print(f"chain period (p_r -> p_r+1): mean {d.mean():.0f} ns, median {np.median(d):.0f} ns")
 for (a, b, lab) in ((0, 1, "wt published -> chain sees it"), (1, 2, "chain sees wt -> p published"), (2, 3, "p published -> coef warp has it"),

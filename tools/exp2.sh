@@ -1,0 +1,13 @@
+# tools/exp2.sh <tag>: rm5 workers vs first generation on one box (timing + cross-check vs the panel path)
+tag=$1
+out=gpurun_out/${tag}_exp.txt
+for cfg in "CHUB_RM5=0" "CHUB_RM5=1"; do
+  echo "=== $cfg" >> $out
+  env $cfg timeout 120 python tools/time_update.py 16384 30 >> $out 2>&1
+done
+for n in 96 130 1000 4000 8200; do
+  echo "=== n=$n" >> $out
+  timeout 120 python tools/time_update.py $n 10 >> $out 2>&1
+done
+CHUB_PROFILE=1 timeout 120 python tools/df_profile.py 16384 C > gpurun_out/${tag}_phase.txt 2>&1
+timeout 300 python tools/time_ops.py > gpurun_out/${tag}_time_ops.txt 2>&1

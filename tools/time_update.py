@@ -16,7 +16,10 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev)
 g.manual_seed(1234)
-L = torch.tril(torch.randn((n, n), dtype=torch.float64, device=dev, generator=g) / np.sqrt(n), -1)
+ldpad = int(os.environ.get("CHUB_LDPAD", "0"))  # leading dimension n + ldpad (power-of-two stride effects)
+ld = n + ldpad
+L = torch.zeros((n, ld), dtype=torch.float64, device=dev)[:, :n]
+L.copy_(torch.tril(torch.randn((n, n), dtype=torch.float64, device=dev, generator=g) / np.sqrt(n), -1))
 L.diagonal().copy_(1 + torch.rand(n, dtype=torch.float64, device=dev, generator=g))
 V = torch.randn((steps + 4, n), dtype=torch.float64, device=dev, generator=g)
 ws_bytes = int(lib.chub_workspace_bytes(1, n))
@@ -25,7 +28,7 @@ status = torch.zeros(steps + 4, dtype=torch.int32, device=dev)
 stream = torch.cuda.current_stream().cuda_stream
 
 # cross-check one update against the panel path
-La, Lb = L.clone(), L.clone()
+La, Lb = L.contiguous().clone(), L.contiguous().clone()
 va, vb = V[0].clone(), V[0].clone()
 assert lib.chub_update_f64(La.data_ptr(), n, n, 0, va.data_ptr(), 0, ws.data_ptr(), ws_bytes, status.data_ptr(), stream) == 0
 lib.chub_set_path(2)
@@ -40,12 +43,12 @@ del La, Lb
 
 Vw = V.clone()
 for i in range(3):
-    lib.chub_update_f64(L.data_ptr(), n, n, 0, Vw[steps + i].data_ptr(), 0, ws.data_ptr(), ws_bytes, status.data_ptr(), stream)
+    lib.chub_update_f64(L.data_ptr(), n, ld, 0, Vw[steps + i].data_ptr(), 0, ws.data_ptr(), ws_bytes, status.data_ptr(), stream)
 torch.cuda.synchronize()
 evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
 for i in range(steps):
     evs[i][0].record()
-    lib.chub_update_f64(L.data_ptr(), n, n, 0, Vw[i].data_ptr(), 0, ws.data_ptr(), ws_bytes, status[i:].data_ptr(), stream)
+    lib.chub_update_f64(L.data_ptr(), n, ld, 0, Vw[i].data_ptr(), 0, ws.data_ptr(), ws_bytes, status[i:].data_ptr(), stream)
     evs[i][1].record()
 torch.cuda.synchronize()
 ms = [a.elapsed_time(b) for a, b in evs]
