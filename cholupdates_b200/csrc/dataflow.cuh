@@ -1374,7 +1374,7 @@ df_kernel_rm(T *L, T *v, DfParams P, const __grid_constant__ CUtensorMap tmap8,
 #ifdef CHUB_CHAIN_V4
     if (threadIdx.x < 256) df_chain_v4<T, CHUB_ROW_MAJOR, PROF>(P, &tmap32, df_smem);
 #elif CHUB_CHAIN_V6
-    if (threadIdx.x < kC6Threads) df_chain_v6<T, CHUB_ROW_MAJOR, PROF>(P, &tmap32, df_smem);
+    if (threadIdx.x < kC6ThreadsSplit) df_chain_v6<T, CHUB_ROW_MAJOR, PROF, false>(P, &tmap32, df_smem);
 #else
     if (threadIdx.x < 256) df_chain_rm<T, CHUB_ROW_MAJOR, PROF>(P, &tmap32, df_smem);
 #endif
@@ -1581,9 +1581,13 @@ __device__ void df_worker_cm(T *L, T *v, const DfParams &P, const CUtensorMap *t
   if (tid < 32) prog[tid] = tid < nrw ? 0 : 0x7fffffff;
   if (tid == 0) { *cprog = 0; *pprog = 0; }
   __syncthreads();
-  if (warp > nrw) return;
+  if (warp > nrw + 1) return;
+  if (warp == nrw + 1) {  // relay warp: p_s from global memory into the ring (split from the coefficient warp)
+    df_relay_warp<PROF>(P, coef, prog, pprog, wkr, lane, kDfD + 1);
+    return;
+  }
   if (warp == nrw) {
-    df_coef_warp<T, UPDATE, PROF>(v, P, coef, prog, cprog, pprog, wkr, lane);
+    df_coef_warp5<T, UPDATE, PROF>(v, P, coef, cprog, pprog, wkr, lane);
     return;
   }
 
@@ -1720,7 +1724,7 @@ inline size_t df_worker_cm_smem(int nrw) {
   return 2048 + (size_t)kDfCoefRing * 4 * kPanel * 8 + (size_t)kCmStages * nrw * CmGeom<T>::TILE;
 }
 
-constexpr int kCmMaxThreads = 256;  // chain: 8 warps; workers: kCmMaxQ row warps + coefficient warp
+constexpr int kCmMaxThreads = kC6ThreadsMerged > 256 ? kC6ThreadsMerged : 256;  // chain: v6 warp roles; workers: kCmMaxQ row warps + coefficient + relay warp
 
 template <typename T, bool UPDATE, bool PROF>
 __global__ void __launch_bounds__(kCmMaxThreads, 1)
@@ -1728,8 +1732,15 @@ df_kernel_cm(T *L, T *v, DfParams P, const __grid_constant__ CUtensorMap tmapc,
              const __grid_constant__ CUtensorMap tmapcb) {
   extern __shared__ __align__(1024) unsigned char df_smem[];
   if (*P.status != 0) return;  // check_diag failed: L and v stay untouched
-  if (blockIdx.x == 0) df_chain_rm<T, CHUB_COL_MAJOR, PROF>(P, &tmapcb, df_smem);
-  else df_worker_cm<T, UPDATE, PROF>(L, v, P, &tmapc, df_smem);
+  if (blockIdx.x == 0) {
+#if CHUB_CHAIN_V6
+    if (threadIdx.x < kC6ThreadsMerged) df_chain_v6<T, CHUB_COL_MAJOR, PROF, true>(P, &tmapcb, df_smem);
+#else
+    if (threadIdx.x < 256) df_chain_rm<T, CHUB_COL_MAJOR, PROF>(P, &tmapcb, df_smem);
+#endif
+  } else {
+    df_worker_cm<T, UPDATE, PROF>(L, v, P, &tmapc, df_smem);
+  }
 }
 
 // ---- downdate sweep, column-major: one warp per block row (lane = row), tiles from the diagonal to
@@ -1983,6 +1994,191 @@ __global__ void __launch_bounds__(128) dd_sweep_rm_kernel(T *L, int n, int64_t l
 template <typename T>
 inline size_t dd_sweep_rm_smem() { return 1024 + (size_t)4 * kSwStages * SwGeom<T>::STAGE; }
 
+// ---- downdate sweep, row-major, second generation: after the (ragged) diagonal tile a warp walks its rows right to
+// left in ITERATIONS of two block columns -- one 3-D tensor-map TMA load and one store per [8 rows][64 columns] tile
+// and three 512-byte bulk copies for (c, s, sgn) instead of fourteen TMA operations per 64 columns (the
+// first-generation kernel above was bound by the issue of those: 480 us = 68 % of the HBM roofline at n = 16384,
+// profiles/r03n).  Same arithmetic and lane mapping.
+constexpr int kSw2Stages = 3;
+
+template <typename T>
+struct Sw2Geom {
+  static constexpr int COEF = 3 * 2 * kPanel * 8;                                  // (c, s, sgn)[64] doubles
+  static constexpr int STAGE = ((2 * RmGeom<T>::WTILE + COEF + 1023) / 1024) * 1024;  // tile pair + coefficients
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) dd_sweep_rm2_kernel(T *L, int n, int64_t ld, LargeWs ws,
+                                                           const int32_t *status, int use3d,
+                                                           const __grid_constant__ CUtensorMap tmap8,
+                                                           const __grid_constant__ CUtensorMap tmap3) {
+  constexpr int HALVES = RmGeom<T>::HALVES, BOXC = RmGeom<T>::BOXC, CPT = RmGeom<T>::CPT;
+  constexpr int WTILE = RmGeom<T>::WTILE, STAGE = Sw2Geom<T>::STAGE;
+  extern __shared__ __align__(1024) unsigned char sw_smem[];
+  if (*status != 0) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int T_ = (n + 31) / 32;
+  const int b = T_ - 1 - blockIdx.x;  // longest rows first
+  const int64_t row0 = (int64_t)b * 32 + warp * 8;
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(sw_smem) + warp * kSw2Stages;
+  unsigned char *mystage = sw_smem + 1024 + (size_t)warp * kSw2Stages * STAGE;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4 * kSw2Stages; ++i) mbar_init(reinterpret_cast<unsigned long long *>(sw_smem) + i, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (row0 >= n) return;
+  const int g = lane >> 3, r8 = lane & 7;
+  const int64_t row = row0 + r8;
+  const int hh = (g * 8 * (int)sizeof(T)) / 128;
+  const int cb = ((g * 8 * (int)sizeof(T)) % 128) / 16;
+  const unsigned my_off = hh * 1024 + r8 * 128;
+  const int n3 = use3d ? (n / BOXC) * BOXC : 0;
+  // iterations: 0 = the diagonal tile b; then pairs (b-1, b-2), (b-3, b-4), ...; a last single tile 0 if b is odd
+  const int NI = 1 + (b + 1) / 2;
+  auto iter = [&](int it, int &pan_lo, int &cnt) {  // block columns pan_lo .. pan_lo + cnt - 1
+    if (it == 0) { pan_lo = b; cnt = 1; return; }
+    const int hi = b - 1 - 2 * (it - 1);
+    if (hi >= 1) { pan_lo = hi - 1; cnt = 2; } else { pan_lo = 0; cnt = 1; }
+  };
+
+  auto issue_load = [&](int it) {  // elected lane
+    if (it >= NI) return;
+    int pan_lo, cnt;
+    iter(it, pan_lo, cnt);
+    const int st = it % kSw2Stages;
+    void *bar = &full[st];
+    unsigned char *stg = mystage + (size_t)st * STAGE;
+    const int c0 = pan_lo * kPanel;
+    const unsigned cbytes = (unsigned)cnt * kPanel * 8u;
+    if (cnt == 2 && c0 + 2 * kPanel <= n3) {
+      mbar_arrive_expect_tx(bar, 2u * WTILE + 3u * cbytes);
+      tma_load_3d(stg, &tmap3, 0, (int)row0, c0 / BOXC, bar);
+    } else {
+      unsigned bytes = 0;
+      for (int t = 0; t < cnt; ++t) bytes += (HALVES == 2 && c0 + t * kPanel + BOXC < n) ? 2048u : 1024u;
+      mbar_arrive_expect_tx(bar, bytes + 3u * cbytes);
+      for (int t = 0; t < cnt; ++t) {
+        const int cc = c0 + t * kPanel;
+        tma_load_2d(stg + t * WTILE, &tmap8, cc, (int)row0, bar);
+        if (HALVES == 2 && cc + BOXC < n) tma_load_2d(stg + t * WTILE + 1024, &tmap8, cc + BOXC, (int)row0, bar);
+      }
+    }
+    // coefficient area: [c | s | sgn], each 64 doubles (the first cnt * 32 used), indexed by column - c0
+    bulk_g2s(stg + 2 * WTILE, ws.c + c0, cbytes, bar);
+    bulk_g2s(stg + 2 * WTILE + 512, ws.sg + c0, cbytes, bar);
+    bulk_g2s(stg + 2 * WTILE + 1024, ws.dn + c0, cbytes, bar);
+  };
+
+  if (elect_one()) {
+    issue_load(0);
+    if (kSw2Stages > 2) issue_load(1);
+  }
+  __syncwarp();
+
+  double xc = 0.0;  // x_i carried from the tile to the right
+  // one tile: tile bytes at tp, coefficients of its 32 columns at cf0 (c), cf0 + 64 (s), cf0 + 128 (sgn)
+  auto do_tile = [&](unsigned char *tp, const double *cf0, int pan, bool diag_step) {
+    unsigned char *rowp = tp + my_off;
+    const double *cf = cf0 + g * 8;
+    const int64_t c0 = (int64_t)pan * kPanel + g * 8;
+    int4 raw[CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) raw[i] = *reinterpret_cast<const int4 *>(rowp + (((cb + i) ^ r8) << 4));
+    T *x = reinterpret_cast<T *>(raw);
+    double cc[8], sc[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const double2 a = *reinterpret_cast<const double2 *>(cf + j);
+      const double2 d = *reinterpret_cast<const double2 *>(cf + 64 + j);
+      cc[j] = a.x; cc[j + 1] = a.y; sc[j] = d.x; sc[j + 1] = d.y;
+    }
+    // pass 1: the affine map x -> A x + B of my 8 columns (right to left)
+    double A = 1.0, B = 0.0;
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+      lo[j] = (double)x[j];
+      if (!diag_step || c0 + j <= row) {
+        B = fma(cc[j], B, sc[j] * lo[j]);
+        A *= cc[j];
+      } else {
+        // above the diagonal: identity map, entry left alone; its bits (never read by the reference,
+        // possibly NaN) must not reach the arithmetic
+        cc[j] = 1.0; sc[j] = 0.0; lo[j] = 0.0;
+      }
+    }
+    // inclusive suffix composition over the 4 lanes of the row: P_g = M_g o M_{g+1} o ... o M_3
+    double PA = A, PB = B;
+    double qa = __shfl_down_sync(0xffffffffu, PA, 8), qb = __shfl_down_sync(0xffffffffu, PB, 8);
+    if (g <= 2) { PB = fma(PA, qb, PB); PA *= qa; }
+    qa = __shfl_down_sync(0xffffffffu, PA, 16); qb = __shfl_down_sync(0xffffffffu, PB, 16);
+    if (g <= 1) { PB = fma(PA, qb, PB); PA *= qa; }
+    // incoming x of my segment = (M_{g+1} o ... o M_3)(xc);  outgoing x of the tile = P_0(xc)
+    const double ea = __shfl_down_sync(0xffffffffu, PA, 8), eb = __shfl_down_sync(0xffffffffu, PB, 8);
+    double xi = g == 3 ? xc : fma(ea, xc, eb);
+    const double xout = fma(__shfl_sync(0xffffffffu, PA, r8), xc, __shfl_sync(0xffffffffu, PB, r8));
+    // pass 2: new entries
+    const double *sgp = cf + 128;
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+      const double lnew = sgp[j] * (cc[j] * lo[j] - sc[j] * xi);
+      xi = fma(cc[j], xi, sc[j] * lo[j]);
+      if (!diag_step || c0 + j <= row) x[j] = (T)lnew;
+    }
+    xc = xout;
+    if (!diag_step) {
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) *reinterpret_cast<int4 *>(rowp + (((cb + i) ^ r8) << 4)) = raw[i];
+    } else if (row < n) {
+      T *gp = L + row * ld + c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j <= row) gp[j] = x[j];
+    }
+  };
+
+  for (int it = 0; it < NI; ++it) {
+    int pan_lo, cnt;
+    iter(it, pan_lo, cnt);
+    const int st = it % kSw2Stages;
+    mbar_wait(&full[st], (unsigned)((it / kSw2Stages) & 1), const_cast<int32_t *>(status));
+    unsigned char *stg = mystage + (size_t)st * STAGE;
+    const double *cfb = reinterpret_cast<const double *>(stg + 2 * WTILE);
+    const bool diag_step = it == 0;
+    if (cnt == 2) do_tile(stg + WTILE, cfb + kPanel, pan_lo + 1, false);  // right tile first (right-to-left sweep)
+    do_tile(stg, cfb, pan_lo, diag_step);
+    // loads run kSw2Stages - 1 iterations ahead; iteration it + stages - 1 reuses the stage of iteration it - 1,
+    // whose store has had this compute phase to leave shared memory
+    if (elect_one()) {
+      if (it >= 1) bulk_wait_read<0>();
+      issue_load(it + kSw2Stages - 1);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (elect_one()) {
+      if (!diag_step) {
+        const int c0 = pan_lo * kPanel;
+        if (cnt == 2 && c0 + 2 * kPanel <= n3) {
+          tma_store_3d(&tmap3, 0, (int)row0, c0 / BOXC, stg);
+        } else {
+          for (int t = 0; t < cnt; ++t) {
+            const int cc = c0 + t * kPanel;
+            tma_store_2d(&tmap8, cc, (int)row0, stg + t * WTILE);
+            if (HALVES == 2 && cc + BOXC < n) tma_store_2d(&tmap8, cc + BOXC, (int)row0, stg + t * WTILE + 1024);
+          }
+        }
+      }
+      bulk_commit();
+    }
+    __syncwarp();
+  }
+  if (elect_one()) bulk_wait_all<0>();
+}
+
+template <typename T>
+inline size_t dd_sweep_rm2_smem() { return 1024 + (size_t)4 * kSw2Stages * Sw2Geom<T>::STAGE; }
+
 // ------------------------------------------------------------------ host side
 inline size_t dataflow_flag_bytes(int64_t n) { return 256 + (256 * 16 + 8 * ((size_t)n / 32 + 2)) * sizeof(long long); }
 
@@ -2052,7 +2248,7 @@ inline RmPlan rm_plan(int64_t n, int64_t ld, const void *L) {
   smem = std::max(smem, df_chain_v6_smem<T>());
   if (smem > (size_t)smem_optin) return pl;
   pl.ok = true; pl.sms = sms; pl.Wk = Wk; pl.Q = Q; pl.nrw = nrw;
-  pl.threads = std::max(std::max(256, kC6Threads), 32 * (nrw + 2));  // row warps + coefficient warp + relay warp
+  pl.threads = std::max(std::max(256, kC6ThreadsSplit), 32 * (nrw + 2));  // row warps + coefficient warp + relay warp
   pl.smem = smem;
   return pl;
 }
@@ -2133,7 +2329,7 @@ inline CmPlan cm_plan(int64_t n, int64_t ld, const void *L) {
   const int64_t nRB = (n + kPanel - 1) / kPanel;
   const int Q = (int)((nRB + Wk - 1) / Wk);
   if (Q > kCmMaxQ) return pl;
-  const size_t smem = std::max(df_chain_rm_smem<T>(), df_worker_cm_smem<T>(Q));
+  const size_t smem = std::max(std::max(df_chain_rm_smem<T>(), df_chain_v6_smem<T>()), df_worker_cm_smem<T>(Q));
   if (smem > (size_t)smem_optin) return pl;
   pl.ok = true; pl.sms = sms; pl.Wk = Wk; pl.Q = Q; pl.smem = smem;
   return pl;
@@ -2259,9 +2455,16 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
   if (e != cudaSuccess) return (int)e;
   ++*launches;
   if (!UPDATE && !chain_only) {
-    large_dd_coef_kernel<T, LAYOUT><<<1, 1024, 0, st>>>(L, ni, ld, v, ws, status);
+    if (getenv("CHUB_DD_COEF_V1")) large_dd_coef_kernel<T, LAYOUT><<<1, 1024, 0, st>>>(L, ni, ld, v, ws, status);
+    else dd_coef_par_kernel<T><<<1, 1024, 0, st>>>(ni, v, ws, status);  // (ws.dg: the pre-pass's copy of the diagonal)
     ++*launches;
-    if (rp.ok && !getenv("CHUB_DD_SWEEP_V1")) {
+    if (rp.ok && !getenv("CHUB_DD_SWEEP_V1") && !getenv("CHUB_DD_SWEEP_V2")) {
+      auto sk = dd_sweep_rm2_kernel<T>;
+      const size_t ssm = dd_sweep_rm2_smem<T>();
+      e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
+      if (e != cudaSuccess) return (int)e;
+      sk<<<nb, 128, ssm, st>>>(L, ni, ld, ws, status, use3d ? 1 : 0, tmap8, tmap3);
+    } else if (rp.ok && !getenv("CHUB_DD_SWEEP_V1")) {
       auto sk = dd_sweep_rm_kernel<T>;
       const size_t ssm = dd_sweep_rm_smem<T>();
       e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
@@ -2350,13 +2553,17 @@ int launch_blocked_rm(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeW
   }
   if (!UPDATE) {
     const int nb = (ni + 31) / 32;
-    large_dd_coef_kernel<T, CHUB_ROW_MAJOR><<<1, 1024, 0, st>>>(L, ni, ld, v, ws, status);
+    if (getenv("CHUB_DD_COEF_V1")) large_dd_coef_kernel<T, CHUB_ROW_MAJOR><<<1, 1024, 0, st>>>(L, ni, ld, v, ws, status);
+    else dd_coef_par_kernel<T><<<1, 1024, 0, st>>>(ni, v, ws, status);
     ++*launches;
-    auto sk = dd_sweep_rm_kernel<T>;
-    const size_t ssm = dd_sweep_rm_smem<T>();
+    alignas(64) CUtensorMap tmap3;
+    const bool use3d = make_tmap3<T>(&tmap3, L, n, ld, 8, 2 * RmGeom<T>::HALVES);
+    if (!use3d) tmap3 = tmap8;
+    auto sk = dd_sweep_rm2_kernel<T>;
+    const size_t ssm = dd_sweep_rm2_smem<T>();
     e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
     if (e != cudaSuccess) return (int)e;
-    sk<<<nb, 128, ssm, st>>>(L, ni, ld, ws, status, tmap8);
+    sk<<<nb, 128, ssm, st>>>(L, ni, ld, ws, status, use3d ? 1 : 0, tmap8, tmap3);
     ++*launches;
   }
   return (int)cudaGetLastError();

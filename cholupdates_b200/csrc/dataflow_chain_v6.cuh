@@ -14,9 +14,9 @@
 //   warps 3.. B : the band tiles at distance 2 .. d: block row r belongs to band warp (r - 2) mod (d-1), which adds
 //                L[r, j] p_j for j = r-d .. r-2 as the p_j arrive (accumulator in registers, lane = row) and
 //                hands the sum over one block row before it is needed.
-//   next     P  : polls wt_r (handed over by the workers through global memory) into a shared ring.
-//   last     T  : one TMA box per block column (all d band tiles) + X, as soon as the ring slot's previous block
-//                column has been taken by everybody; L2 prefetch further ahead.
+//   last     PT : polls wt_r (handed over by the workers through global memory) into a shared ring, and issues one
+//                TMA box per block column (all d band tiles) + X as soon as the ring slot's previous block column
+//                has been taken by everybody; L2 prefetch further ahead.
 // The two hand-overs on the critical path (w_r: Ca -> Cb, p_r: Cb -> Ca) carry no flag and no fence: the data
 // is its own flag (NaN sentinel in the shared-memory ring, lane l polls element l, __syncwarp, then everybody
 // reads all 32).  The critical path per block row is: poll -> 16 broadcast LDS -> 32 DFMA (4 chains), twice.
@@ -25,7 +25,8 @@
 namespace chub {
 
 constexpr int kC6Ring = 8;  // p / g / wt rings (block rows)
-constexpr int kC6Threads = 32 * (5 + kDfD - 1);  // Ca x 2, Cb, d-1 band warps, P, T
+constexpr int kC6ThreadsMerged = 32 * (4 + kDfD - 1);  // Ca x 2, Cb, d-1 band warps, PT
+constexpr int kC6ThreadsSplit = 32 * (5 + kDfD - 1);   // ... with P and T on a warp each
 
 template <typename T>
 struct C6Geom {
@@ -120,12 +121,16 @@ __device__ __forceinline__ double c6_dot(const double (&t)[kPanel], const double
   return (a0 + a1) + (a2 + a3);
 }
 
-template <typename T, int LAYOUT, bool PROF>
+// MERGE_PT: one warp both polls wt and issues the TMA boxes (8 warps for d = 5: the column-major workers'
+// register budget allows 256 threads); split, the row-major update is 10 % faster (0.452 vs 0.50 ms at n = 16384:
+// the poller never sits behind a ring-slot wait, the TMA issue never behind a poll).
+template <typename T, int LAYOUT, bool PROF, bool MERGE_PT>
 __device__ void df_chain_v6(const DfParams &P, const CUtensorMap *tmapB, unsigned char *smem) {
+  constexpr int kC6Threads = MERGE_PT ? kC6ThreadsMerged : kC6ThreadsSplit;
   constexpr int HALVES = RmGeom<T>::HALVES;
   constexpr int TILES = C6Geom<T>::TILES, SLOT = C6Geom<T>::SLOT;
   constexpr int NB = kDfD - 1;  // band warps: distances 2 .. d, block row r belongs to band warp (r - 2) mod NB
-  static_assert(NB >= 1 && 5 + NB <= 16, "warp roles");
+  static_assert(NB >= 1 && 4 + NB <= 16, "warp roles");
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
   const int T_ = P.T;
@@ -265,7 +270,7 @@ __device__ void df_chain_v6(const DfParams &P, const CUtensorMap *tmapB, unsigne
       __syncwarp();
       if (lane == 0) st_release_cta_smem(bprog + k4, j + 1);  // my reads of ring slot j % kDfSlots are done
     }
-  } else if (warp == 3 + NB) {
+  } else if (!MERGE_PT && warp == 3 + NB) {
     // ------------------------------------------------------------ P: wt_r from the workers (global memory)
     unsigned long long b0 = ld_relaxed_u64(P.ws.w + lane);
     for (int r = 0; r < T_; ++r) {
@@ -285,8 +290,13 @@ __device__ void df_chain_v6(const DfParams &P, const CUtensorMap *tmapB, unsigne
       if (lane == 0) st_release_cta_smem(wtdone, r + 1);
     }
   } else {
-    // ------------------------------------------------------------ T: TMA loads, block column jj -> slot jj % kDfSlots
-    for (int jj = 0; jj + 1 < T_; ++jj) {
+    // ------------------------------------------------------------ T (split) / PT (merged)
+    // PT: wt_r from the workers (global memory) into
+    // the shared ring, and the TMA box of block column r + slots-1 (one warp: the CTA stays at 8 warps for d = 5,
+    // which the column-major workers' register budget needs).  Order: P(r) then T(r + slots - 1) -- T waits for
+    // block column r-1 to have been consumed, which needs wt_{r-1}: delivered one iteration earlier.
+    auto issue_column = [&](int jj) {  // all lanes call; one elected lane works
+      if (jj + 1 >= T_) return;
       if (elect_one()) {
         if (kDfPf > 0 && jj + kDfPf + 1 < T_) {  // the band box of a later block column -> L2
           if (LAYOUT == CHUB_COL_MAJOR) tma_prefetch_2d(tmapB, (jj + kDfPf + 1) * kPanel, (jj + kDfPf) * kPanel);
@@ -309,9 +319,32 @@ __device__ void df_chain_v6(const DfParams &P, const CUtensorMap *tmapB, unsigne
         bulk_g2s(sb + TILES, P.ws.X + (int64_t)(jj + 1) * kXBlock, kXBlock * 8u, bar);
       }
       __syncwarp();
+    };
+    if (!MERGE_PT) {
+      for (int jj = 0; jj + 1 < T_; ++jj) issue_column(jj);
+      return;
+    }
+    for (int jj = 0; jj < kDfSlots - 1; ++jj) issue_column(jj);
+    unsigned long long b0 = ld_relaxed_u64(P.ws.w + lane);
+    for (int r = 0; r < T_; ++r) {
+      if (r == late0) pacc[4] = 0;
+      long long tq = DF_PROF_T();
+#ifdef CHUB_EXP_CHAIN_FREE  // timing experiment (results are garbage): the chain never waits for the workers
+      const double wt = b0 != kSentinelBits ? __longlong_as_double((long long)b0) : 0.0;
+#else
+      const double wt = b0 != kSentinelBits ? __longlong_as_double((long long)b0)
+                                            : df_wait_value(P.ws.w + (int64_t)r * kPanel + lane, P.status);
+#endif
+      b0 = r + 1 < T_ ? ld_relaxed_u64(P.ws.w + (int64_t)(r + 1) * kPanel + lane) : kSentinelBits;
+      if (lane == 0) { DF_PROF_ADD(4, tq); DF_TRACE(1, r); }
+      if (r >= kC6Ring) c6_spin_lazy(wdone, r - kC6Ring + 1, P.status);  // ring slot: w_{r-8} has been formed
+      wtb[(r % kC6Ring) * kPanel + lane] = wt;
+      __syncwarp();
+      if (lane == 0) st_release_cta_smem(wtdone, r + 1);
+      issue_column(r + kDfSlots - 1);
     }
   }
-  if (PROF && P.prof && lane == 0 && (warp == 0 || warp == 2 || warp == 3 + NB)) {
+  if (PROF && P.prof && lane == 0 && (warp == 0 || warp == 2 || warp == 3 + NB)) {  // Ca (even rows), Cb, PT
     for (int i = 0; i < 8; ++i)
       if (pacc[i]) P.prof[(size_t)blockIdx.x * 16 + i + (warp == 0 ? 8 : 0)] = pacc[i];
   }

@@ -27,7 +27,7 @@ namespace chub {
 // rsqrt per block column (~1100 cycles) was what the row warps waited for (profiles/r02v).
 template <bool PROF>
 __device__ __forceinline__ void df_relay_warp(const DfParams &P, double *coef, volatile int *prog, volatile int *pprog,
-                                              int wkr, int lane) {
+                                              int wkr, int lane, int reuse_lag = 1) {
   const int T_ = P.T;
   long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   unsigned long long b0 = ld_relaxed_u64(P.ws.p + lane);
@@ -44,7 +44,9 @@ __device__ __forceinline__ void df_relay_warp(const DfParams &P, double *coef, v
     if (lane == 0) DF_PROF_ADD(6, tq);
     if (lane == 0 && wkr == 0) DF_TRACE(3, pan);
     if (pan >= kDfCoefRing) {  // the slot's previous block column (pan - ring) is no longer needed by any row warp
-      const int need = pan - kDfCoefRing + 1;
+      // prog[] = the next block column a row warp still needs (rm5, reuse_lag = 1) or the steps it has finished
+      // (column-major workers: block column pan - ring is read for the last time at step pan - ring + d)
+      const int need = pan - kDfCoefRing + reuse_lag;
       const long long t0 = clock64();
       while (__reduce_min_sync(0xffffffffu, ld_acquire_cta_smem(prog + lane)) < need) {
         if (clock64() - t0 > kWatchdogCycles) { atomicMax(P.status, CHUB_STATUS_INTERNAL); break; }
@@ -69,22 +71,33 @@ __device__ __forceinline__ void df_coef_warp5(T *v, const DfParams &P, double *c
   if (!UPDATE) return;  // forward substitution only: the row warps never look at cprog
   const int n = P.n, T_ = P.T, Wk = P.Wk;
   double t_run = P.ws.scal[0], S_run = P.ws.scal[1];  // (1, 1) unless a blocked driver carries them over
-  double ndgA = P.ws.dg[lane], ndgB = T_ > 1 ? P.ws.dg[kPanel + lane] : 1.0;
-  for (int pan = 0; pan < T_; pan += 2) {
-    const bool two = pan + 1 < T_;
-    const int upto = pan + (two ? 2 : 1);
-    if (ld_acquire_cta_smem(pprog) < upto) {
+  // the input diagonal of the next three block columns, prefetched (an L2 round trip each)
+  double d0 = P.ws.dg[lane], d1 = T_ > 1 ? P.ws.dg[kPanel + lane] : 1.0, d2 = T_ > 2 ? P.ws.dg[2 * kPanel + lane] : 1.0;
+  for (int pan = 0; pan < T_;) {
+    if (ld_acquire_cta_smem(pprog) < pan + 1) {
       const long long t0 = clock64();
-      while (ld_acquire_cta_smem(pprog) < upto) {
+      while (ld_acquire_cta_smem(pprog) < pan + 1) {
         if (clock64() - t0 > kWatchdogCycles) { atomicMax(P.status, CHUB_STATUS_INTERNAL); break; }
       }
     }
+    // two block columns at once when the second one's p is already there (the row-major row warps consume pairs,
+    // and while the chain runs ahead of the workers it always is); never wait for it (the column-major row
+    // warps take one block column per step: waiting would add a chain period to every other step)
+    const bool two = pan + 1 < T_ && ld_acquire_cta_smem(pprog) >= pan + 2;
+    const int upto = pan + (two ? 2 : 1);
     double *cfA = coef + (size_t)(pan % kDfCoefRing) * 4 * kPanel;
     double *cfB = coef + (size_t)((pan + 1) % kDfCoefRing) * 4 * kPanel;
     const double pA = cfA[lane], pB = two ? cfB[lane] : 0.0;
-    const double dgA = ndgA, dgB = ndgB;
-    if (pan + 2 < T_) ndgA = P.ws.dg[(pan + 2) * kPanel + lane];
-    if (pan + 3 < T_) ndgB = P.ws.dg[(pan + 3) * kPanel + lane];
+    const double dgA = d0, dgB = two ? d1 : 1.0;
+    if (two) {
+      d0 = d2;
+      d1 = pan + 3 < T_ ? P.ws.dg[(pan + 3) * kPanel + lane] : 1.0;
+      d2 = pan + 4 < T_ ? P.ws.dg[(pan + 4) * kPanel + lane] : 1.0;
+    } else {
+      d0 = d1;
+      d1 = d2;
+      d2 = pan + 3 < T_ ? P.ws.dg[(pan + 3) * kPanel + lane] : 1.0;
+    }
     double inA = pA * pA, inB = pB * pB;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -139,6 +152,7 @@ __device__ __forceinline__ void df_coef_warp5(T *v, const DfParams &P, double *c
     }
     if (two && (__popc(negB) & 1)) S_run = -S_run;
     t_run = two ? t_mid + __shfl_sync(0xffffffffu, inB, 31) : t_mid;
+    pan = upto;
   }
   if (wkr == 0 && lane == 0) { P.ws.scal[4] = t_run; P.ws.scal[5] = S_run; }
 }

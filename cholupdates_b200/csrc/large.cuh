@@ -458,6 +458,87 @@ __global__ void __launch_bounds__(256) tri_transpose_kernel(T *dst, int64_t ldd,
 // input diagonal, v <- rotg's z_k (or v <- p when the result is not positive definite).
 // Thread t owns the contiguous chunk [b0, b1) of columns; the chunk sums are combined by a block-wide
 // suffix scan (warp shuffles + one shared-memory hop) instead of every thread summing all 1024 partials.
+// The same coefficients for the persistent-kernel paths, which keep a copy of the input diagonal (ws.dg): every
+// access coalesced, 1024 elements per block step (suffix scan over the block: warp shuffles + one exchange of the
+// 32 warp totals), the square roots / divisions of different elements independent of each other.  (The kernel
+// below walks 16 consecutive elements per thread with strided loads and a serial sqrt/div chain: 88 us at
+// n = 16384, a tenth of the whole downdate -- profiles/r03n.)
+template <typename T>
+__global__ void __launch_bounds__(1024) dd_coef_par_kernel(int n, T *v, LargeWs ws, int32_t *status) {
+  constexpr int NT = 1024;
+  __shared__ double wsum[NT / 32];
+  __shared__ double wabove[NT / 32];
+  __shared__ double total_s;
+  if (*status != 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nch = (n + NT - 1) / NT;
+  // pass 1: p . p
+  double acc = 0.0;
+  for (int i = tid; i < n; i += NT) { const double x = ws.p[i]; acc = fma(x, x, acc); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if (lane == 0) wsum[warp] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    double t = wsum[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    if (lane == 0) total_s = t;
+  }
+  __syncthreads();
+  const double p_dot_p = total_s;
+  const T rho_sq_t = T(1) - T(p_dot_p);
+  if (tid == 0) { ws.scal[2] = p_dot_p; ws.scal[3] = (double)rho_sq_t; }
+  if (rho_sq_t <= T(0)) {
+    for (int i = tid; i < n; i += NT) v[i] = (T)ws.p[i];
+    if (tid == 0) *status = CHUB_STATUS_NOT_PD;
+    return;
+  }
+  const double rho_sq = (double)rho_sq_t;
+  // pass 2: blocks of 1024 elements from the end; carry = sum of p_j^2 over all later blocks
+  double carry = 0.0;
+  int k = (nch - 1) * NT + tid;
+  double pk = k < n ? ws.p[k] : 0.0, dgk = k < n ? ws.dg[k] : 1.0;
+  for (int c = nch - 1; c >= 0; --c) {
+    const int kn = k - NT;
+    const double pn = (c > 0) ? ws.p[kn] : 0.0, dgn = (c > 0) ? ws.dg[kn] : 1.0;  // next block, in flight
+    const double x = pk * pk;
+    double suf = x;  // inclusive suffix sum within the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double y = __shfl_down_sync(0xffffffffu, suf, o);
+      if (lane + o < 32) suf += y;
+    }
+    __syncthreads();  // (wsum / wabove of the previous block have been read)
+    if (lane == 0) wsum[warp] = suf;
+    __syncthreads();
+    if (warp == 0) {
+      const double t = wsum[lane];
+      double s2 = t;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_down_sync(0xffffffffu, s2, o);
+        if (lane + o < 32) s2 += y;
+      }
+      wabove[lane] = s2 - t;  // warps strictly above
+      if (lane == 0) total_s = s2;
+    }
+    __syncthreads();
+    const double after = carry + wabove[warp] + (suf - x);  // sum_{j > k} p_j^2
+    if (k < n) {
+      const double qk1 = sqrt(rho_sq + after);
+      const double qk = sqrt(rho_sq + (after + x));
+      const double cc = qk1 / qk, ss = pk / qk;
+      ws.c[k] = cc;
+      ws.sg[k] = ss;
+      ws.dn[k] = dgk < 0.0 ? -1.0 : 1.0;
+      v[k] = rotg_z<T>(T(qk1), T(pk), T(cc), T(ss));
+    }
+    carry += total_s;
+    k = kn; pk = pn; dgk = dgn;
+  }
+}
+
 template <typename T, int LAYOUT>
 __global__ void __launch_bounds__(1024) large_dd_coef_kernel(const T *L, int n, int64_t ld, T *v,
                                                              LargeWs ws, int32_t *status) {
