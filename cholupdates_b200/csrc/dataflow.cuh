@@ -2515,15 +2515,20 @@ int launch_blocked_rm(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeW
   int sms = 0, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // block sizes: as many full blocks as fit, the remainder split evenly over the last two if it is small
+  // block sizes: the fewest blocks that fit one launch each, all about the same size (a multiple of 32).  (A full
+  // block followed by a short remainder leaves the rectangle kernel a few hundred row groups walking 16384 columns
+  // each: 2.4 TB/s at n = 20000, profiles/r02_ncu_launch_list_n20000.csv.)
   int64_t sizes[64];
-  int nblk = 0;
-  for (int64_t left = n; left > 0;) {
-    int64_t take = left <= kBlockedMax ? left : kBlockedMax;
-    if (left > kBlockedMax && left - kBlockedMax < 2048) take = ((left / 2 + kPanel - 1) / kPanel) * kPanel;
-    if (nblk >= 64) return (int)cudaErrorNotSupported;
-    sizes[nblk++] = take;
-    left -= take;
+  const int64_t nblk64 = (n + kBlockedMax - 1) / kBlockedMax;
+  if (nblk64 > 64) return (int)cudaErrorNotSupported;
+  const int nblk = (int)nblk64;
+  {
+    const int64_t each = ((n + nblk - 1) / nblk + kPanel - 1) / kPanel * kPanel;
+    int64_t left = n;
+    for (int J = 0; J < nblk; ++J) {
+      sizes[J] = J + 1 < nblk ? std::min(each, left) : left;
+      left -= sizes[J];
+    }
   }
   blocked_init_kernel<T, CHUB_ROW_MAJOR><<<(ni + 255) / 256, 256, 0, st>>>(L, ni, ld, v, ws, flags, status);
   ++*launches;

@@ -708,3 +708,39 @@ def test_device_generators():
     assert 0.2 <= float(p @ p) <= 0.9
     L_dd = rank_1.downdate(L, v)
     assert bool((torch.diagonal(L_dd) > 0).all())
+
+
+# ------------------------------------------------- the A/B switches of the persistent kernels stay correct
+@pytest.mark.parametrize(
+    "env",
+    [
+        {"CHUB_RM5": "0"},  # first-generation row warps
+        {"CHUB_RM5_3D": "0"},  # second generation without the 3-D tensor map (2-D boxes only)
+        {"CHUB_DD_SWEEP_V2": "1", "CHUB_DD_COEF_V1": "1"},  # first-generation downdate sweep / coefficient kernel
+        {"CHUB_DD_SWEEP_V1": "1"},  # launch-per-row-block sweep
+    ],
+)
+@pytest.mark.parametrize("n", [1022, 3000])
+def test_persistent_kernel_switches(n, env, monkeypatch):
+    """The library reads its A/B switches at call time: every variant of the row-major persistent path (and its
+    ragged right edge, n = 1022: the last 16-column block is outside the 3-D view) against the oracle."""
+    for k, val in env.items():
+        monkeypatch.setenv(k, val)
+    L = synth_factor(n, n + 7, np.float64)
+    v = np.random.default_rng(n).standard_normal(n)
+    L_ref, v_ref = _oracle("update", L, v)
+    Lt = torch.from_numpy(L.copy()).cuda()
+    Lt = Lt + torch.triu(torch.full_like(Lt, float("nan")), 1)
+    vt = torch.from_numpy(v.copy()).cuda()
+    rank_1.update(Lt, vt, check_diag=False, overwrite_L=True, overwrite_v=True)
+    got = Lt.cpu().numpy()
+    assert np.all(np.isnan(got[np.triu_indices(n, 1)]))
+    assert rel_fro(np.nan_to_num(got), L_ref) <= tol_for(np.float64, n)
+    assert rel_vec(vt.cpu().numpy(), v_ref) <= tol_for(np.float64, n)
+    vd = downdate_vector(np.tril(L_ref), n + 3)
+    L_dd, vd_ref = _oracle("downdate", np.tril(L_ref), vd)
+    Ld = torch.from_numpy(np.tril(L_ref).copy()).cuda()
+    vdt = torch.from_numpy(vd.copy()).cuda()
+    rank_1.downdate(Ld, vdt, overwrite_L=True, overwrite_v=True)
+    assert rel_fro(Ld.cpu().numpy(), L_dd) <= tol_for(np.float64, n)
+    assert rel_vec(vdt.cpu().numpy(), vd_ref) <= tol_for(np.float64, n)
