@@ -1724,6 +1724,272 @@ inline size_t df_worker_cm_smem(int nrw) {
   return 2048 + (size_t)kDfCoefRing * 4 * kPanel * 8 + (size_t)kCmStages * nrw * CmGeom<T>::TILE;
 }
 
+// ---- column-major workers, second generation: TWO warps per block row.
+// What the one-warp-per-block-row worker is bound by (gpurun r03m, n = 16384): 1400 of its 2050 cycles per step
+// are the tile arithmetic of ONE warp (32 shared-memory loads, four 8-long dependent FMA chains, 32 updates and
+// stores per lane, nothing else resident on its scheduler to hide the latencies) -- and that warp is on the
+// chain <-> worker hand-over loop.  Here warps 2q and 2q+1 share block row q's tile: warp h takes columns
+// [16 h, 16 h + 16).  The prefix products do not depend on the residual, so both halves run concurrently; the
+// four 8-column segment totals cross through shared memory (one named barrier of 64 threads), every warp then
+// forms w_i - (prefix) exactly as the one-warp kernel does (same association: bit-identical results).  Warp 2q's
+// elected lane issues all TMA loads and stores of the pair (bulk async-groups are per thread).
+// H = warps per block row: 2 (any Q <= kCmMaxQ) or 4 (Q <= kCm4MaxQ: the thread count caps the registers).
+constexpr int kCm4MaxQ = 4;
+
+template <int H> struct Cm2Stages { static constexpr int N = H == 4 ? 6 : kCmStages; };  // (H = 4: Q <= 4, room for six)
+
+template <typename T, bool UPDATE, bool PROF, int kCmH>
+__device__ void df_worker_cm2(T *L, T *v, const DfParams &P, const CUtensorMap *tmapc, unsigned char *smem) {
+  constexpr int TILE = CmGeom<T>::TILE;
+  constexpr int kCmCW = kPanel / kCmH;  // columns per warp and tile
+  constexpr int kCmSeg = kCmCW / 8;     // 8-column segments per warp
+  constexpr int NS = Cm2Stages<kCmH>::N;  // tile ring per block row; loads run NS - 2 steps ahead
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int wkr = blockIdx.x - 1;
+  const int n = P.n, T_ = P.T, Wk = P.Wk, nrw = P.nw;  // nrw = block rows (warp pairs) per worker
+  const int64_t ld = P.ld;
+  long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);      // [nrw][NS]
+  volatile int *prog = reinterpret_cast<volatile int *>(smem + 256);             // [32] steps finished per block row
+  volatile int *cprog = prog + 32;
+  volatile int *pprog = prog + 33;
+  double *coef = reinterpret_cast<double *>(smem + 2048);                        // [kDfCoefRing][4][32]
+  unsigned char *stages = smem + 2048 + kDfCoefRing * 4 * kPanel * 8;            // [nrw][NS][TILE]
+  double *xch = reinterpret_cast<double *>(stages + (size_t)nrw * NS * TILE);  // [nrw][2][4][32] segment totals
+
+  if (tid == 0) {
+    for (int i = 0; i < NS * nrw; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) prog[tid] = tid < nrw ? 0 : 0x7fffffff;
+  if (tid == 0) { *cprog = 0; *pprog = 0; }
+  __syncthreads();
+  if (warp > kCmH * nrw + 1) return;
+  if (warp == kCmH * nrw + 1) {
+    df_relay_warp<PROF>(P, coef, prog, pprog, wkr, lane, kDfD + 1);
+    return;
+  }
+  if (warp == kCmH * nrw) {
+    df_coef_warp5<T, UPDATE, PROF>(v, P, coef, cprog, pprog, wkr, lane);
+    return;
+  }
+
+  // ---------------- row warps: pair q = block row (32 rows, lane = row), h = which 16 columns of every tile
+  const int q = warp / kCmH, h = warp % kCmH;
+  const int b = wkr + q * Wk;
+  const int64_t row0 = (int64_t)b * kPanel;
+  if (row0 >= n) {  // (both warps of the pair leave: nobody is left at the pair's barrier)
+    if (lane == 0 && h == 0) prog[q] = 0x7fffffff;
+    return;
+  }
+  const int64_t row = row0 + lane;
+  const bool valid = row < n;
+  const int last_step = min(T_ + kDfD - 1, b + kDfD);
+  double w = valid ? P.ws.v0[row] : 0.0;
+  const bool prof_me = PROF && P.prof && lane == 0 && h == 0 && (q + 1 >= nrw || (int64_t)(b + Wk) * kPanel >= n);
+  unsigned long long *myfull = full + q * NS;
+  unsigned char *mytile = stages + (size_t)q * (NS * TILE);
+  double *myx = xch + (size_t)q * (2 * 4 * kPanel);
+  const int bar_id = 1 + q;
+  const int k0 = h * kCmCW;  // my first column within a tile
+  unsigned nx = 0;           // tiles processed so far (parity = exchange buffer)
+
+  auto issue_load = [&](int s) {  // elected lane of warp h = 0
+    if (s > last_step) return;
+    void *bar = &myfull[s % NS];
+    const int pan = df_panel_at<kDfD>(b, s);
+    if (pan < 0) { mbar_arrive(bar); return; }
+    mbar_arrive_expect_tx(bar, (unsigned)TILE);
+    tma_load_2d(mytile + (s % NS) * TILE, tmapc, (int)row0, pan * kPanel, bar);
+  };
+  auto wait_flag = [&](volatile int *flag, int need) {
+    if (ld_acquire_cta_smem(flag) < need) {
+      const long long t0 = clock64();
+      while (ld_acquire_cta_smem(flag) < need) {
+        if (clock64() - t0 > kWatchdogCycles) { atomicMax(P.status, CHUB_STATUS_INTERNAL); break; }
+      }
+    }
+  };
+
+  // The update of tile s is DEFERRED to step s + 1 (after that step's prefix products): (c, sigma) of a block
+  // column leave the coefficient warp ~0.6 us after its p arrives (scan + rsqrt), and a row warp that waited for
+  // them inside the step could not start the next step before then -- the wait was 40 % of the one-warp worker's
+  // step and set the kernel's period (gpurun r04b).  One step later they are always there.  The deferred update
+  // reloads its 16 entries per lane from the tile (still in its stage) and rebuilds the prefix products on the fly.
+  int dpan = -1, dstage = 0;   // the deferred tile: block column, ring stage
+  double dwq[kCmSeg];          // ... and the residual in front of each of my segments
+  auto deferred_update = [&]() {  // both warps of the pair, together (they share the barrier)
+    if (!UPDATE || dpan < 0) return;
+    wait_flag(cprog, dpan + 1);
+    T *tile = reinterpret_cast<T *>(mytile + dstage * TILE) + lane + k0 * kPanel;
+    const double *cf = coef + (size_t)(dpan % kDfCoefRing) * 4 * kPanel + k0;
+    const bool diag = (dpan == b);
+    if (!diag) {
+#pragma unroll
+      for (int g = 0; g < kCmSeg; ++g) {
+        double run = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const int k = 8 * g + j;
+          const double2 pp = *reinterpret_cast<const double2 *>(cf + k);
+          const double2 c2 = *reinterpret_cast<const double2 *>(cf + kPanel + k);
+          const double2 s2 = *reinterpret_cast<const double2 *>(cf + 2 * kPanel + k);
+          const double l0 = (double)tile[k * kPanel], l1 = (double)tile[(k + 1) * kPanel];
+          tile[k * kPanel] = (T)fma(c2.x, l0, s2.x * (dwq[g] - run));
+          run = fma(l0, pp.x, run);
+          tile[(k + 1) * kPanel] = (T)fma(c2.y, l1, s2.y * (dwq[g] - run));
+          run = fma(l1, pp.y, run);
+        }
+      }
+      fence_proxy_async();  // my generic-proxy writes -> visible to the TMA (async proxy) store
+    } else if (valid) {  // ragged diagonal tile: straight to global memory, nothing above the diagonal
+      T *gp = L + row + (int64_t)(row0 + k0) * ld;  // (row, row0 + k0 + k) at gp[k * ld]
+#pragma unroll
+      for (int g = 0; g < kCmSeg; ++g) {
+        double run = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = 8 * g + j;
+          const double l0 = (double)tile[k * kPanel];
+          if (k0 + k < lane) {
+            gp[(int64_t)k * ld] = (T)fma(cf[kPanel + k], l0, cf[2 * kPanel + k] * (dwq[g] - run));
+            run = fma(l0, cf[k], run);
+          } else if (k0 + k == lane) {
+            gp[(int64_t)k * ld] = (T)cf[3 * kPanel + k];
+          }
+        }
+      }
+    }
+    named_sync(bar_id, 32 * kCmH);  // the other warp's tile writes and coefficient reads are complete too
+    if (h == 0 && elect_one()) {
+      if (!diag) tma_store_2d(tmapc, (int)row0, dpan * kPanel, mytile + dstage * TILE);
+      bulk_commit();
+    }
+    __syncwarp();
+    dpan = -1;
+  };
+
+  if (h == 0 && elect_one()) {
+    for (int s = 0; s < NS - 2; ++s) issue_load(s);
+  }
+  __syncwarp();
+  const long long t_wk0 = DF_PROF_T();
+  for (int s = 0; s <= last_step; ++s) {
+    long long tp = DF_PROF_T();
+    mbar_wait(&myfull[s % NS], (unsigned)((s / NS) & 1), P.status);
+    if (prof_me) DF_PROF_ADD(1, tp);
+    tp = DF_PROF_T();
+    // step s is gated on p_s: p_s published implies that the chain has consumed everything step s overwrites
+    wait_flag(pprog, min(s, T_ - 1) + 1);
+    if (prof_me) DF_PROF_ADD(4, tp);
+    tp = DF_PROF_T();
+    const int pan = df_panel_at<kDfD>(b, s);  // (the same for both warps of the pair: they take the same barriers)
+    int npan = -1;
+    double nwq[kCmSeg];
+    if (pan >= 0) {
+      const T *tile = reinterpret_cast<const T *>(mytile + (s % NS) * TILE) + lane + k0 * kPanel;  // (lane, k0 + k) at tile[k * 32]
+      const double *cf = coef + (size_t)(pan % kDfCoefRing) * 4 * kPanel + k0;
+      const bool diag = (pan == b);  // columns c0 + k, c0 = row0: k < lane below, k == lane on the diagonal
+      double lo[kCmCW];
+      double *xs = myx + (nx++ & 1) * (4 * kPanel) + lane;  // segment g's total of this row at xs[g * 32] (two buffers:
+      // a warp may write step s+1's totals while the other one still reads step s's)
+#pragma unroll
+      for (int k = 0; k < kCmCW; ++k) lo[k] = (double)tile[k * kPanel];
+#pragma unroll
+      for (int g = 0; g < kCmSeg; ++g) {
+        double run = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const int k = 8 * g + j;
+          const double2 pp = *reinterpret_cast<const double2 *>(cf + k);
+          if (!diag || k0 + k < lane) run = fma(lo[k], pp.x, run);
+          if (!diag || k0 + k + 1 < lane) run = fma(lo[k + 1], pp.y, run);
+        }
+        xs[(h * kCmSeg + g) * kPanel] = run;
+      }
+      named_sync(bar_id, 32 * kCmH);
+      double wq[4];
+      wq[0] = w;
+      wq[1] = wq[0] - xs[0];
+      wq[2] = wq[1] - xs[kPanel];
+      wq[3] = wq[2] - xs[2 * kPanel];
+      w = wq[3] - xs[3 * kPanel];
+      // hand the residual over to the chain after the last far-left block column
+      if (s == b - kDfD - 1 && valid && h == 0) {
+        st_relaxed_f64(P.ws.w + row, df_sanitize(w));
+        if (lane == 0) DF_TRACE(0, b);
+      }
+#pragma unroll
+      for (int g = 0; g < kCmSeg; ++g) {  // nwq[g] = wq[h * kCmSeg + g], as selects (no local array)
+        if (kCmH == 2) nwq[g] = h == 0 ? wq[g] : wq[kCmSeg + g];
+        else nwq[g] = h < 2 ? (h == 0 ? wq[0] : wq[1]) : (h == 2 ? wq[2] : wq[3]);
+      }
+      npan = pan;
+    }
+    if (prof_me) DF_PROF_ADD(3, tp);
+    tp = DF_PROF_T();
+    if (UPDATE) {
+      if (h == 0 && elect_one()) {
+        // tile s+2 goes into the stage of tile s-2, whose store was committed one step ago
+        bulk_wait_read<0>();
+        issue_load(s + NS - 2);
+      }
+      __syncwarp();
+      if (prof_me) DF_PROF_ADD(2, tp);
+      tp = DF_PROF_T();
+      deferred_update();  // tile s-1
+      if (h == 0 && lane == 0) prog[q] = s;  // steps < s: all coefficient reads done (ring-slot reuse)
+      if (npan >= 0) {
+        dpan = npan;
+        dstage = s % NS;
+#pragma unroll
+        for (int g = 0; g < kCmSeg; ++g) dwq[g] = nwq[g];
+      }
+    } else {
+      // forward substitution only: nothing is written; both warps' reads of p_s are behind the barrier above
+      if (h == 0 && elect_one()) {
+        prog[q] = s >= last_step ? 0x7fffffff : s + 1;
+        issue_load(s + NS - 2);
+      }
+      __syncwarp();
+    }
+    if (prof_me) DF_PROF_ADD(5, tp);
+  }
+  deferred_update();  // the last tile (the diagonal one)
+  if (UPDATE && h == 0 && lane == 0) prog[q] = 0x7fffffff;
+  if (prof_me) DF_PROF_ADD(0, t_wk0);
+  if (h == 0 && elect_one()) bulk_wait_all<0>();
+  if (prof_me) {
+    for (int i = 0; i < 6; ++i) P.prof[(size_t)blockIdx.x * 16 + i] = pacc[i];
+  }
+}
+
+template <typename T>
+inline size_t df_worker_cm2_smem(int nrw, int H) {
+  const int ns = H == 4 ? Cm2Stages<4>::N : Cm2Stages<2>::N;
+  return 2048 + (size_t)kDfCoefRing * 4 * kPanel * 8 + (size_t)ns * nrw * CmGeom<T>::TILE + (size_t)nrw * 2 * 4 * kPanel * 8;
+}
+
+template <int H> struct Cm2Threads {  // row warps + coefficient + relay warp
+  static constexpr int MAX = 32 * (H * (H == 2 ? kCmMaxQ : kCm4MaxQ) + 2);
+};
+
+template <typename T, bool UPDATE, bool PROF, int H>
+__global__ void __launch_bounds__(Cm2Threads<H>::MAX, 1)
+df_kernel_cm2(T *L, T *v, DfParams P, const __grid_constant__ CUtensorMap tmapc,
+              const __grid_constant__ CUtensorMap tmapcb) {
+  extern __shared__ __align__(1024) unsigned char df_smem[];
+  if (*P.status != 0) return;  // check_diag failed: L and v stay untouched
+  if (blockIdx.x == 0) {
+    // (split poll / TMA warps, as in the row-major kernel: these workers leave the registers for 288 chain threads)
+    if (threadIdx.x < kC6ThreadsSplit) df_chain_v6<T, CHUB_COL_MAJOR, PROF, false>(P, &tmapcb, df_smem);
+  } else {
+    df_worker_cm2<T, UPDATE, PROF, H>(L, v, P, &tmapc, df_smem);
+  }
+}
+
 constexpr int kCmMaxThreads = kC6ThreadsMerged > 256 ? kC6ThreadsMerged : 256;  // chain: v6 warp roles; workers: kCmMaxQ row warps + coefficient + relay warp
 
 template <typename T, bool UPDATE, bool PROF>
@@ -2329,7 +2595,7 @@ inline CmPlan cm_plan(int64_t n, int64_t ld, const void *L) {
   const int64_t nRB = (n + kPanel - 1) / kPanel;
   const int Q = (int)((nRB + Wk - 1) / Wk);
   if (Q > kCmMaxQ) return pl;
-  const size_t smem = std::max(std::max(df_chain_rm_smem<T>(), df_chain_v6_smem<T>()), df_worker_cm_smem<T>(Q));
+  const size_t smem = std::max(std::max(df_chain_rm_smem<T>(), df_chain_v6_smem<T>()), df_worker_cm2_smem<T>(Q, Q <= kCm4MaxQ ? 4 : 2));
   if (smem > (size_t)smem_optin) return pl;
   pl.ok = true; pl.sms = sms; pl.Wk = Wk; pl.Q = Q; pl.smem = smem;
   return pl;
@@ -2439,11 +2705,18 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
     e = cudaLaunchCooperativeKernel((void *)kern, dim3(rp.sms), dim3(rp.threads), args, rp.smem, st);
   } else if (cp.ok) {
     P.R = 32; P.r_shift = 5; P.Wk = cp.Wk; P.rows_max = cp.Q * 32; P.nw = cp.Q;
-    auto kern = P.prof ? df_kernel_cm<T, UPDATE, true> : df_kernel_cm<T, UPDATE, false>;
+    const char *ep = getenv("CHUB_CM_PAIR");
+    // warps per block row: 4 where the thread count allows, else 2 (df_worker_cm2); 0 / 1: one (df_worker_cm, A/B)
+    int H = cp.Q <= kCm4MaxQ ? 4 : 2;
+    if (ep) H = ep[0] == '4' ? (cp.Q <= kCm4MaxQ ? 4 : 2) : ep[0] == '2' ? 2 : 1;
+    auto kern = H == 4   ? (P.prof ? df_kernel_cm2<T, UPDATE, true, 4> : df_kernel_cm2<T, UPDATE, false, 4>)
+                : H == 2 ? (P.prof ? df_kernel_cm2<T, UPDATE, true, 2> : df_kernel_cm2<T, UPDATE, false, 2>)
+                         : (P.prof ? df_kernel_cm<T, UPDATE, true> : df_kernel_cm<T, UPDATE, false>);
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.smem);
     if (e != cudaSuccess) return (int)e;
     void *args[] = {(void *)&L, (void *)&v, (void *)&P, (void *)&tmapc, (void *)&tmapcb};
-    e = cudaLaunchCooperativeKernel((void *)kern, dim3(cp.sms), dim3(kCmMaxThreads), args, cp.smem, st);
+    const int threads = H > 1 ? std::max(kC6ThreadsSplit, 32 * (H * cp.Q + 2)) : kCmMaxThreads;
+    e = cudaLaunchCooperativeKernel((void *)kern, dim3(cp.sms), dim3(threads), args, cp.smem, st);
   } else {
     P.R = pl.R; P.r_shift = pl.r_shift; P.Wk = pl.Wk; P.rows_max = pl.rows_max; P.nw = pl.nw;
     auto kern = df_kernel_v2<T, LAYOUT, UPDATE>;
