@@ -7,7 +7,11 @@
 // triangle of the host array is never modified.
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
 #include <cstdio>
+#include <functional>
 #include <cstdlib>
 #include <condition_variable>
 #include <cstring>
@@ -15,6 +19,9 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "large.cuh"
 
@@ -36,6 +43,10 @@ struct HostCache {
   void *bin[2] = {nullptr, nullptr}, *bout[2] = {nullptr, nullptr};
   size_t b_bytes = 0;
   cudaEvent_t ev_bin[2] = {nullptr, nullptr}, ev_bout[2] = {nullptr, nullptr};
+  // staged path (run_host_staged): one pinned staging buffer holding the packed triangle blocks, one event per block
+  void *stage = nullptr;
+  size_t stage_bytes = 0;
+  std::vector<cudaEvent_t> ev_blk;
 };
 std::mutex h_mu[64];  // one per device: host calls on different devices of a process do not serialise
 HostCache h_cache[64];
@@ -199,6 +210,7 @@ struct Unpacker {
 // touches its own 256 columns (plus the n-vector w), so a panel can be finished and shipped back as
 // soon as it has arrived; PCIe runs full duplex and the update costs about one H2D of the triangle.
 constexpr int64_t kStreamMinN = 2048;
+constexpr int64_t kStreamPinnedMinN = 4096;  // pinned caller memory: streamed from here on (else staged)
 constexpr int64_t kXferCols = 512;  // columns per host <-> device transfer panel (measured: 256 24.7 ms, 512 24.0, 1024 27.7 at n = 16384)
 
 template <typename T, int LAYOUT>
@@ -312,6 +324,257 @@ int run_host_update_streamed(HostCache &c, const T *Lh, int64_t ld, T *Lo, int64
 
 typedef int (*dev_fn)(void *, int64_t, int64_t, int, void *, int, void *, size_t, int32_t *, void *);
 
+// One row of a block, with non-temporal stores: the destination (staging buffer on the way in, the caller's array
+// on the way out) is not read again by this core, and a regular store would first read the line it overwrites
+// (3 bytes of memory traffic per byte copied instead of 2 -- host memory bandwidth is what bounds pageable callers).
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void copy_stream_avx2(char *dst, const char *src, size_t bytes) {
+  size_t head = (32 - (reinterpret_cast<uintptr_t>(dst) & 31)) & 31;
+  if (head > bytes) head = bytes;
+  if (head) { memcpy(dst, src, head); dst += head; src += head; bytes -= head; }
+  size_t i = 0;
+  for (; i + 128 <= bytes; i += 128) {
+    const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
+    const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 32));
+    const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 64));
+    const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 96));
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), a);
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 32), b);
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 64), c);
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 96), d);
+  }
+  for (; i + 32 <= bytes; i += 32)
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i)));
+  if (i < bytes) memcpy(dst + i, src + i, bytes - i);
+  _mm_sfence();
+}
+#endif
+void copy_stream(char *dst, const char *src, size_t bytes) {
+#if defined(__x86_64__)
+  static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("CHUB_HOST_NO_NT");
+  if (avx2 && bytes >= 256) { copy_stream_avx2(dst, src, bytes); return; }
+#endif
+  memcpy(dst, src, bytes);
+}
+
+// ---- persistent host thread pool (staged path).  Spawning threads per call costs more than a whole n = 1000
+// update; the workers spin for a short while after their last task (a caller updating in a loop finds them hot)
+// and then sleep on a condition variable.
+class HostPool {
+ public:
+  static HostPool &get() {
+    static HostPool *p = new HostPool(host_threads());  // (leaked on purpose: no destructor race at process exit)
+    return *p;
+  }
+  void submit(std::function<void()> f) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      q_.push_back(std::move(f));
+      pending_.fetch_add(1, std::memory_order_release);
+    }
+    if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_one();
+  }
+  int size() const { return (int)th_.size(); }
+
+ private:
+  explicit HostPool(int n) {
+    for (int t = 0; t < n; ++t) th_.emplace_back([this] { run(); });
+    for (auto &x : th_) x.detach();
+  }
+  void run() {
+    for (;;) {
+      std::function<void()> f;
+      if (pending_.load(std::memory_order_acquire) > 0) {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!q_.empty()) {
+          f = std::move(q_.front());
+          q_.pop_front();
+          pending_.fetch_sub(1, std::memory_order_relaxed);
+        }
+      }
+      if (f) { f(); continue; }
+      // nothing to do: spin ~200 us, then sleep
+      const auto t0 = std::chrono::steady_clock::now();
+      bool got = false;
+      while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(200)) {
+        if (pending_.load(std::memory_order_acquire) > 0) { got = true; break; }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+      if (got) continue;
+      std::unique_lock<std::mutex> lk(mu_);
+      sleepers_.fetch_add(1, std::memory_order_release);
+      cv_.wait(lk, [this] { return !q_.empty(); });
+      sleepers_.fetch_sub(1, std::memory_order_release);
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::function<void()>> q_;
+  std::atomic<int> pending_{0}, sleepers_{0};
+  std::vector<std::thread> th_;
+};
+
+// ---- staged path: any operation, any size, pageable or pinned caller memory.
+// The lower triangle is cut into K blocks of about equal area (row blocks that end at the diagonal for row-major,
+// column blocks that start at it for column-major).  Pool threads pack block b from the caller's (strided,
+// pageable) array into a pinned staging buffer; the calling thread issues block b's DMA as soon as it is packed,
+// so packing and PCIe overlap.  Then the device-resident kernels (the same entry points a CUDA-tensor caller
+// reaches), then the way back: all K device -> staging copies are queued at once, pool threads scatter block b
+// into the caller's array as soon as its copy has landed.  Nothing above the diagonal blocks' own little
+// triangles crosses PCIe; pinned caller memory skips the staging buffer.
+struct TriBlock { int64_t b0, b1; size_t off_h, off_o, off_d, width, height, stage_off; };
+
+int run_host_staged(HostCache &c, dev_fn fn, size_t es, const void *L, int64_t ld, void *Lo, int64_t ldo, int64_t n,
+                    int layout, void *v, int flags, int32_t *status) {
+  HostPool &pool = HostPool::get();
+  const size_t tri_bytes = (size_t)n * (size_t)(n + 1) / 2 * es;
+  int K = (int)std::min<size_t>((size_t)8 * pool.size(), std::max<size_t>(1, tri_bytes / (256u << 10)));
+  if (const char *e = getenv("CHUB_HOST_BLOCKS")) K = std::max(1, atoi(e));
+  K = (int)std::min<int64_t>(K, (n + 31) / 32);
+  std::vector<TriBlock> blk;
+  size_t stage_need = 0;
+  {
+    int64_t prev = 0;
+    for (int b = 1; b <= K && prev < n; ++b) {
+      const double f = (double)b / K;
+      int64_t cut = layout == CHUB_ROW_MAJOR ? (int64_t)std::llround(n * std::sqrt(f))
+                                             : (int64_t)std::llround(n * (1.0 - std::sqrt(1.0 - f)));
+      cut = b == K ? n : std::min<int64_t>(n, (cut + 31) / 32 * 32);
+      if (cut <= prev) continue;
+      TriBlock t;
+      t.b0 = prev; t.b1 = cut;
+      if (layout == CHUB_ROW_MAJOR) {  // rows [b0, b1) x columns [0, b1)
+        t.off_h = (size_t)prev * ld; t.off_o = (size_t)prev * ldo; t.off_d = (size_t)prev * n;
+        t.width = (size_t)cut * es; t.height = (size_t)(cut - prev);
+      } else {                         // columns [b0, b1) x rows [b0, n)
+        t.off_h = (size_t)prev * ld + prev; t.off_o = (size_t)prev * ldo + prev; t.off_d = (size_t)prev * n + prev;
+        t.width = (size_t)(n - prev) * es; t.height = (size_t)(cut - prev);
+      }
+      t.stage_off = stage_need;
+      stage_need += (t.width * t.height + 255) / 256 * 256;
+      blk.push_back(t);
+      prev = cut;
+    }
+  }
+  const int nb = (int)blk.size();
+  const bool pin_in = is_pinned(L), pin_out = is_pinned(Lo);
+  if (!pin_in || !pin_out) {
+    if (c.stage_bytes < stage_need) {
+      if (c.stage) cudaFreeHost(c.stage);
+      c.stage = nullptr; c.stage_bytes = 0;
+      HCK(cudaHostAlloc(&c.stage, stage_need + stage_need / 8, cudaHostAllocDefault));
+      c.stage_bytes = stage_need + stage_need / 8;
+    }
+  }
+  while ((int)c.ev_blk.size() < nb) {
+    cudaEvent_t e;
+    HCK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c.ev_blk.push_back(e);
+  }
+  char *stage = (char *)c.stage;
+  char *Ld = (char *)c.L;
+  auto copy_rows = [](char *dst, size_t dpitch, const char *src, size_t spitch, size_t width, size_t height) {
+    for (size_t r = 0; r < height; ++r) copy_stream(dst + r * dpitch, src + r * spitch, width);
+  };
+
+  // ---- way in
+  HCK(cudaMemcpyAsync(c.v, v, (size_t)n * es, cudaMemcpyHostToDevice, c.st));
+  if (pin_in) {
+    for (const TriBlock &t : blk)
+      HCK(cudaMemcpy2DAsync(Ld + t.off_d * es, (size_t)n * es, (const char *)L + t.off_h * es, (size_t)ld * es, t.width,
+                            t.height, cudaMemcpyHostToDevice, c.st));
+  } else {
+    std::vector<std::atomic<int>> packed(nb);
+    for (auto &x : packed) x.store(0, std::memory_order_relaxed);
+    const char *Lh = (const char *)L;
+    for (int b = 1; b < nb; ++b) {  // (block 0 is packed by this thread: no hand-over latency for tiny factors)
+      const TriBlock t = blk[b];
+      std::atomic<int> *flag = &packed[b];
+      pool.submit([=] {
+        copy_rows(stage + t.stage_off, t.width, Lh + t.off_h * es, (size_t)ld * es, t.width, t.height);
+        flag->store(1, std::memory_order_release);
+      });
+    }
+    copy_rows(stage + blk[0].stage_off, blk[0].width, Lh + blk[0].off_h * es, (size_t)ld * es, blk[0].width, blk[0].height);
+    packed[0].store(1, std::memory_order_release);
+    cudaError_t err = cudaSuccess;
+    for (int b = 0; b < nb; ++b) {
+      while (packed[b].load(std::memory_order_acquire) == 0) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+      // (every task is waited for even after an error: the tasks reference this frame)
+      if (err == cudaSuccess)
+        err = cudaMemcpy2DAsync(Ld + blk[b].off_d * es, (size_t)n * es, stage + blk[b].stage_off, blk[b].width,
+                                blk[b].width, blk[b].height, cudaMemcpyHostToDevice, c.st);
+    }
+    HCK(err);
+  }
+
+  // ---- the update / downdate, device resident
+  int rc = fn(c.L, n, n, layout, c.v, flags, nullptr, 0, c.status, c.st);
+  if (rc) {
+    cudaDeviceSynchronize();  // (the message is already in chub_last_error())
+    return rc;
+  }
+  HCK(cudaMemcpyAsync(status, c.status, sizeof(int32_t), cudaMemcpyDeviceToHost, c.st));
+
+  // ---- way out.  Into the staging buffer the copies start at once (nothing reaches the caller's array before the
+  // status is known); straight into pinned caller memory only after the status has been read.
+  if (!pin_out) {
+    for (int b = 0; b < nb; ++b) {
+      HCK(cudaMemcpy2DAsync(stage + blk[b].stage_off, blk[b].width, Ld + blk[b].off_d * es, (size_t)n * es, blk[b].width,
+                            blk[b].height, cudaMemcpyDeviceToHost, c.st));
+      HCK(cudaEventRecord(c.ev_blk[b], c.st));
+    }
+  }
+  if (!pin_out) HCK(cudaEventSynchronize(c.ev_blk[0]));
+  else HCK(cudaStreamSynchronize(c.st));
+  // (status was queued before the first block: it is there once block 0 has landed / the stream is idle)
+  if (*status == CHUB_STATUS_ZERO_DIAG) { HCK(cudaStreamSynchronize(c.st)); return 0; }  // L and v untouched
+  if (*status != CHUB_STATUS_OK) {  // not positive definite: v holds p, L stays as it was
+    HCK(cudaMemcpyAsync(v, c.v, (size_t)n * es, cudaMemcpyDeviceToHost, c.st));
+    HCK(cudaStreamSynchronize(c.st));
+    return 0;
+  }
+  HCK(cudaMemcpyAsync(v, c.v, (size_t)n * es, cudaMemcpyDeviceToHost, c.st));
+  if (pin_out) {
+    for (const TriBlock &t : blk)
+      HCK(cudaMemcpy2DAsync((char *)Lo + t.off_o * es, (size_t)ldo * es, Ld + t.off_d * es, (size_t)n * es, t.width,
+                            t.height, cudaMemcpyDeviceToHost, c.st));
+    HCK(cudaStreamSynchronize(c.st));
+    return 0;
+  }
+  {
+    std::atomic<int> left{nb - 1};
+    std::atomic<int> bad{0};
+    char *Loh = (char *)Lo;
+    for (int b = 1; b < nb; ++b) {
+      const TriBlock t = blk[b];
+      cudaEvent_t ev = c.ev_blk[b];
+      std::atomic<int> *lp = &left, *bp = &bad;
+      pool.submit([=] {
+        if (cudaEventSynchronize(ev) != cudaSuccess) bp->store(1);
+        else copy_rows(Loh + t.off_o * es, (size_t)ldo * es, stage + t.stage_off, t.width, t.width, t.height);
+        lp->fetch_sub(1, std::memory_order_release);
+      });
+    }
+    copy_rows(Loh + blk[0].off_o * es, (size_t)ldo * es, stage + blk[0].stage_off, blk[0].width, blk[0].width, blk[0].height);
+    while (left.load(std::memory_order_acquire) > 0) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    HCK(cudaStreamSynchronize(c.st));
+    if (bad.load()) HCK(cudaErrorUnknown);
+  }
+  return 0;
+}
+
+
 // Strict upper triangle src -> dst on the host (copy mode: the reference returns a full copy of L,
 // _seeger.py:272-273, so whatever sits above the diagonal travels along -- on the host, never over PCIe).
 void copy_upper_host(char *dst, int64_t ldd, const char *src, int64_t lds, int64_t n, int layout, size_t es,
@@ -363,7 +626,17 @@ int run_host(dev_fn fn, bool is_update, size_t es, const void *L, int64_t ld, vo
     std::vector<std::thread> &t;
     ~Joiner() { for (auto &x : t) if (x.joinable()) x.join(); }
   } joiner{uppers};
-  if (is_update && n >= kStreamMinN && !getenv("CHUB_HOST_NO_STREAM")) {
+  // Which path: the streamed update overlaps the two PCIe directions (about ONE triangle transfer per update) but
+  // runs the launch-per-panel kernels and wants pinned memory; the staged path takes anything and uses the
+  // persistent kernels.  CHUB_HOST_PATH = streamed | staged | direct overrides (direct: plain 2-D copies, A/B).
+  const char *hp = getenv("CHUB_HOST_PATH");
+  bool streamed = is_update && n >= kStreamPinnedMinN && is_pinned(L) && is_pinned(Lo);
+  if (hp && !strcmp(hp, "streamed")) streamed = is_update && n >= kStreamMinN;
+  if (hp && (!strcmp(hp, "staged") || !strcmp(hp, "direct"))) streamed = false;
+  if (getenv("CHUB_HOST_NO_STREAM")) streamed = false;
+  if (!streamed && !(hp && !strcmp(hp, "direct")))
+    return run_host_staged(c, fn, es, L, ld, Lo, ldo, n, layout, v, flags, status);
+  if (streamed) {
     if (es == 8)
       return layout == CHUB_ROW_MAJOR
                  ? run_host_update_streamed<double, CHUB_ROW_MAJOR>(c, (const double *)L, ld, (double *)Lo, ldo, n, (double *)v, status)
@@ -443,6 +716,9 @@ int chub_host_release(void) {
     c.bin[k] = c.bout[k] = nullptr;
   }
   c.b_bytes = 0;
+  if (c.stage) cudaFreeHost(c.stage);
+  c.stage = nullptr;
+  c.stage_bytes = 0;
   return 0;
 }
 
