@@ -151,8 +151,7 @@ int run_single(void *Lv, int64_t n, int64_t ld, int layout, void *vv, int flags,
   if (path == 1 && n > kSmallMaxN) path = 2;
   // (row-major beyond the persistent kernel's capacity: blocked driver; column-major shapes the native
   // kernel does not take: row-major scratch -- both decided below)
-  if (path == 3 && !dataflow_supported<T>(n, ld, layout, L) &&
-      !(layout == CHUB_ROW_MAJOR && blocked_supported<T>(n, ld, L)) &&
+  if (path == 3 && !dataflow_supported<T>(n, ld, layout, L) && !blocked_supported<T>(n, ld, L, layout) &&
       !(layout == CHUB_COL_MAJOR && n > kSmallFallback))
     path = (g_path.load() == 0 && n <= kSmallFallback) ? 1 : 2;
   if (path == 1) return launch_small<T, UPDATE>(L, n, ld, 0, layout, v, 0, 1, flags, status, st);
@@ -166,10 +165,13 @@ int run_single(void *Lv, int64_t n, int64_t ld, int layout, void *vv, int flags,
     return (int)cudaErrorInvalidValue;
   }
   LargeWs ws = large_ws_carve(workspace, n);
-  if (path == 3 && layout == CHUB_ROW_MAJOR && blocked_supported<T>(n, ld, L)) {
-    // beyond the persistent kernel's row capacity: diagonal blocks + rectangles (launch_blocked_rm)
+  if (path == 3 && blocked_supported<T>(n, ld, L, layout) &&
+      (layout == CHUB_ROW_MAJOR || !dataflow_native<T>(n, ld, layout, L))) {
+    // beyond the persistent kernel's row capacity (row-major: one launch takes n <= 16464; column-major: the
+    // two-warp workers take n <= 28224): diagonal blocks + rectangles (launch_blocked)
     int64_t nl = 0;
-    int rc = launch_blocked_rm<T, UPDATE>(L, n, ld, v, flags, ws, status, st, &nl);
+    int rc = layout == CHUB_ROW_MAJOR ? launch_blocked<T, CHUB_ROW_MAJOR, UPDATE>(L, n, ld, v, flags, ws, status, st, &nl)
+                                      : launch_blocked<T, CHUB_COL_MAJOR, UPDATE>(L, n, ld, v, flags, ws, status, st, &nl);
     g_launches.fetch_add(nl, std::memory_order_relaxed);
     if (rc == 0) return 0;
     return fail((cudaError_t)rc, "blocked dataflow launch");
@@ -204,7 +206,7 @@ int run_single(void *Lv, int64_t n, int64_t ld, int layout, void *vv, int flags,
       LAUNCHED();
       int64_t nl = 0;
       int rc = blocked_supported<T>(n, ldr, tmp)
-                   ? launch_blocked_rm<T, UPDATE>(tmp, n, ldr, v, flags, ws, status, st, &nl)
+                   ? launch_blocked<T, CHUB_ROW_MAJOR, UPDATE>(tmp, n, ldr, v, flags, ws, status, st, &nl)
                    : launch_dataflow<T, CHUB_ROW_MAJOR, UPDATE>(tmp, n, ldr, v, flags, ws, status, st, &nl);
       g_launches.fetch_add(nl, std::memory_order_relaxed);
       if (rc == 0) {

@@ -2107,6 +2107,109 @@ __global__ void __launch_bounds__(128) dd_sweep_cm_kernel(T *L, int n, int64_t l
 template <typename T>
 inline size_t dd_sweep_cm_smem() { return 1024 + (size_t)4 * kSwCmStages * SwCmGeom<T>::STAGE; }
 
+// ---- rectangle below a diagonal block, column-major (blocked driver for factors beyond the persistent kernel's
+// row capacity; the column-major twin of rect_apply_rm_kernel).  A warp takes a block row of 32 rows (lane = row)
+// and walks the diagonal block's columns in [32 rows x 32 columns] TMA boxes through a ring, the block column's
+// (p, c, sigma) riding along; nothing here waits for anybody, so the row's residual chain stays a plain
+// sequential FMA chain per lane (six warps per SM hide it: the kernel is a pure stream).
+//     L_ik <- c_k L_ik + sigma_k w_i ,   w_i <- w_i - L_ik p_k
+// UPDATE = false: residual only (forward substitution of the downdate).
+constexpr int kRectCmStages = 4;
+constexpr int kRectCmWarps = 6;
+
+template <typename T>
+struct RectCmGeom {
+  static constexpr int STAGE = CmGeom<T>::TILE + 1024;  // tile + (p, c, sigma)[32] doubles (768 B, padded)
+};
+
+template <typename T, bool UPDATE>
+__global__ void __launch_bounds__(kRectCmWarps * 32, 1)
+rect_apply_cm_kernel(int n, int row_begin, int col_begin, int ncols, LargeWs ws, const int32_t *status,
+                     const __grid_constant__ CUtensorMap tmapc) {
+  constexpr int TILE = CmGeom<T>::TILE, STAGE = RectCmGeom<T>::STAGE;
+  extern __shared__ __align__(1024) unsigned char rcm_smem[];
+  if (*status != 0) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(rcm_smem) + warp * kRectCmStages;
+  unsigned char *mystage = rcm_smem + 1024 + (size_t)warp * kRectCmStages * STAGE;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRectCmWarps * kRectCmStages; ++i) mbar_init(reinterpret_cast<unsigned long long *>(rcm_smem) + i, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int nsteps = ncols / kPanel;
+  const int ngroups = (n - row_begin + kPanel - 1) / kPanel;
+  unsigned it = 0;  // tiles this warp has consumed so far (ring position / mbarrier phase)
+  for (int grp = (int)blockIdx.x * kRectCmWarps + warp; grp < ngroups; grp += (int)gridDim.x * kRectCmWarps) {
+    const int row0 = row_begin + grp * kPanel;
+    const int row = row0 + lane;
+    double w = row < n ? ws.w[row] : 0.0;
+
+    auto issue_load = [&](int s) {  // elected lane; stage / phase follow the warp's running tile count
+      if (s >= nsteps) return;
+      const unsigned st = (it + (unsigned)s) % kRectCmStages;
+      void *bar = &full[st];
+      unsigned char *stg = mystage + (size_t)st * STAGE;
+      const int c0 = col_begin + s * kPanel;
+      mbar_arrive_expect_tx(bar, (unsigned)TILE + (UPDATE ? 768u : 256u));
+      tma_load_2d(stg, &tmapc, row0, c0, bar);
+      bulk_g2s(stg + TILE, ws.p + c0, 256u, bar);
+      if (UPDATE) {
+        bulk_g2s(stg + TILE + 256, ws.c + c0, 256u, bar);
+        bulk_g2s(stg + TILE + 512, ws.sg + c0, 256u, bar);
+      }
+    };
+
+    if (elect_one()) {
+      bulk_wait_read<0>();  // (the previous group's last stores have left their stages)
+      for (int s = 0; s < kRectCmStages - 1; ++s) issue_load(s);
+    }
+    __syncwarp();
+    for (int s = 0; s < nsteps; ++s) {
+      const unsigned st = (it + (unsigned)s) % kRectCmStages;
+      const unsigned ph = ((it + (unsigned)s) / kRectCmStages) & 1u;
+      mbar_wait(&full[st], ph, const_cast<int32_t *>(status));
+      unsigned char *stg = mystage + (size_t)st * STAGE;
+      T *tile = reinterpret_cast<T *>(stg) + lane;  // element (lane, k) at tile[k * 32]
+      const double *cf = reinterpret_cast<const double *>(stg + TILE);
+#pragma unroll
+      for (int k = 0; k < kPanel; k += 2) {
+        const double2 pp = *reinterpret_cast<const double2 *>(cf + k);
+        const double l0 = (double)tile[k * kPanel], l1 = (double)tile[(k + 1) * kPanel];
+        if (UPDATE) {
+          const double2 c2 = *reinterpret_cast<const double2 *>(cf + kPanel + k);
+          const double2 s2 = *reinterpret_cast<const double2 *>(cf + 2 * kPanel + k);
+          tile[k * kPanel] = (T)fma(c2.x, l0, s2.x * w);
+          w = fma(-l0, pp.x, w);
+          tile[(k + 1) * kPanel] = (T)fma(c2.y, l1, s2.y * w);
+          w = fma(-l1, pp.y, w);
+        } else {
+          w = fma(-l0, pp.x, w);
+          w = fma(-l1, pp.y, w);
+        }
+      }
+      if (UPDATE) fence_proxy_async();
+      __syncwarp();
+      if (elect_one()) {
+        if (UPDATE) {
+          tma_store_2d(&tmapc, row0, col_begin + s * kPanel, stg);
+          bulk_commit();
+          bulk_wait_read<1>();  // the store of step s-1 has left the stage that step s+3 loads into
+        }
+        issue_load(s + kRectCmStages - 1);
+      }
+      __syncwarp();
+    }
+    it += (unsigned)nsteps;
+    if (row < n) ws.w[row] = w;
+  }
+  if (elect_one()) bulk_wait_all<0>();
+}
+
+template <typename T>
+inline size_t rect_apply_cm_smem() { return 1024 + (size_t)kRectCmWarps * kRectCmStages * RectCmGeom<T>::STAGE; }
+
 // =====================================================================================
 // Downdate sweep (row-major): TMA-pipelined, 4 lanes per row, right-to-left affine scan
 // =====================================================================================
@@ -2619,6 +2722,11 @@ inline bool make_tmap_cm(CUtensorMap *map, T *L, int64_t n, int64_t ld, int box_
 template <typename T>
 inline bool dataflow_native(int64_t n, int64_t ld, int layout, const T *L) {
   if (!get_encode_tiled() || getenv("CHUB_DF_V2")) return false;
+  if (layout == CHUB_COL_MAJOR) {  // (test knob: send smaller column-major factors through the blocked driver)
+    if (const char *e = getenv("CHUB_CM_NATIVE_MAX_N")) {
+      if (n > atoll(e)) return false;
+    }
+  }
   return layout == CHUB_ROW_MAJOR ? rm_plan<T>(n, ld, L).ok : cm_plan<T>(n, ld, L).ok;
 }
 
@@ -2634,7 +2742,7 @@ template <typename T, int LAYOUT, bool UPDATE>
 int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs &ws,
                     int32_t *status, cudaStream_t st, int64_t *launches, const double *w_in = nullptr,
                     bool chain_only = false) {
-  // w_in / chain_only: blocked driver (launch_blocked_rm) -- this call handles one diagonal block whose
+  // w_in / chain_only: blocked driver (launch_blocked) -- this call handles one diagonal block whose
   // input vector is the residual w_in, and for a downdate only the forward substitution (the
   // coefficient and sweep kernels run once, over the whole factor, afterwards)
   *launches = 0;
@@ -2773,16 +2881,18 @@ inline LargeWs ws_offset(const LargeWs &ws, int64_t off) {  // the workspace as 
   return w;  // scal and flags are shared
 }
 
+// layout-agnostic part of the test; the row-major dispatch (api.cu) uses it for every n beyond one launch
 template <typename T>
-inline bool blocked_supported(int64_t n, int64_t ld, const T *L) {
+inline bool blocked_supported(int64_t n, int64_t ld, const T *L, int layout = CHUB_ROW_MAJOR) {
   constexpr int EPC = 16 / sizeof(T);
   if (n <= kBlockedMax || n >= (1LL << 31) || (ld % EPC) != 0 || (reinterpret_cast<uintptr_t>(L) & 15) != 0) return false;
-  return get_encode_tiled() != nullptr && rm_plan<T>(kBlockedMax, ld, L).ok;
+  if (!get_encode_tiled()) return false;
+  return layout == CHUB_ROW_MAJOR ? rm_plan<T>(kBlockedMax, ld, L).ok : cm_plan<T>(kBlockedMax, ld, L).ok;
 }
 
-template <typename T, bool UPDATE>
-int launch_blocked_rm(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs &ws, int32_t *status,
-                      cudaStream_t st, int64_t *launches) {
+template <typename T, int LAYOUT, bool UPDATE>
+int launch_blocked(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs &ws, int32_t *status,
+                   cudaStream_t st, int64_t *launches) {
   *launches = 0;
   const int ni = (int)n;
   int sms = 0, dev = 0;
@@ -2803,12 +2913,16 @@ int launch_blocked_rm(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeW
       left -= sizes[J];
     }
   }
-  blocked_init_kernel<T, CHUB_ROW_MAJOR><<<(ni + 255) / 256, 256, 0, st>>>(L, ni, ld, v, ws, flags, status);
+  blocked_init_kernel<T, LAYOUT><<<(ni + 255) / 256, 256, 0, st>>>(L, ni, ld, v, ws, flags, status);
   ++*launches;
-  alignas(64) CUtensorMap tmap8;
-  if (!make_tmap<T>(&tmap8, L, n, ld, 8)) return (int)cudaErrorNotSupported;
-  auto rk = rect_apply_rm_kernel<T, UPDATE>;
-  const size_t rsm = rect_apply_rm_smem<T>();
+  // the whole factor as the rectangle kernel (and the downdate's sweep) sees it
+  alignas(64) CUtensorMap tmapw;
+  if (LAYOUT == CHUB_ROW_MAJOR ? !make_tmap<T>(&tmapw, L, n, ld, 8) : !make_tmap_cm<T>(&tmapw, L, n, ld))
+    return (int)cudaErrorNotSupported;
+  constexpr bool RM = LAYOUT == CHUB_ROW_MAJOR;
+  auto rk = RM ? rect_apply_rm_kernel<T, UPDATE> : rect_apply_cm_kernel<T, UPDATE>;
+  const size_t rsm = RM ? rect_apply_rm_smem<T>() : rect_apply_cm_smem<T>();
+  const int rwarps = RM ? kRectWarps : kRectCmWarps, rrows = RM ? 8 : kPanel;
   cudaError_t e = cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
   if (e != cudaSuccess) return (int)e;
   int64_t off = 0;
@@ -2816,32 +2930,40 @@ int launch_blocked_rm(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeW
     const int64_t nb_ = sizes[J];
     int64_t nl = 0;
     // (check_diag was done for the whole diagonal by the init kernel; status != 0 stops every kernel)
-    int rc = launch_dataflow<T, CHUB_ROW_MAJOR, UPDATE>(L + off * ld + off, nb_, ld, v + off, 0, ws_offset(ws, off),
-                                                        status, st, &nl, ws.w + off, true);
+    int rc = launch_dataflow<T, LAYOUT, UPDATE>(L + off * ld + off, nb_, ld, v + off, 0, ws_offset(ws, off),
+                                                status, st, &nl, ws.w + off, true);
     *launches += nl;
     if (rc) return rc;
     if (off + nb_ < n) {
       const int rows = (int)(n - off - nb_);
-      const int groups = (rows + 7) / 8;
-      const int grid = std::max(1, std::min(sms, (groups + kRectWarps - 1) / kRectWarps));
-      rk<<<grid, kRectWarps * 32, rsm, st>>>(ni, (int)(off + nb_), (int)off, (int)nb_, ws, status, tmap8);
+      const int groups = (rows + rrows - 1) / rrows;
+      const int grid = std::max(1, std::min(sms, (groups + rwarps - 1) / rwarps));
+      rk<<<grid, rwarps * 32, rsm, st>>>(ni, (int)(off + nb_), (int)off, (int)nb_, ws, status, tmapw);
       ++*launches;
     }
     off += nb_;
   }
   if (!UPDATE) {
     const int nb = (ni + 31) / 32;
-    if (getenv("CHUB_DD_COEF_V1")) large_dd_coef_kernel<T, CHUB_ROW_MAJOR><<<1, 1024, 0, st>>>(L, ni, ld, v, ws, status);
+    if (getenv("CHUB_DD_COEF_V1")) large_dd_coef_kernel<T, LAYOUT><<<1, 1024, 0, st>>>(L, ni, ld, v, ws, status);
     else dd_coef_par_kernel<T><<<1, 1024, 0, st>>>(ni, v, ws, status);
     ++*launches;
-    alignas(64) CUtensorMap tmap3;
-    const bool use3d = make_tmap3<T>(&tmap3, L, n, ld, 8, 2 * RmGeom<T>::HALVES);
-    if (!use3d) tmap3 = tmap8;
-    auto sk = dd_sweep_rm2_kernel<T>;
-    const size_t ssm = dd_sweep_rm2_smem<T>();
-    e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
-    if (e != cudaSuccess) return (int)e;
-    sk<<<nb, 128, ssm, st>>>(L, ni, ld, ws, status, use3d ? 1 : 0, tmap8, tmap3);
+    if (RM) {
+      alignas(64) CUtensorMap tmap3;
+      const bool use3d = make_tmap3<T>(&tmap3, L, n, ld, 8, 2 * RmGeom<T>::HALVES);
+      if (!use3d) tmap3 = tmapw;
+      auto sk = dd_sweep_rm2_kernel<T>;
+      const size_t ssm = dd_sweep_rm2_smem<T>();
+      e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
+      if (e != cudaSuccess) return (int)e;
+      sk<<<nb, 128, ssm, st>>>(L, ni, ld, ws, status, use3d ? 1 : 0, tmapw, tmap3);
+    } else {
+      auto sk = dd_sweep_cm_kernel<T>;
+      const size_t ssm = dd_sweep_cm_smem<T>();
+      e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
+      if (e != cudaSuccess) return (int)e;
+      sk<<<(nb + 3) / 4, 128, ssm, st>>>(L, ni, ld, ws, status, tmapw);
+    }
     ++*launches;
   }
   return (int)cudaGetLastError();

@@ -106,3 +106,60 @@ def test_update_and_downdate_above_16464(n, order):
     Lt = torch.nan_to_num(Lt)
     rank_1.downdate(Lt, torch.from_numpy(vd.copy()).cuda(), check_diag=True, overwrite_L=True, overwrite_v=True)
     assert rel_fro(Lt.cpu().numpy(), L_dd) <= tol_for(np.float64, n) * 2
+
+
+def test_blocked_driver_column_major_vs_oracle(monkeypatch):
+    """Column-major factors beyond the native kernel's row capacity (n > 28224) go through diagonal blocks +
+    rect_apply_cm_kernel.  The knob sends n = 20000 down that path (two diagonal blocks of ~10000), where the
+    oracle is still a direct comparison."""
+    monkeypatch.setenv("CHUB_CM_NATIVE_MAX_N", "16384")
+    n = 20000
+    L = synth_factor(n, 15)
+    v = np.random.default_rng(16).standard_normal(n)
+    L_ref, v_ref = np.array(L, order="F"), v.copy()
+    oracle.update(L_ref, v_ref)
+    Lt = _to_cuda(L, "F")
+    vt = torch.from_numpy(v.copy()).cuda()
+    rank_1.update(Lt, vt, check_diag=False, overwrite_L=True, overwrite_v=True)
+    assert rel_fro(Lt.cpu().numpy(), L_ref) <= tol_for(np.float64, n)
+    assert np.linalg.norm(vt.cpu().numpy() - v_ref) <= tol_for(np.float64, n) * np.linalg.norm(v_ref)
+    vd = downdate_vector(np.tril(L_ref), 17)
+    L_dd, vd_ref = np.array(L_ref, order="F"), vd.copy()
+    oracle.downdate(L_dd, vd_ref)
+    vdt = torch.from_numpy(vd.copy()).cuda()
+    rank_1.downdate(Lt, vdt, check_diag=True, overwrite_L=True, overwrite_v=True)
+    assert rel_fro(Lt.cpu().numpy(), L_dd) <= tol_for(np.float64, n) * 2
+    assert np.linalg.norm(vdt.cpu().numpy() - vd_ref) <= tol_for(np.float64, n) * 2 * np.linalg.norm(vd_ref)
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_update_and_downdate_n32768_properties(order):
+    """n = 32768 (8.6 GB, two diagonal blocks + one rectangle in either layout), checked without a host copy:
+    the leading 4096 x 4096 block against the oracle (the update of a leading block depends on that block and
+    v[:m] only), and 64 sampled rows of L' L'^T against L L^T +/- v v^T (all rows enter through the products)."""
+    n, m = 32768, 4096
+    g = torch.Generator(device="cuda").manual_seed(32768)
+    L = torch.tril(torch.randn(n, n, dtype=torch.float64, device="cuda", generator=g) / np.sqrt(n), -1)
+    L.diagonal().copy_(1 + torch.rand(n, dtype=torch.float64, device="cuda", generator=g))
+    if order == "F":
+        L = L.t().contiguous().t()
+    v = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    rows = torch.randint(0, n, (64,), device="cuda", generator=g)
+    rows[0], rows[1] = n - 1, n // 2 + 5
+    A_rows = L[rows] @ L.t()
+    lead, v_lead = np.array(L[:m, :m].cpu().numpy(), order="F"), v[:m].cpu().numpy().copy()
+    for op, sign in (("update", 1.0), ("downdate", -1.0)):
+        if op == "downdate":  # v = L p with ||p|| = 0.7 keeps the result positive definite
+            p = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+            v = L @ (0.7 * p / p.norm())
+            v_lead = v[:m].cpu().numpy().copy()
+        want = A_rows + sign * torch.outer(v[rows], v)
+        v_in = v.clone()
+        getattr(rank_1, op)(L, v_in, check_diag=False, overwrite_L=True, overwrite_v=True)
+        assert bool((torch.triu(L, 1) == 0).all())
+        A_rows = L[rows] @ L.t()
+        err = float((A_rows - want).norm() / want.norm())
+        assert err <= 1e-12 * np.sqrt(n), (op, err)
+        getattr(oracle, op)(lead, v_lead)
+        assert rel_fro(L[:m, :m].cpu().numpy(), lead) <= tol_for(np.float64, n), op
+        assert np.linalg.norm(v_in[:m].cpu().numpy() - v_lead) <= tol_for(np.float64, n) * np.linalg.norm(v_lead), op
