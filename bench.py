@@ -701,6 +701,71 @@ def leg_downdate(ctx, args):
     return out
 
 
+# ------------------------------------------------------------------- leg: other sizes / the other layout
+def leg_update_sized(ctx, args, n, layout, steps=10, warmup=3):
+    """In-place updates of one resident factor of order n in `layout` through the C ABI (device pointers): the
+    column-major layout the reference recommends (_seeger.py:65-68) and sizes beyond one persistent launch
+    (blocked driver).  Parity: leading block vs the oracle, as in the headline leg."""
+    torch, lib = ctx.torch, ctx.lib
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
+    L = make_factor_cuda(torch, n, 777 + rank + n, dev)
+    if layout == "F":
+        L = L.t().contiguous().t()
+    g = torch.Generator(device=dev)
+    g.manual_seed(29 + rank)
+    V = torch.randn((warmup + steps, n), dtype=torch.float64, device=dev, generator=g)
+    V0 = V[:, :LEAD].cpu().numpy().copy()
+    ws_bytes = int(lib.chub_workspace_bytes(1, n))
+    ws_buf = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    status_all = torch.zeros(warmup + steps, dtype=torch.int32, device=dev)
+    lay = 0 if layout == "C" else 1
+    L_lead0 = L[:LEAD, :LEAD].cpu().numpy()
+
+    def step(i):
+        rc = lib.chub_update_f64(L.data_ptr(), n, n, lay, V[i].data_ptr(), 0, ws_buf.data_ptr(), ws_bytes,
+                                 status_all[i:].data_ptr(), ctx.stream.cuda_stream)
+        if rc != 0:
+            raise RuntimeError(lib.chub_last_error().decode())
+
+    _, step_ms = timed_steps(ctx, step, warmup, steps)
+    ms = ctx.max_over_ranks(statistics.mean(step_ms))
+    if int(torch.count_nonzero(status_all).item()):
+        raise RuntimeError("an update reported a non-zero status")
+    b2 = algorithmic_bytes_update(n)
+    out = {"workload": f"update_n{n}_f64_inplace_{layout}", "n": n, "layout": layout, "steps": steps, "warmup": warmup,
+           "ms_per_update": ms, "ms_best": min(step_ms), "value": world / (ms * 1e-3), "unit": "updates/s",
+           "roofline": {"bound": "hbm", "achieved": b2 / (ms * 1e-3) / 1e9, "peak": ctx.peak, "unit": "GB/s",
+                        "frac": b2 / (ms * 1e-3) / 1e9 / ctx.peak, "algorithmic_bytes": b2}}
+    tr, src = ctx.traffic(out["workload"])
+    if tr:
+        out["roofline"]["traffic"], out["roofline"]["traffic_source"] = tr, src
+    if rank == 0:
+        L_ref = oracle_apply(L_lead0, [("update", v) for v in V0])
+        out["parity"] = parity_report(L[:LEAD, :LEAD].cpu().numpy(), L_ref, n_tol=n)
+        out["parity"]["what"] = (f"leading {LEAD} x {LEAD} block after {warmup + steps} successive updates vs the oracle "
+                                 "applied to the leading block")
+    del L, V, ws_buf
+    torch.cuda.empty_cache()
+    return out
+
+
+def leg_layouts_and_sizes(ctx, args):
+    """Column-major n = 16384 (update and downdate) and n = 32768 in both layouts (two diagonal blocks + one
+    rectangle each: the blocked driver)."""
+    import copy
+
+    out = {}
+    fargs = copy.copy(args)
+    fargs.layout = "F"
+    out["update_n16384_F"] = leg_update_sized(ctx, args, N_BIG, "F", steps=20)
+    dd = leg_downdate(ctx, fargs)
+    dd.pop("not_pd_case", None)
+    out["downdate_n16384_F"] = dd
+    out["update_n32768_C"] = leg_update_sized(ctx, args, 32768, "C", steps=5)
+    out["update_n32768_F"] = leg_update_sized(ctx, args, 32768, "F", steps=5)
+    return out
+
+
 # ------------------------------------------------------------------- leg: batched 8192 x 256 per GPU
 def leg_batched(ctx, args):
     torch, rank_1 = ctx.torch, ctx.rank_1
@@ -939,6 +1004,11 @@ def leg_public_api(ctx, args):
             for order in ("C", "F"):
                 Lo = np.asarray(L0, order=order)
                 for mode, kw in (("copy", {}), ("inplace", {"overwrite_L": True, "overwrite_v": True})):
+                    # (steady state of a caller's loop: after a compute-only stretch the first transfers run on a
+                    # PCIe link that is still in its low-power state -- 3 ms instead of 0.6 ms at n = 1000)
+                    t_warm = time.perf_counter()
+                    while time.perf_counter() - t_warm < 0.15:
+                        rank_1.update(Lo.copy(order="K"), v0.copy(), check_diag=False, **kw)
                     ts = []
                     for _ in range(6):
                         Lx, vx = Lo.copy(order="K"), v0.copy()
@@ -992,6 +1062,12 @@ def run_gpu_arm(args):
         if wl == "all":
             legs = {}
             legs["downdate_n16384"] = safe_leg(ctx, "downdate", lambda: leg_downdate(ctx, args))
+            other = safe_leg(ctx, "layouts_and_sizes", lambda: leg_layouts_and_sizes(ctx, args))
+            if isinstance(other, dict) and "error" not in other:
+                other.pop("leg_wall_s", None)
+                legs.update(other)
+            else:
+                legs["layouts_and_sizes"] = other
             legs["batched_8192x256"] = safe_leg(ctx, "batched", lambda: leg_batched(ctx, args))
             rc = safe_leg(ctx, "rowcyclic", lambda: leg_rowcyclic(ctx, args, RC_N, RC_K))
             if isinstance(rc, dict) and "error" not in rc:

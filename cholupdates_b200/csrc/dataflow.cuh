@@ -2104,6 +2104,284 @@ __global__ void __launch_bounds__(128) dd_sweep_cm_kernel(T *L, int n, int64_t l
   if (elect_one()) bulk_wait_all<0>();
 }
 
+// ---- the same sweep with the block rows dealt so that every SM moves the same number of tiles.  Block row b
+// has b + 1 tiles; dd_sweep_cm_kernel gives CTA i the four longest remaining rows, so the first CTA (2040 of the
+// 131 k tiles at n = 16384) sets the kernel's time at the bandwidth ONE SM can pull: 552 us for 2.15 GB
+// (profiles/r04j launch list).  Here one CTA per SM (eight warps), rows sorted by length and dealt in a snake:
+// round j goes c = 0 .. G-1 for even j and back for odd j, warp w takes rounds w, w + 8, ...
+constexpr int kSwCm2Warps = 8;
+constexpr int kSwCm2StagesTotal = 24;  // ring stages per CTA, shared out over the warps that have rows (ns each):
+// a warp streams one block row and is bound by (tiles in flight) / (memory latency), so with few rows per SM
+// (n = 16384: 3.5) each of them gets a deep ring; ns >= 4: loads run ns - 2 steps ahead and land in the stage
+// stored from two steps ago; ns = 3: two steps ahead, behind a wait for the previous step's store
+
+template <typename T>
+__global__ void __launch_bounds__(kSwCm2Warps * 32, 1)
+dd_sweep_cm2_kernel(T *L, int n, int64_t ld, LargeWs ws, const int32_t *status, int ns,
+                    const __grid_constant__ CUtensorMap tmapc) {
+  constexpr int TILE = CmGeom<T>::TILE, STAGE = SwCmGeom<T>::STAGE;
+  extern __shared__ __align__(1024) unsigned char sw_smem[];
+  if (*status != 0) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int T_ = (n + 31) / 32;
+  const int G = (int)gridDim.x, c = (int)blockIdx.x;
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(sw_smem) + warp * ns;
+  unsigned char *mystage = sw_smem + 1024 + (size_t)warp * ns * STAGE;
+  const bool deep = ns >= 4;
+  const int pf = deep ? ns - 2 : ns - 1;  // prefetch distance in steps
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSwCm2StagesTotal; ++i) mbar_init(reinterpret_cast<unsigned long long *>(sw_smem) + i, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  unsigned it = 0;  // tiles this warp has consumed so far (ring position / mbarrier phase)
+  const int R = (T_ + G - 1) / G;  // rounds
+  for (int j = warp; j < R; j += kSwCm2Warps) {
+    const int pos = j * G + ((j & 1) ? G - 1 - c : c);  // position in the list of rows sorted by length
+    if (pos >= T_) continue;  // (last round only)
+    const int b = T_ - 1 - pos;
+    const int64_t row0 = (int64_t)b * kPanel, row = row0 + lane;
+    const bool valid = row < n;
+    const int nsteps = b + 1;  // tiles b, b-1, ..., 0
+
+    auto issue_load = [&](int s) {  // elected lane
+      if (s >= nsteps) return;
+      const int pan = b - s;
+      const unsigned st = (it + (unsigned)s) % (unsigned)ns;
+      void *bar = &full[st];
+      unsigned char *stg = mystage + (size_t)st * STAGE;
+      mbar_arrive_expect_tx(bar, (unsigned)TILE + 768u);
+      tma_load_2d(stg, &tmapc, (int)row0, pan * kPanel, bar);
+      bulk_g2s(stg + TILE, ws.c + pan * kPanel, 256u, bar);
+      bulk_g2s(stg + TILE + 256, ws.sg + pan * kPanel, 256u, bar);
+      bulk_g2s(stg + TILE + 512, ws.dn + pan * kPanel, 256u, bar);
+    };
+
+    if (elect_one()) {
+      bulk_wait_read<0>();  // (the previous row's last stores have left their stages)
+      for (int s = 0; s < pf; ++s) issue_load(s);
+    }
+    __syncwarp();
+    double x = 0.0;  // x_i carried from the tile to the right
+    for (int s = 0; s < nsteps; ++s) {
+      if (elect_one()) {
+        if (deep) bulk_wait_read<1>();  // the store of step s-2 has left its stage (= the stage of step s + ns - 2)
+        else bulk_wait_read<0>();       // ... of step s-1 (= the stage of step s + ns - 1)
+        issue_load(s + pf);
+      }
+      __syncwarp();
+      const unsigned st = (it + (unsigned)s) % (unsigned)ns;
+      mbar_wait(&full[st], ((it + (unsigned)s) / (unsigned)ns) & 1u, const_cast<int32_t *>(status));
+      const int pan = b - s;
+      unsigned char *stg = mystage + (size_t)st * STAGE;
+      T *tile = reinterpret_cast<T *>(stg) + lane;  // element (lane, k) at tile[k * 32]
+      const double *cf = reinterpret_cast<const double *>(stg + TILE);
+      const bool diag = (s == 0);
+      double lnew[kPanel];
+#pragma unroll
+      for (int k = kPanel - 1; k >= 0; --k) {
+        const double lo = (double)tile[k * kPanel];
+        const double cc = cf[k], sn = cf[kPanel + k];
+        const double ln = cf[2 * kPanel + k] * (cc * lo - sn * x);
+        const double xn = fma(cc, x, sn * lo);
+        // above the diagonal (diagonal tile, k > lane): identity, the entry's bits never reach x or L
+        const bool on = !diag || k <= lane;
+        lnew[k] = ln;
+        x = on ? xn : x;
+      }
+      if (!diag) {
+#pragma unroll
+        for (int k = 0; k < kPanel; ++k) tile[k * kPanel] = (T)lnew[k];
+      } else if (valid) {
+        T *gp = L + row + (int64_t)row0 * ld;
+#pragma unroll
+        for (int k = 0; k < kPanel; ++k)
+          if (k <= lane) gp[(int64_t)k * ld] = (T)lnew[k];
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (elect_one()) {
+        if (!diag) tma_store_2d(&tmapc, (int)row0, pan * kPanel, stg);
+        bulk_commit();
+      }
+      __syncwarp();
+    }
+    it += (unsigned)nsteps;
+  }
+  if (elect_one()) bulk_wait_all<0>();
+}
+
+template <typename T>
+inline size_t dd_sweep_cm2_smem() { return 1024 + (size_t)kSwCm2StagesTotal * SwCmGeom<T>::STAGE; }
+
+// ---- third generation: FOUR warps per block row, each on 8 of a tile's 32 columns.  What bounds the kernels above
+// is instruction issue, not bandwidth and not the dependent FMA chain: ~500 warp instructions per tile on ONE warp,
+// 1.25 warps per scheduler, one instruction every 7.8 cycles (ncu, gpurun r04n) -- and the longest block row (T
+// tiles in sequence) sets the kernel's time.  (Tried on the way: two warps taking alternate tiles with x handed over
+// through shared memory, 0.82 ms; that plus packed coefficients, 0.84; that plus four-segment affine maps inside one
+// warp, 0.95 -- more instructions, slower.)  The recurrence is affine in x, so warp h turns its 8 columns into
+// (A_h, B_h): x behind the segment = A_h x_front + B_h, all four at once; the maps cross through shared memory (one
+// named barrier of 128 threads), every warp composes the row's x across the tile for itself (4 FMAs) and the x in
+// front of its own segment, then forms its 8 columns of L'.  A second barrier before the quad's TMA store.
+constexpr int kSwCm4Quads = 4;   // block rows in flight per CTA (16 warps)
+constexpr int kSwCm4Stages = 5;  // ring per block row; loads run three steps ahead
+
+template <typename T>
+__global__ void __launch_bounds__(kSwCm4Quads * 128, 1)
+dd_sweep_cm4_kernel(T *L, int n, int64_t ld, LargeWs ws, const int32_t *status, const __grid_constant__ CUtensorMap tmapc) {
+  constexpr int TILE = CmGeom<T>::TILE, STAGE = SwCmGeom<T>::STAGE, NS = kSwCm4Stages;
+  extern __shared__ __align__(1024) unsigned char sw_smem[];
+  if (*status != 0) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int q = warp >> 2, h = warp & 3;
+  const int T_ = (n + 31) / 32;
+  const int G = (int)gridDim.x, c = (int)blockIdx.x;
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(sw_smem) + q * NS;
+  double2 *xch = reinterpret_cast<double2 *>(sw_smem + 1024) + (size_t)q * (2 * 4 * 32);  // [parity][segment][lane] (A, B)
+  unsigned char *mystage = sw_smem + 1024 + kSwCm4Quads * 4096 + (size_t)q * NS * STAGE;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSwCm4Quads * NS; ++i) mbar_init(reinterpret_cast<unsigned long long *>(sw_smem) + i, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  unsigned it = 0;  // tiles this quad has consumed so far (ring position / mbarrier phase / exchange parity)
+  const int R = (T_ + G - 1) / G;  // rounds
+  for (int j = q; j < R; j += kSwCm4Quads) {
+    const int pos = j * G + ((j & 1) ? G - 1 - c : c);  // position in the list of rows sorted by length (snake)
+    if (pos >= T_) continue;  // (last round only; the whole quad skips it)
+    const int b = T_ - 1 - pos;
+    const int64_t row0 = (int64_t)b * kPanel, row = row0 + lane;
+    const bool valid = row < n;
+    const int nsteps = b + 1;  // tiles b, b-1, ..., 0
+
+    auto issue_load = [&](int s) {  // elected lane of warp h = 0
+      if (s >= nsteps) return;
+      const int pan = b - s;
+      const unsigned st = (it + (unsigned)s) % NS;
+      void *bar = &full[st];
+      unsigned char *stg = mystage + (size_t)st * STAGE;
+      mbar_arrive_expect_tx(bar, (unsigned)TILE + 1024u);
+      tma_load_2d(stg, &tmapc, (int)row0, pan * kPanel, bar);
+      bulk_g2s(stg + TILE, ws.X + (size_t)pan * (4 * kPanel), 1024u, bar);  // (c, s, sgn c, sgn s) per column
+    };
+
+    if (h == 0 && elect_one()) {
+      bulk_wait_read<0>();  // (the previous row's last stores have left their stages)
+      for (int s = 0; s < NS - 2; ++s) issue_load(s);
+    }
+    __syncwarp();
+    double x = 0.0;  // x_i carried from the tile to the right (every warp of the quad keeps its own copy)
+    for (int s = 0; s < nsteps; ++s) {
+      if (h == 0 && elect_one()) {
+        bulk_wait_read<1>();  // the store of step s-2 has left its stage (= the stage of step s + NS - 2)
+        issue_load(s + NS - 2);
+      }
+      __syncwarp();
+      const unsigned st = (it + (unsigned)s) % NS;
+      mbar_wait(&full[st], ((it + (unsigned)s) / NS) & 1u, const_cast<int32_t *>(status));
+      const int pan = b - s;
+      unsigned char *stg = mystage + (size_t)st * STAGE;
+      T *tile = reinterpret_cast<T *>(stg) + lane + (8 * h) * kPanel;  // element (lane, 8h + k) at tile[k * 32]
+      const double2 *cf = reinterpret_cast<const double2 *>(stg + TILE) + 2 * (8 * h);  // column 8h + k: cf[2k] = (c, s), cf[2k+1] = sgn (c, s)
+      const bool diag = (s == 0);
+      double lo[8], sl[8], ck[8];
+      double a = 1.0, bb = 0.0;
+#pragma unroll
+      for (int k = 7; k >= 0; --k) {
+        const double2 cs = cf[2 * k];
+        lo[k] = (double)tile[k * kPanel];
+        ck[k] = cs.x;
+        sl[k] = cs.y * lo[k];
+        if (!diag || 8 * h + k <= lane) {  // above the diagonal (diagonal tile, column > lane): identity
+          bb = fma(ck[k], bb, sl[k]);
+          a *= ck[k];
+        }
+      }
+      double2 *xs = xch + ((it + (unsigned)s) & 1u) * (4 * 32) + lane;  // segment g's map of this row at xs[g * 32]
+      xs[h * 32] = make_double2(a, bb);
+      named_sync(1 + q, 128);
+      // x in front of my segment (segments 3, 2, ... are to my right), and x behind the whole tile
+      double xf = x;
+#pragma unroll
+      for (int g = 3; g >= 0; --g) {
+        const double2 m = xs[g * 32];
+        x = fma(m.x, x, m.y);
+        if (g == h + 1) xf = x;
+      }
+      T *gp = L + row + (int64_t)(row0 + 8 * h) * ld;  // (diagonal tile: straight to global memory, nothing above the diagonal)
+#pragma unroll
+      for (int k = 7; k >= 0; --k) {
+        const double2 d = cf[2 * k + 1];
+        const double ln = fma(-d.y, xf, d.x * lo[k]);
+        if (!diag) {
+          tile[k * kPanel] = (T)ln;
+          xf = fma(ck[k], xf, sl[k]);
+        } else if (8 * h + k <= lane) {
+          if (valid) gp[(int64_t)k * ld] = (T)ln;
+          xf = fma(ck[k], xf, sl[k]);
+        }
+      }
+      if (!diag) {
+        fence_proxy_async();
+        named_sync(1 + q, 128);  // the other warps' tile writes too
+        if (h == 0 && elect_one()) {
+          tma_store_2d(&tmapc, (int)row0, pan * kPanel, stg);
+          bulk_commit();
+        }
+      } else if (h == 0 && elect_one()) {
+        bulk_commit();  // (keeps the wait_group arithmetic: one group per step)
+      }
+      __syncwarp();
+    }
+    it += (unsigned)nsteps;
+  }
+  if (h == 0 && elect_one()) bulk_wait_all<0>();
+}
+
+template <typename T>
+inline size_t dd_sweep_cm4_smem() { return 1024 + kSwCm4Quads * 4096 + (size_t)kSwCm4Quads * kSwCm4Stages * SwCmGeom<T>::STAGE; }
+
+template <typename T>
+inline size_t dd_sweep_cm_smem();
+
+template <typename T>
+inline cudaError_t launch_dd_sweep_cm(T *L, int n, int64_t ld, const LargeWs &ws, const int32_t *status,
+                                      const CUtensorMap &tmapc, cudaStream_t st) {
+  const int nb = (n + 31) / 32;
+  if (getenv("CHUB_DD_SWEEP_CM_V1")) {  // A/B: four consecutive block rows per CTA
+    auto sk = dd_sweep_cm_kernel<T>;
+    const size_t ssm = dd_sweep_cm_smem<T>();
+    cudaError_t e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
+    if (e != cudaSuccess) return e;
+    sk<<<(nb + 3) / 4, 128, ssm, st>>>(L, n, ld, ws, status, tmapc);
+    return cudaSuccess;
+  }
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (!getenv("CHUB_DD_SWEEP_CM_V2") && !getenv("CHUB_DD_COEF_V1")) {  // (V2: one warp per block row, A/B; the packed
+    // coefficients this kernel reads come from dd_coef_par_kernel only)
+    auto sk = dd_sweep_cm4_kernel<T>;
+    const size_t ssm = dd_sweep_cm4_smem<T>();
+    cudaError_t e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
+    if (e != cudaSuccess) return e;
+    sk<<<std::max(1, std::min(sms, nb)), kSwCm4Quads * 128, ssm, st>>>(L, n, ld, ws, status, tmapc);
+    return cudaSuccess;
+  }
+  auto sk = dd_sweep_cm2_kernel<T>;
+  const size_t ssm = dd_sweep_cm2_smem<T>();
+  cudaError_t e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
+  if (e != cudaSuccess) return e;
+  const int grid = std::max(1, std::min(sms, nb));
+  const int rounds = (nb + grid - 1) / grid;  // block rows per CTA
+  int ns = std::max(3, std::min(8, kSwCm2StagesTotal / std::min(kSwCm2Warps, rounds)));
+  if (const char *e = getenv("CHUB_DD_SWEEP_CM_NS")) ns = std::max(3, std::min(ns, atoi(e)));
+  sk<<<grid, kSwCm2Warps * 32, ssm, st>>>(L, n, ld, ws, status, ns, tmapc);
+  return cudaSuccess;
+}
+
 template <typename T>
 inline size_t dd_sweep_cm_smem() { return 1024 + (size_t)4 * kSwCmStages * SwCmGeom<T>::STAGE; }
 
@@ -2141,7 +2419,8 @@ rect_apply_cm_kernel(int n, int row_begin, int col_begin, int ncols, LargeWs ws,
   const int nsteps = ncols / kPanel;
   const int ngroups = (n - row_begin + kPanel - 1) / kPanel;
   unsigned it = 0;  // tiles this warp has consumed so far (ring position / mbarrier phase)
-  for (int grp = (int)blockIdx.x * kRectCmWarps + warp; grp < ngroups; grp += (int)gridDim.x * kRectCmWarps) {
+  // (groups dealt CTA-first: with fewer groups than warp slots every SM still gets its share)
+  for (int grp = (int)blockIdx.x + warp * (int)gridDim.x; grp < ngroups; grp += (int)gridDim.x * kRectCmWarps) {
     const int row0 = row_begin + grp * kPanel;
     const int row = row0 + lane;
     double w = row < n ? ws.w[row] : 0.0;
@@ -2852,11 +3131,8 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
       if (e != cudaSuccess) return (int)e;
       sk<<<nb, 128, ssm, st>>>(L, ni, ld, ws, status, tmap8);
     } else if (cp.ok && !getenv("CHUB_DD_SWEEP_V1")) {
-      auto sk = dd_sweep_cm_kernel<T>;
-      const size_t ssm = dd_sweep_cm_smem<T>();
-      e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
+      e = launch_dd_sweep_cm<T>(L, ni, ld, ws, status, tmapc, st);
       if (e != cudaSuccess) return (int)e;
-      sk<<<(nb + 3) / 4, 128, ssm, st>>>(L, ni, ld, ws, status, tmapc);
     } else {
       large_dd_sweep_kernel<T, LAYOUT><<<(ni + 127) / 128, 128, 0, st>>>(L, ni, ld, ws, status);
     }
@@ -2937,7 +3213,7 @@ int launch_blocked(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs &
     if (off + nb_ < n) {
       const int rows = (int)(n - off - nb_);
       const int groups = (rows + rrows - 1) / rrows;
-      const int grid = std::max(1, std::min(sms, (groups + rwarps - 1) / rwarps));
+      const int grid = std::max(1, RM ? std::min(sms, (groups + rwarps - 1) / rwarps) : std::min(sms, groups));
       rk<<<grid, rwarps * 32, rsm, st>>>(ni, (int)(off + nb_), (int)off, (int)nb_, ws, status, tmapw);
       ++*launches;
     }
@@ -2958,11 +3234,8 @@ int launch_blocked(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs &
       if (e != cudaSuccess) return (int)e;
       sk<<<nb, 128, ssm, st>>>(L, ni, ld, ws, status, use3d ? 1 : 0, tmapw, tmap3);
     } else {
-      auto sk = dd_sweep_cm_kernel<T>;
-      const size_t ssm = dd_sweep_cm_smem<T>();
-      e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
+      e = launch_dd_sweep_cm<T>(L, ni, ld, ws, status, tmapw, st);
       if (e != cudaSuccess) return (int)e;
-      sk<<<(nb + 3) / 4, 128, ssm, st>>>(L, ni, ld, ws, status, tmapw);
     }
     ++*launches;
   }

@@ -529,9 +529,15 @@ __global__ void __launch_bounds__(1024) dd_coef_par_kernel(int n, T *v, LargeWs 
       const double qk1 = sqrt(rho_sq + after);
       const double qk = sqrt(rho_sq + (after + x));
       const double cc = qk1 / qk, ss = pk / qk;
+      const double sgn = dgk < 0.0 ? -1.0 : 1.0;
       ws.c[k] = cc;
       ws.sg[k] = ss;
-      ws.dn[k] = dgk < 0.0 ? -1.0 : 1.0;
+      ws.dn[k] = sgn;
+      // the same, packed per column for the sweeps that take them in one 32-byte piece: (c, s, sgn c, sgn s).
+      // (ws.X is free by now: the forward substitution that used the inverse diagonal blocks is over.)
+      double2 *pk4 = reinterpret_cast<double2 *>(ws.X) + 2 * (size_t)k;
+      pk4[0] = make_double2(cc, ss);
+      pk4[1] = make_double2(sgn * cc, sgn * ss);
       v[k] = rotg_z<T>(T(qk1), T(pk), T(cc), T(ss));
     }
     carry += total_s;
