@@ -173,17 +173,27 @@ def _validate(L, v, check_diag: bool, strided: bool = False) -> bool:
 
 
 _ws_cache: dict = {}
+_WS_CACHE_MAX = 32
 
 
 def _torch_workspace(device, stream_id: int, nbytes: int):
     import torch
 
     key = (device.index, stream_id)
-    buf = _ws_cache.get(key)
+    buf = _ws_cache.pop(key, None)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
-        _ws_cache[key] = buf
+    _ws_cache[key] = buf  # (re-inserted last: the dict doubles as the LRU order)
+    while len(_ws_cache) > _WS_CACHE_MAX:  # streams come and go: keep the most recently used scratch buffers only
+        old_key = next(iter(_ws_cache))
+        torch.cuda.synchronize(old_key[0])  # (rare path: a kernel on that stream may still be using the buffer)
+        _ws_cache.pop(old_key)
     return buf
+
+
+def release_workspaces() -> None:
+    """Drop the cached per-(device, stream) scratch buffers (they are re-created on demand)."""
+    _ws_cache.clear()
 
 
 def _raise_for_status(status: int, op: str) -> None:
