@@ -1360,6 +1360,7 @@ inline size_t df_worker_rm_smem(int nrw) {
 #define CHUB_CHAIN_V6 1  // 1: barrier-free chain CTA (dataflow_chain_v6.cuh); 0: the barrier chain df_chain_rm (A/B)
 #endif
 #include "dataflow_chain_v6.cuh"
+#include "dataflow_chain_v7.cuh"
 namespace chub {
 
 // V5: second-generation row warps (dataflow_rm5.cuh); false = the first generation above (CHUB_RM5=0, A/B only)
@@ -1373,6 +1374,8 @@ df_kernel_rm(T *L, T *v, DfParams P, const __grid_constant__ CUtensorMap tmap8,
 #ifndef CHUB_EXP_NO_CHAIN
 #ifdef CHUB_CHAIN_V4
     if (threadIdx.x < 256) df_chain_v4<T, CHUB_ROW_MAJOR, PROF>(P, &tmap32, df_smem);
+#elif CHUB_CHAIN_V7
+    if (threadIdx.x < kC7Threads) df_chain_v7<T, CHUB_ROW_MAJOR, PROF>(P, &tmap32, df_smem);
 #elif CHUB_CHAIN_V6
     if (threadIdx.x < kC6ThreadsSplit) df_chain_v6<T, CHUB_ROW_MAJOR, PROF, false>(P, &tmap32, df_smem);
 #else
@@ -1984,7 +1987,11 @@ df_kernel_cm2(T *L, T *v, DfParams P, const __grid_constant__ CUtensorMap tmapc,
   if (*P.status != 0) return;  // check_diag failed: L and v stay untouched
   if (blockIdx.x == 0) {
     // (split poll / TMA warps, as in the row-major kernel: these workers leave the registers for 288 chain threads)
+#if CHUB_CHAIN_V7
+    if (threadIdx.x < kC7Threads) df_chain_v7<T, CHUB_COL_MAJOR, PROF>(P, &tmapcb, df_smem);
+#else
     if (threadIdx.x < kC6ThreadsSplit) df_chain_v6<T, CHUB_COL_MAJOR, PROF, false>(P, &tmapcb, df_smem);
+#endif
   } else {
     df_worker_cm2<T, UPDATE, PROF, H>(L, v, P, &tmapc, df_smem);
   }
@@ -2894,6 +2901,9 @@ inline RmPlan rm_plan(int64_t n, int64_t ld, const void *L) {
   smem = std::max(smem, df_chain_v4_smem<T>());
 #endif
   smem = std::max(smem, df_chain_v6_smem<T>());
+#if CHUB_CHAIN_V7
+  smem = std::max(smem, df_chain_v7_smem<T>());
+#endif
   if (smem > (size_t)smem_optin) return pl;
   pl.ok = true; pl.sms = sms; pl.Wk = Wk; pl.Q = Q; pl.nrw = nrw;
   pl.threads = std::max(std::max(256, kC6ThreadsSplit), 32 * (nrw + 2));  // row warps + coefficient warp + relay warp
@@ -2977,7 +2987,10 @@ inline CmPlan cm_plan(int64_t n, int64_t ld, const void *L) {
   const int64_t nRB = (n + kPanel - 1) / kPanel;
   const int Q = (int)((nRB + Wk - 1) / Wk);
   if (Q > kCmMaxQ) return pl;
-  const size_t smem = std::max(std::max(df_chain_rm_smem<T>(), df_chain_v6_smem<T>()), df_worker_cm2_smem<T>(Q, Q <= kCm4MaxQ ? 4 : 2));
+  size_t smem = std::max(std::max(df_chain_rm_smem<T>(), df_chain_v6_smem<T>()), df_worker_cm2_smem<T>(Q, Q <= kCm4MaxQ ? 4 : 2));
+#if CHUB_CHAIN_V7
+  smem = std::max(smem, df_chain_v7_smem<T>());
+#endif
   if (smem > (size_t)smem_optin) return pl;
   pl.ok = true; pl.sms = sms; pl.Wk = Wk; pl.Q = Q; pl.smem = smem;
   return pl;
@@ -3034,7 +3047,11 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
   if (LAYOUT == CHUB_ROW_MAJOR && !getenv("CHUB_DF_V2")) {
     rp = rm_plan<T>(n, ld, L);
     // tmap32: the chain's box (all d band tiles of a block column); tmap8 / tmap3: the row warps' boxes
-#ifdef CHUB_CHAIN_V4
+#if CHUB_CHAIN_V7  // (the distance-1 and -2 tiles are not loaded: M1 and M2 stand for them)
+    if (rp.ok && !(make_tmap<T>(&tmap8, L, n, ld, 8) &&
+                   make_tmap3<T>(&tmap32, L, n, ld, kPanel * (kDfD - 2), RmGeom<T>::HALVES)))
+      rp.ok = false;
+#elif defined(CHUB_CHAIN_V4)
     if (rp.ok && !(make_tmap<T>(&tmap8, L, n, ld, 8) &&
                    make_tmap3<T>(&tmap32, L, n, ld, kPanel * (kDfD - 1), RmGeom<T>::HALVES)))
       rp.ok = false;
@@ -3053,7 +3070,7 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
   alignas(64) CUtensorMap tmapc, tmapcb;  // tmapcb: the chain's box (32 d rows x 32 columns)
   if (LAYOUT == CHUB_COL_MAJOR && !getenv("CHUB_DF_V2")) {
     cp = cm_plan<T>(n, ld, L);
-    if (cp.ok && !(make_tmap_cm<T>(&tmapc, L, n, ld) && make_tmap_cm<T>(&tmapcb, L, n, ld, kPanel * kDfD)))
+    if (cp.ok && !(make_tmap_cm<T>(&tmapc, L, n, ld) && make_tmap_cm<T>(&tmapcb, L, n, ld, kPanel * (CHUB_CHAIN_V7 ? kDfD - 2 : kDfD))))
       cp.ok = false;
   }
   const bool tm = rp.ok || cp.ok;  // a tensor-map kernel (band depth kDfD)
@@ -3064,7 +3081,9 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
   }
   // one pre-pass: w-tilde / v0 / dg / sentinels (prepare) and the inverse diagonal blocks
   df_prepass_kernel<T, LAYOUT><<<(nb + 3) / 4, 128, 0, st>>>(L, ni, ld, v, ws, flags, status,
-#ifdef CHUB_CHAIN_V4
+#if CHUB_CHAIN_V7
+                                                              tm ? kDfD : kV2D, tm, w_in);
+#elif defined(CHUB_CHAIN_V4)
                                                               tm ? kDfD : kV2D, rp.ok, w_in);
 #else
                                                               tm ? kDfD : kV2D, false, w_in);
@@ -3103,6 +3122,7 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
     if (e != cudaSuccess) return (int)e;
     void *args[] = {(void *)&L, (void *)&v, (void *)&P, (void *)&tmapc, (void *)&tmapcb};
     const int threads = H > 1 ? std::max(kC6ThreadsSplit, 32 * (H * cp.Q + 2)) : kCmMaxThreads;
+    if (H == 1 && !make_tmap_cm<T>(&tmapcb, L, n, ld, kPanel * kDfD)) return (int)cudaErrorNotSupported;  // (v6 chain: d tiles)
     e = cudaLaunchCooperativeKernel((void *)kern, dim3(cp.sms), dim3(threads), args, cp.smem, st);
   } else {
     P.R = pl.R; P.r_shift = pl.r_shift; P.Wk = pl.Wk; P.rows_max = pl.rows_max; P.nw = pl.nw;
@@ -3152,7 +3172,7 @@ constexpr int64_t kBlockedMax = 16384;
 inline LargeWs ws_offset(const LargeWs &ws, int64_t off) {  // the workspace as diagonal block [off, ..) sees it
   LargeWs w = ws;
   w.X += (off / kPanel) * kXBlock;
-  if (w.M1) w.M1 += (off / kPanel) * kXBlock;
+  if (w.M1) w.M1 += (off / kPanel) * (CHUB_CHAIN_V7 ? 2 : 1) * kXBlock;
   w.w += off; w.p += off; w.c += off; w.sg += off; w.dn += off; w.v0 += off; w.dg += off;
   return w;  // scal and flags are shared
 }

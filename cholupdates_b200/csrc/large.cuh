@@ -24,6 +24,10 @@
 // both layouts.  The persistent dataflow kernel (dataflow.cuh) reuses its pieces.
 #pragma once
 
+#ifndef CHUB_CHAIN_V7
+#define CHUB_CHAIN_V7 0  // 1: chain CTA with one mat-vec per block row (dataflow_chain_v7.cuh, needs M1 from the pre-pass); 0: v6
+#endif
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -36,7 +40,8 @@ constexpr int kXBlock = kPanel * kXStride;  // lane = row reads of 16 bytes are 
 
 struct LargeWs {
   double *X;      // [nb][kXBlock] inverse of each 32x32 diagonal block (rows of kXStride, identity padded)
-  double *M1;     // [nb][kXBlock] M1_r = X_r L[r, r-1] (dataflow kernel: the chain's one mat-vec per block row)
+  double *M1;     // [nb][2][kXBlock] M1_r = X_r L[r, r-1], M2_r = X_r L[r, r-2] (dataflow kernel: the chain's one mat-vec
+                  // per block row on its critical path, dataflow_chain_v7.cuh)
   double *w;      // [n_pad]  forward-substitution residual, initialised to v
   double *p;      // [n_pad]  p = L^{-1} v
   double *c;      // [n_pad]  c_k (sign folded)
@@ -68,7 +73,9 @@ inline size_t large_ws_doubles(int64_t n) {
   int64_t nb = n_pad / 32;
   // (+ 2 * kWsPadMax: room for the two tuning pads of large_ws_carve)
   return (size_t)(nb * kXBlock + 7 * n_pad + 8 + 2 * kWsPadMax
-#ifdef CHUB_CHAIN_V4
+#if CHUB_CHAIN_V7
+                  + 2 * nb * kXBlock
+#elif defined(CHUB_CHAIN_V4)
                   + nb * kXBlock
 #endif
   );
@@ -92,7 +99,9 @@ inline LargeWs large_ws_carve(void *base, int64_t n) {
   ws.dg = d; d += n_pad;
   ws.scal = d; d += 8;
   d += 2 * kWsPadMax - pad_w - pad_p;  // (the flags keep their place whatever the pads)
-#ifdef CHUB_CHAIN_V4
+#if CHUB_CHAIN_V7
+  ws.M1 = d; d += 2 * nb * kXBlock;  // [nb][M1 | M2]
+#elif defined(CHUB_CHAIN_V4)
   ws.M1 = d; d += nb * kXBlock;
 #else
   ws.M1 = nullptr;
@@ -172,28 +181,36 @@ __device__ __forceinline__ void invdiag_block_smem(const T *L, int n, int64_t ld
   }
 #pragma unroll
   for (int i = 0; i < kPanel; ++i) X[i * kXStride + j] = x[i];
-#ifdef CHUB_CHAIN_V4  // (only the experimental chain of dataflow_chain_v4.cuh uses M1; compiled out of the library:
-                      //  the dead code alone made the pre-pass measurably slower)
+#if defined(CHUB_CHAIN_V4) || CHUB_CHAIN_V7  // (chains that do not use M1: compiled out, the dead code alone made the
+                                             //  pre-pass measurably slower)
   if (M1 == nullptr) return;
-  // M1[i][c] = sum_{k <= i} X[i][k] Lt[k][c],  Lt = L[blk, blk-1];  lane = column c.  X goes through the
+  // M_q[i][c] = sum_{k <= i} X[i][k] Lt[k][c],  Lt = L[blk, blk-q], q = 1, 2;  lane = column c.  X goes through the
   // staging area (its L_D copy is no longer needed), Lt[.][c] sits in registers.
   __syncwarp();
 #pragma unroll
   for (int i = 0; i < kPanel; ++i) Lw[i][j] = x[i];
-  double lt[kPanel];
-#pragma unroll
-  for (int k = 0; k < kPanel; ++k)
-    lt[k] = (blk > 0 && c0 + k < n) ? (double)L[idx<LAYOUT>(c0 + k, c0 - kPanel + lane, ld)] : 0.0;
   __syncwarp();
+#if CHUB_CHAIN_V7
+  constexpr int NQ = 2;
+#else
+  constexpr int NQ = 1;
+#endif
+  for (int q = 1; q <= NQ; ++q) {
+    double lt[kPanel];
 #pragma unroll
-  for (int i = 0; i < kPanel; ++i) {
-    double a0 = 0.0, a1 = 0.0;
+    for (int k = 0; k < kPanel; ++k)
+      lt[k] = (blk >= q && c0 + k < n) ? (double)L[idx<LAYOUT>(c0 + k, c0 - q * kPanel + lane, ld)] : 0.0;
+    double *Mq = M1 + (q - 1) * kXBlock;
 #pragma unroll
-    for (int k = 0; k < kPanel; k += 2) {
-      if (k <= i) a0 = fma(Lw[i][k], lt[k], a0);
-      if (k + 1 <= i) a1 = fma(Lw[i][k + 1], lt[k + 1], a1);
+    for (int i = 0; i < kPanel; ++i) {
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < kPanel; k += 2) {
+        if (k <= i) a0 = fma(Lw[i][k], lt[k], a0);
+        if (k + 1 <= i) a1 = fma(Lw[i][k + 1], lt[k + 1], a1);
+      }
+      Mq[i * kXStride + lane] = a0 + a1;
     }
-    M1[i * kXStride + lane] = a0 + a1;
   }
 #else
   (void)M1;
@@ -202,7 +219,7 @@ __device__ __forceinline__ void invdiag_block_smem(const T *L, int n, int64_t ld
 template <typename T, int LAYOUT>
 __device__ __forceinline__ void invdiag_block(const T *L, int n, int64_t ld, LargeWs ws, int blk, bool with_m1 = false) {
   invdiag_block_to<T, LAYOUT>(L, n, ld, ws.X + (int64_t)blk * kXBlock, blk,
-                              with_m1 ? ws.M1 + (int64_t)blk * kXBlock : nullptr);
+                              with_m1 ? ws.M1 + (int64_t)blk * (CHUB_CHAIN_V7 ? 2 : 1) * kXBlock : nullptr);
 }
 
 template <typename T, int LAYOUT>
