@@ -232,7 +232,22 @@ int run_host_update_streamed(HostCache &c, const T *Lh, int64_t ld, T *Lo, int64
   // below the PCIe rate; beyond 512 columns the coarser pipeline costs more than it gains (CHUB_HOST_XFER_COLS overrides).
   int64_t xfer = kXferCols;
   if (const char *e = getenv("CHUB_HOST_XFER_COLS")) xfer = std::max<int64_t>(kBig, atoll(e) / kBig * kBig);
-  const int nP = (int)((n + xfer - 1) / xfer);
+  // Panel boundaries.  The first panels are the tallest and nothing overlaps the first one's H2D (nor the
+  // kernels that wait for it); CHUB_HOST_XFER_LEAD = number of narrow (256-column) lead panels before the
+  // pipeline widens to `xfer`.  Measured at n = 16384 (gpurun r04x): 0 / 1 / 2 / 4 / 8 lead panels give
+  // 25.7 / 25.3 / 26.0 / 26.0 / 25.6 ms -- the PCIe rate (~42 GB/s each way), not the fill, bounds the call.
+  std::vector<int64_t> pj0;
+  {
+    int lead = 0;
+    if (const char *e = getenv("CHUB_HOST_XFER_LEAD")) lead = std::max(0, atoi(e));
+    int64_t j = 0;
+    while (j < n) {
+      pj0.push_back(j);
+      j += ((int)pj0.size() <= lead) ? kBig : xfer;
+    }
+    pj0.push_back(n);
+  }
+  const int nP = (int)pj0.size() - 1;
   while ((int)c.ev_in.size() < nP + 1) {
     cudaEvent_t a, b;
     HCK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -266,8 +281,8 @@ int run_host_update_streamed(HostCache &c, const T *Lh, int64_t ld, T *Lo, int64
   HCK(cudaMemcpyAsync(vd, vh, (size_t)n * es, cudaMemcpyHostToDevice, c.st));
   large_prepare_kernel<T, LAYOUT><<<(ni + 255) / 256, 256, 0, c.st>>>(Ld, ni, ldd, vd, ws, 0, c.status);
   for (int P = 0; P < nP; ++P) {
-    const int64_t j0 = (int64_t)P * xfer;
-    const int64_t bw = std::min<int64_t>(xfer, n - j0);
+    const int64_t j0 = pj0[P];
+    const int64_t bw = std::min<int64_t>(pj0[P + 1], n) - j0;
     // rectangle rows [j0, n) x columns [j0, j0 + bw)
     size_t off_d, off_h, off_o, width, height;
     if (LAYOUT == CHUB_ROW_MAJOR) {
