@@ -73,7 +73,10 @@ int chub_device_info(int *sm_count, int64_t *l2_bytes, int *cc_major, int *cc_mi
 
 /* Bytes of device workspace the device-pointer entry points need for a factor of
  * order n (per call, independent of batch).  Pass a buffer of at least this size,
- * or workspace == NULL to let the library use an internal per-device buffer. */
+ * or workspace == NULL to let the library use an internal per-device buffer.
+ * The internal buffer is ONE per device: calls that rely on it must be issued on a
+ * single stream (or serialised by the caller); concurrent streams / threads each pass
+ * their own workspace (the Python front-end keeps one per (device, stream)). */
 size_t chub_workspace_bytes(int dtype, int64_t n);
 
 /* ---- device-pointer entry points: L, v, workspace, status are DEVICE pointers;
