@@ -447,7 +447,8 @@ int rcw_apply(void *A, int64_t m_loc, int64_t n, int64_t ld, int G, int rank, in
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       }
-      auto kern = rcw_bulk_tma_kernel<T>;
+      const char *bt = getenv("CHUB_RCW_BULK_TMA");
+      auto kern = (bt && bt[0] == '1') ? rcw_bulk_tma_kernel<T> : rcw_bulk_tma2_kernel<T>;  // 1: per-item pipeline (A/B)
       const size_t smem = rect_apply_rm_smem<T>();
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const int ntasks = Jhi - Jlo + 1;
