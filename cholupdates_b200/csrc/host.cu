@@ -649,7 +649,13 @@ int run_host(dev_fn fn, bool is_update, size_t es, const void *L, int64_t ld, vo
   if (hp && !strcmp(hp, "streamed")) streamed = is_update && n >= kStreamMinN;
   if (hp && (!strcmp(hp, "staged") || !strcmp(hp, "direct"))) streamed = false;
   if (getenv("CHUB_HOST_NO_STREAM")) streamed = false;
-  if (!streamed && !(hp && !strcmp(hp, "direct")))
+  // (the staged path holds the packed triangle in pinned memory: beyond CHUB_HOST_STAGE_MAX_MB, default 6 GB
+  // = n ~ 38000 in fp64, pageable callers go back to the streamed bounce ring (updates) or plain 2-D copies)
+  size_t stage_max = (size_t)6144 << 20;
+  if (const char *e = getenv("CHUB_HOST_STAGE_MAX_MB")) stage_max = (size_t)std::max(0LL, atoll(e)) << 20;
+  const bool stage_fits = (size_t)n * (size_t)(n + 1) / 2 * es <= stage_max || (is_pinned(L) && is_pinned(Lo));
+  if (!stage_fits && !streamed && is_update && n >= kStreamMinN && !getenv("CHUB_HOST_NO_STREAM")) streamed = true;
+  if (!streamed && stage_fits && !(hp && !strcmp(hp, "direct")))
     return run_host_staged(c, fn, es, L, ld, Lo, ldo, n, layout, v, flags, status);
   if (streamed) {
     if (es == 8)

@@ -744,3 +744,55 @@ def test_persistent_kernel_switches(n, env, monkeypatch):
     rank_1.downdate(Ld, vdt, overwrite_L=True, overwrite_v=True)
     assert rel_fro(Ld.cpu().numpy(), L_dd) <= tol_for(np.float64, n)
     assert rel_vec(vdt.cpu().numpy(), vd_ref) <= tol_for(np.float64, n)
+
+
+# ------------------------------------------------- every host path (NumPy in / NumPy out) stays correct
+@pytest.mark.parametrize(
+    "env",
+    [
+        {},  # staged (default for pageable arrays)
+        {"CHUB_HOST_PATH": "streamed"},  # streamed panels + pinned bounce ring (updates)
+        {"CHUB_HOST_PATH": "direct"},  # plain 2-D copies
+        {"CHUB_HOST_STAGE_MAX_MB": "1"},  # staging buffer too small: streamed (update) / direct (downdate)
+        {"CHUB_HOST_BLOCKS": "1"},  # staged, a single block
+        {"CHUB_HOST_BLOCKS": "97"},  # staged, many ragged blocks
+    ],
+)
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_host_paths(env, order, monkeypatch):
+    """Pageable NumPy arrays through each host path: lower triangle vs the oracle, junk above the diagonal
+    untouched, copy mode returns a fresh array of the same order, the not-positive-definite downdate leaves L
+    as it was and v <- p."""
+    for k, val in env.items():
+        monkeypatch.setenv(k, val)
+    n = 3000
+    base = synth_factor(n, 91)
+    junk = np.triu(np.random.default_rng(92).standard_normal((n, n)), 1)
+    L = np.array(base + junk, order=order)
+    v = np.random.default_rng(93).standard_normal(n)
+    L_ref, v_ref = _oracle("update", base, v)
+    out = rank_1.update(L, v.copy(), check_diag=False)  # copy mode
+    assert out is not L and out.flags.f_contiguous == L.flags.f_contiguous
+    assert np.array_equal(np.triu(out, 1), junk) and np.array_equal(np.triu(L, 1), junk)
+    assert rel_fro(np.tril(out), L_ref) <= tol_for(np.float64, n)
+    vv = v.copy()
+    rank_1.update(L, vv, check_diag=True, overwrite_L=True, overwrite_v=True)  # in place
+    assert np.array_equal(np.triu(L, 1), junk)
+    assert rel_fro(np.tril(L), L_ref) <= tol_for(np.float64, n)
+    assert rel_vec(vv, v_ref) <= tol_for(np.float64, n)
+    vd = downdate_vector(np.tril(L_ref), 94)
+    L_dd, vd_ref = _oracle("downdate", np.tril(L_ref), vd)
+    vdd = vd.copy()
+    rank_1.downdate(L, vdd, overwrite_L=True, overwrite_v=True)
+    assert np.array_equal(np.triu(L, 1), junk)
+    assert rel_fro(np.tril(L), L_dd) <= tol_for(np.float64, n) * 2
+    assert rel_vec(vdd, vd_ref) <= tol_for(np.float64, n) * 2
+    # ||L^{-1} v|| = 1.2: LinAlgError, L bit-unchanged, v <- p
+    before = L.copy(order="K")
+    p = np.random.default_rng(95).standard_normal(n)
+    p *= 1.2 / np.linalg.norm(p)
+    vbad = np.tril(L) @ p
+    with pytest.raises(np.linalg.LinAlgError):
+        rank_1.downdate(L, vbad, overwrite_L=True, overwrite_v=True)
+    assert np.array_equal(L, before)
+    assert rel_vec(vbad, p) <= 1e-9
