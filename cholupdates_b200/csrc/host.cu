@@ -131,16 +131,122 @@ int host_threads() {
   return n;
 }
 
-// rows [0, height) of `width` bytes: strided (pitch) <-> packed, split over host threads
+// One row of a block, with non-temporal stores: the destination (staging buffer on the way in, the caller's array
+// on the way out) is not read again by this core, and a regular store would first read the line it overwrites
+// (3 bytes of memory traffic per byte copied instead of 2 -- host memory bandwidth is what bounds pageable callers).
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void copy_stream_avx2(char *dst, const char *src, size_t bytes) {
+  size_t head = (32 - (reinterpret_cast<uintptr_t>(dst) & 31)) & 31;
+  if (head > bytes) head = bytes;
+  if (head) { memcpy(dst, src, head); dst += head; src += head; bytes -= head; }
+  size_t i = 0;
+  for (; i + 128 <= bytes; i += 128) {
+    const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
+    const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 32));
+    const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 64));
+    const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 96));
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), a);
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 32), b);
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 64), c);
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 96), d);
+  }
+  for (; i + 32 <= bytes; i += 32)
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i)));
+  if (i < bytes) memcpy(dst + i, src + i, bytes - i);
+  _mm_sfence();
+}
+#endif
+void copy_stream(char *dst, const char *src, size_t bytes) {
+#if defined(__x86_64__)
+  static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("CHUB_HOST_NO_NT");
+  if (avx2 && bytes >= 256) { copy_stream_avx2(dst, src, bytes); return; }
+#endif
+  memcpy(dst, src, bytes);
+}
+
+// ---- persistent host thread pool (staged path).  Spawning threads per call costs more than a whole n = 1000
+// update; the workers spin for a short while after their last task (a caller updating in a loop finds them hot)
+// and then sleep on a condition variable.
+class HostPool {
+ public:
+  static HostPool &get() {
+    static HostPool *p = new HostPool(host_threads());  // (leaked on purpose: no destructor race at process exit)
+    return *p;
+  }
+  void submit(std::function<void()> f) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      q_.push_back(std::move(f));
+      pending_.fetch_add(1, std::memory_order_release);
+    }
+    if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_one();
+  }
+  int size() const { return (int)th_.size(); }
+
+ private:
+  explicit HostPool(int n) {
+    for (int t = 0; t < n; ++t) th_.emplace_back([this] { run(); });
+    for (auto &x : th_) x.detach();
+  }
+  void run() {
+    for (;;) {
+      std::function<void()> f;
+      if (pending_.load(std::memory_order_acquire) > 0) {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!q_.empty()) {
+          f = std::move(q_.front());
+          q_.pop_front();
+          pending_.fetch_sub(1, std::memory_order_relaxed);
+        }
+      }
+      if (f) { f(); continue; }
+      // nothing to do: spin ~200 us, then sleep
+      const auto t0 = std::chrono::steady_clock::now();
+      bool got = false;
+      while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(200)) {
+        if (pending_.load(std::memory_order_acquire) > 0) { got = true; break; }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+      if (got) continue;
+      std::unique_lock<std::mutex> lk(mu_);
+      sleepers_.fetch_add(1, std::memory_order_release);
+      cv_.wait(lk, [this] { return !q_.empty(); });
+      sleepers_.fetch_sub(1, std::memory_order_release);
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::function<void()>> q_;
+  std::atomic<int> pending_{0}, sleepers_{0};
+  std::vector<std::thread> th_;
+};
+
+// rows [0, height) of `width` bytes: strided (pitch) <-> packed, split over the host thread pool (non-temporal
+// stores: the destination is not read again by this core)
 void copy_rows_parallel(char *dst, size_t dpitch, const char *src, size_t spitch, size_t width, size_t height) {
-  const int nt = (int)std::min<size_t>(host_threads(), std::max<size_t>(1, height * width / (1 << 20)));
+  HostPool &pool = HostPool::get();
+  const int nt = (int)std::min<size_t>((size_t)pool.size() + 1, std::max<size_t>(1, height * width / (1 << 20)));
   auto work = [=](size_t r0, size_t r1) {
-    for (size_t r = r0; r < r1; ++r) memcpy(dst + r * dpitch, src + r * spitch, width);
+    for (size_t r = r0; r < r1; ++r) copy_stream(dst + r * dpitch, src + r * spitch, width);
   };
   if (nt <= 1) { work(0, height); return; }
-  std::vector<std::thread> th;
-  for (int t = 0; t < nt; ++t) th.emplace_back(work, height * t / nt, height * (t + 1) / nt);
-  for (auto &x : th) x.join();
+  std::atomic<int> left{nt - 1};
+  std::atomic<int> *lp = &left;
+  for (int t = 1; t < nt; ++t) {
+    const size_t r0 = height * t / nt, r1 = height * (t + 1) / nt;
+    pool.submit([=] {
+      work(r0, r1);
+      lp->fetch_sub(1, std::memory_order_release);
+    });
+  }
+  work(0, height / nt);
+  while (left.load(std::memory_order_acquire) > 0) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
 }
 
 int ensure_bounce(HostCache &c, size_t bytes) {
@@ -210,6 +316,8 @@ struct Unpacker {
 // touches its own 256 columns (plus the n-vector w), so a panel can be finished and shipped back as
 // soon as it has arrived; PCIe runs full duplex and the update costs about one H2D of the triangle.
 constexpr int64_t kStreamMinN = 2048;
+constexpr int64_t kStreamPageableMinN = 12288;  // pageable caller memory: the streamed bounce ring from here on (n = 16384:
+                                               // 49-57 ms against 63-65 ms staged; n = 5000: staged 6.6-7.3 against 10-11 ms)
 constexpr int64_t kStreamPinnedMinN = 4096;  // pinned caller memory: streamed from here on (else staged)
 constexpr int64_t kXferCols = 512;  // columns per host <-> device transfer panel (measured: 256 24.7 ms, 512 24.0, 1024 27.7 at n = 16384)
 
@@ -338,98 +446,6 @@ int run_host_update_streamed(HostCache &c, const T *Lh, int64_t ld, T *Lo, int64
 }
 
 typedef int (*dev_fn)(void *, int64_t, int64_t, int, void *, int, void *, size_t, int32_t *, void *);
-
-// One row of a block, with non-temporal stores: the destination (staging buffer on the way in, the caller's array
-// on the way out) is not read again by this core, and a regular store would first read the line it overwrites
-// (3 bytes of memory traffic per byte copied instead of 2 -- host memory bandwidth is what bounds pageable callers).
-#if defined(__x86_64__)
-__attribute__((target("avx2"))) void copy_stream_avx2(char *dst, const char *src, size_t bytes) {
-  size_t head = (32 - (reinterpret_cast<uintptr_t>(dst) & 31)) & 31;
-  if (head > bytes) head = bytes;
-  if (head) { memcpy(dst, src, head); dst += head; src += head; bytes -= head; }
-  size_t i = 0;
-  for (; i + 128 <= bytes; i += 128) {
-    const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
-    const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 32));
-    const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 64));
-    const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 96));
-    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), a);
-    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 32), b);
-    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 64), c);
-    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 96), d);
-  }
-  for (; i + 32 <= bytes; i += 32)
-    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i)));
-  if (i < bytes) memcpy(dst + i, src + i, bytes - i);
-  _mm_sfence();
-}
-#endif
-void copy_stream(char *dst, const char *src, size_t bytes) {
-#if defined(__x86_64__)
-  static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("CHUB_HOST_NO_NT");
-  if (avx2 && bytes >= 256) { copy_stream_avx2(dst, src, bytes); return; }
-#endif
-  memcpy(dst, src, bytes);
-}
-
-// ---- persistent host thread pool (staged path).  Spawning threads per call costs more than a whole n = 1000
-// update; the workers spin for a short while after their last task (a caller updating in a loop finds them hot)
-// and then sleep on a condition variable.
-class HostPool {
- public:
-  static HostPool &get() {
-    static HostPool *p = new HostPool(host_threads());  // (leaked on purpose: no destructor race at process exit)
-    return *p;
-  }
-  void submit(std::function<void()> f) {
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      q_.push_back(std::move(f));
-      pending_.fetch_add(1, std::memory_order_release);
-    }
-    if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_one();
-  }
-  int size() const { return (int)th_.size(); }
-
- private:
-  explicit HostPool(int n) {
-    for (int t = 0; t < n; ++t) th_.emplace_back([this] { run(); });
-    for (auto &x : th_) x.detach();
-  }
-  void run() {
-    for (;;) {
-      std::function<void()> f;
-      if (pending_.load(std::memory_order_acquire) > 0) {
-        std::lock_guard<std::mutex> lk(mu_);
-        if (!q_.empty()) {
-          f = std::move(q_.front());
-          q_.pop_front();
-          pending_.fetch_sub(1, std::memory_order_relaxed);
-        }
-      }
-      if (f) { f(); continue; }
-      // nothing to do: spin ~200 us, then sleep
-      const auto t0 = std::chrono::steady_clock::now();
-      bool got = false;
-      while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(200)) {
-        if (pending_.load(std::memory_order_acquire) > 0) { got = true; break; }
-#if defined(__x86_64__)
-        __builtin_ia32_pause();
-#endif
-      }
-      if (got) continue;
-      std::unique_lock<std::mutex> lk(mu_);
-      sleepers_.fetch_add(1, std::memory_order_release);
-      cv_.wait(lk, [this] { return !q_.empty(); });
-      sleepers_.fetch_sub(1, std::memory_order_release);
-    }
-  }
-  std::mutex mu_;
-  std::condition_variable cv_;
-  std::deque<std::function<void()>> q_;
-  std::atomic<int> pending_{0}, sleepers_{0};
-  std::vector<std::thread> th_;
-};
 
 // ---- staged path: any operation, any size, pageable or pinned caller memory.
 // The lower triangle is cut into K blocks of about equal area (row blocks that end at the diagonal for row-major,
@@ -645,7 +661,7 @@ int run_host(dev_fn fn, bool is_update, size_t es, const void *L, int64_t ld, vo
   // runs the launch-per-panel kernels and wants pinned memory; the staged path takes anything and uses the
   // persistent kernels.  CHUB_HOST_PATH = streamed | staged | direct overrides (direct: plain 2-D copies, A/B).
   const char *hp = getenv("CHUB_HOST_PATH");
-  bool streamed = is_update && n >= kStreamPinnedMinN && is_pinned(L) && is_pinned(Lo);
+  bool streamed = is_update && ((n >= kStreamPinnedMinN && is_pinned(L) && is_pinned(Lo)) || n >= kStreamPageableMinN);
   if (hp && !strcmp(hp, "streamed")) streamed = is_update && n >= kStreamMinN;
   if (hp && (!strcmp(hp, "staged") || !strcmp(hp, "direct"))) streamed = false;
   if (getenv("CHUB_HOST_NO_STREAM")) streamed = false;
