@@ -1,5 +1,6 @@
 """End-to-end rank_1.update on pinned NumPy arrays for several lead-panel counts / panel widths of the streamed
-path (env CHUB_HOST_XFER_LEAD, CHUB_HOST_XFER_COLS), with a parity check of the leading block against the oracle."""
+path (env CHUB_HOST_XFER_LEAD, CHUB_HOST_XFER_COLS); the leading block is checked against the device-resident path
+(CUDA tensors through the same front-end; that path is what tests/ holds against the oracle)."""
 import os
 import sys
 import time
@@ -9,9 +10,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 from cholupdates_b200 import rank_1  # noqa: E402
-import seeger_oracle as oracle  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 m = 2048
@@ -27,15 +26,16 @@ for lead, cols in ((0, 512), (1, 512), (2, 512), (4, 512), (2, 768), (4, 1024), 
     os.environ["CHUB_HOST_XFER_LEAD"] = str(lead)
     os.environ["CHUB_HOST_XFER_COLS"] = str(cols)
     Lh[...] = L0
-    ref = np.array(L0[:m, :m], order="F")
+    ref = torch.from_numpy(np.ascontiguousarray(L0[:m, :m])).cuda()
     ts = []
     for i in range(6):
         vh[:] = vs[i]
         t0 = time.perf_counter()
         rank_1.update(Lh, vh, check_diag=False, overwrite_L=True, overwrite_v=True)
         ts.append(time.perf_counter() - t0)
-        oracle.update(ref, vs[i, :m].copy())
-    err = np.linalg.norm(np.tril(Lh[:m, :m]) - np.tril(ref)) / np.linalg.norm(np.tril(ref))
+        rank_1.update(ref, torch.from_numpy(vs[i, :m].copy()).cuda(), check_diag=False, overwrite_L=True, overwrite_v=True)
+    refh = ref.cpu().numpy()
+    err = np.linalg.norm(np.tril(Lh[:m, :m]) - np.tril(refh)) / np.linalg.norm(np.tril(refh))
     t = min(ts[1:])
     print(f"lead {lead} cols {cols:4d}: best {1e3 * t:6.2f} ms  median {1e3 * float(np.median(ts[1:])):6.2f} ms "
           f"({tri / t / 1e9:5.1f} GB/s each way)  parity {err:.1e}", flush=True)
