@@ -163,3 +163,25 @@ def test_update_and_downdate_n32768_properties(order):
         getattr(oracle, op)(lead, v_lead)
         assert rel_fro(L[:m, :m].cpu().numpy(), lead) <= tol_for(np.float64, n), op
         assert np.linalg.norm(v_in[:m].cpu().numpy() - v_lead) <= tol_for(np.float64, n) * np.linalg.norm(v_lead), op
+
+
+@pytest.mark.parametrize("blocked", [False, True])
+def test_column_major_fp32_n20000(blocked, monkeypatch):
+    """fp32, column-major, n = 20000: the two-warps-per-block-row workers (Q = 5) and, with the knob, the blocked
+    driver (two diagonal blocks + rect_apply_cm_kernel<float>), update and downdate against the fp32 oracle."""
+    if blocked:
+        monkeypatch.setenv("CHUB_CM_NATIVE_MAX_N", "16384")
+    n = 20000
+    L = synth_factor(n, 25, np.float32)
+    v = np.random.default_rng(26).standard_normal(n).astype(np.float32)
+    L_ref, v_ref = np.array(L, order="F"), v.copy()
+    oracle.update(L_ref, v_ref)
+    Lt = _to_cuda(L, "F")
+    vt = torch.from_numpy(v.copy()).cuda()
+    rank_1.update(Lt, vt, check_diag=False, overwrite_L=True, overwrite_v=True)
+    assert rel_fro(Lt.cpu().numpy(), L_ref) <= tol_for(np.float32, n)
+    vd = downdate_vector(np.tril(L_ref), 27)
+    L_dd = np.array(L_ref, order="F")
+    oracle.downdate(L_dd, vd.copy())
+    rank_1.downdate(Lt, torch.from_numpy(vd.copy()).cuda(), check_diag=True, overwrite_L=True, overwrite_v=True)
+    assert rel_fro(Lt.cpu().numpy(), L_dd) <= tol_for(np.float32, n) * 30
