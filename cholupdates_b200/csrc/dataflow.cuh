@@ -3136,7 +3136,8 @@ int launch_dataflow(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs 
   ++*launches;
   if (!UPDATE && !chain_only) {
     if (getenv("CHUB_DD_COEF_V1")) large_dd_coef_kernel<T, LAYOUT><<<1, 1024, 0, st>>>(L, ni, ld, v, ws, status);
-    else dd_coef_par_kernel<T><<<1, 1024, 0, st>>>(ni, v, ws, status);  // (ws.dg: the pre-pass's copy of the diagonal)
+    else if (getenv("CHUB_DD_COEF_V2")) dd_coef_par_kernel<T><<<1, 1024, 0, st>>>(ni, v, ws, status);  // (one CTA, A/B)
+    else dd_coef_par2_kernel<T><<<(ni + 1023) / 1024, 1024, 0, st>>>(ni, v, ws, status);  // (ws.dg: the pre-pass's copy of the diagonal)
     ++*launches;
     if (rp.ok && !getenv("CHUB_DD_SWEEP_V1") && !getenv("CHUB_DD_SWEEP_V2")) {
       auto sk = dd_sweep_rm2_kernel<T>;
@@ -3242,7 +3243,8 @@ int launch_blocked(T *L, int64_t n, int64_t ld, T *v, int flags, const LargeWs &
   if (!UPDATE) {
     const int nb = (ni + 31) / 32;
     if (getenv("CHUB_DD_COEF_V1")) large_dd_coef_kernel<T, LAYOUT><<<1, 1024, 0, st>>>(L, ni, ld, v, ws, status);
-    else dd_coef_par_kernel<T><<<1, 1024, 0, st>>>(ni, v, ws, status);
+    else if (getenv("CHUB_DD_COEF_V2")) dd_coef_par_kernel<T><<<1, 1024, 0, st>>>(ni, v, ws, status);
+    else dd_coef_par2_kernel<T><<<(ni + 1023) / 1024, 1024, 0, st>>>(ni, v, ws, status);
     ++*launches;
     if (RM) {
       alignas(64) CUtensorMap tmap3;

@@ -572,6 +572,94 @@ __global__ void __launch_bounds__(1024) dd_coef_par_kernel(int n, T *v, LargeWs 
   }
 }
 
+// The same on one CTA per 1024 columns: every CTA forms p . p (the rho^2 test: the same reduction order in every
+// CTA, so all of them take the same decision) and the sum over the columns behind its own block by itself
+// (n doubles out of L2 per CTA), then scans its block -- no CTA waits for another one.  28 -> ~6 us at n = 16384.
+template <typename T>
+__global__ void __launch_bounds__(1024) dd_coef_par2_kernel(int n, T *v, LargeWs ws, int32_t *status) {
+  constexpr int NT = 1024;
+  __shared__ double wsum[NT / 32];
+  __shared__ double wsum2[NT / 32];
+  __shared__ double wabove[NT / 32];
+  __shared__ double total_s, behind_s;
+  // (NOT_PD can only come from a sibling CTA of this launch: a CTA that starts late still has to take the same
+  // branch and write its part of v <- p; every other status means that an earlier kernel gave up)
+  const int32_t st0 = *status;
+  if (st0 != 0 && st0 != CHUB_STATUS_NOT_PD) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = (int)blockIdx.x;
+  const int k_end = (c + 1) * NT;  // columns >= k_end are behind my block
+  double acc = 0.0, acc2 = 0.0;
+  for (int i = tid; i < n; i += NT) {
+    const double x = ws.p[i];
+    acc = fma(x, x, acc);
+    if (i >= k_end) acc2 = fma(x, x, acc2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_down_sync(0xffffffffu, acc, o);
+    acc2 += __shfl_down_sync(0xffffffffu, acc2, o);
+  }
+  if (lane == 0) { wsum[warp] = acc; wsum2[warp] = acc2; }
+  __syncthreads();
+  if (warp == 0) {
+    double t = wsum[lane], t2 = wsum2[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      t += __shfl_down_sync(0xffffffffu, t, o);
+      t2 += __shfl_down_sync(0xffffffffu, t2, o);
+    }
+    if (lane == 0) { total_s = t; behind_s = t2; }
+  }
+  __syncthreads();
+  const double p_dot_p = total_s;
+  const T rho_sq_t = T(1) - T(p_dot_p);
+  const int k = c * NT + tid;
+  if (c == 0 && tid == 0) { ws.scal[2] = p_dot_p; ws.scal[3] = (double)rho_sq_t; }
+  if (rho_sq_t <= T(0)) {  // not positive definite: v <- p, L stays as it is (the sweep sees the status)
+    if (k < n) v[k] = (T)ws.p[k];
+    if (tid == 0) *status = CHUB_STATUS_NOT_PD;  // (every CTA writes the same value)
+    return;
+  }
+  const double rho_sq = (double)rho_sq_t;
+  const double pk = k < n ? ws.p[k] : 0.0, dgk = k < n ? ws.dg[k] : 1.0;
+  const double x = pk * pk;
+  double suf = x;  // inclusive suffix sum within the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double y = __shfl_down_sync(0xffffffffu, suf, o);
+    if (lane + o < 32) suf += y;
+  }
+  __syncthreads();
+  if (lane == 0) wsum[warp] = suf;
+  __syncthreads();
+  if (warp == 0) {
+    const double t = wsum[lane];
+    double s2 = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double y = __shfl_down_sync(0xffffffffu, s2, o);
+      if (lane + o < 32) s2 += y;
+    }
+    wabove[lane] = s2 - t;  // warps strictly above
+  }
+  __syncthreads();
+  const double after = behind_s + wabove[warp] + (suf - x);  // sum_{j > k} p_j^2
+  if (k < n) {
+    const double qk1 = sqrt(rho_sq + after);
+    const double qk = sqrt(rho_sq + (after + x));
+    const double cc = qk1 / qk, ss = pk / qk;
+    const double sgn = dgk < 0.0 ? -1.0 : 1.0;
+    ws.c[k] = cc;
+    ws.sg[k] = ss;
+    ws.dn[k] = sgn;
+    double2 *pk4 = reinterpret_cast<double2 *>(ws.X) + 2 * (size_t)k;  // packed (c, s, sgn c, sgn s), see above
+    pk4[0] = make_double2(cc, ss);
+    pk4[1] = make_double2(sgn * cc, sgn * ss);
+    v[k] = rotg_z<T>(T(qk1), T(pk), T(cc), T(ss));
+  }
+}
+
 template <typename T, int LAYOUT>
 __global__ void __launch_bounds__(1024) large_dd_coef_kernel(const T *L, int n, int64_t ld, T *v,
                                                              LargeWs ws, int32_t *status) {
